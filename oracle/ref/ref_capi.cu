@@ -141,6 +141,11 @@ void ref_hpr_destroy(void* p)
 	delete r->c;
 	delete r->io;
 	delete r;
+	/* ~IOGPU calls cudaFree on cudaHostAlloc memory (io.h:72-76) and
+	 * ~MedianFilterGPU calls nppsFree on nppiMalloc memory (mfilt.h:218-225);
+	 * the error they leave behind would make the next object's first thrust
+	 * kernel throw ("invalid device ordinal", observed on the B200 box). */
+	clear_stale_error("HPR/IOGPU destructors");
 }
 
 void ref_hpr_use_sse(void* p)
@@ -243,6 +248,7 @@ int ref_fakert_latency(int backend, float fs, int hop, float beta, int nocopybor
 	catch (const zen::ZgException&) {
 		return -1;
 	}
+	clear_stale_error("HPRRealtime/IOGPU destructors");
 	return 0;
 }
 
@@ -257,6 +263,7 @@ double ref_offline_process(int backend, float fs, int hop_h, int hop_p, float be
 		std::vector<float> in(audio, audio + n);
 		std::array<std::vector<float>, 3> res;
 		double ms;
+		clear_stale_error("before HPRIOffline");
 		if (backend == 0) {
 			auto hpss = zen::hps::HPRIOffline<Backend::GPU>(fs, hop_h, hop_p, beta_h, beta_p, nocopybord != 0);
 			if (flags & 1) hpss.use_sse_filter();
@@ -278,6 +285,7 @@ double ref_offline_process(int backend, float fs, int hop_h, int hop_p, float be
 		std::memcpy(h_out, res[0].data(), n * sizeof(float));
 		std::memcpy(p_out, res[1].data(), n * sizeof(float));
 		std::memcpy(r_out, res[2].data(), n * sizeof(float));
+		clear_stale_error("HPRIOffline destructors");
 		return ms;
 	}
 	catch (const zen::ZgException&) {
