@@ -1,0 +1,166 @@
+/* zen_b200 — C ABI of the B200-native HPR hot path (libzen_b200.so).
+ *
+ * The reference (sevagh/Zen) has no C ABI: its boundary is the C++ API of
+ * libzen.  The C++ headers under zen_b200/include/
+ * reproduce that API by name and forward to the entry points below; each entry
+ * point cites the reference interface it replaces.  Plain pointers and sizes
+ * only — no thrust / torch types.
+ *
+ * Pointers named d_* must be device-accessible (cudaMalloc memory, or the
+ * device alias of mapped pinned host memory such as zen_io_alloc() hands out,
+ * which is what the reference's callers pass: zen/fakert.h:229-230).
+ * Pointers named h_* are ordinary host memory.
+ *
+ * All functions return ZEN_OK or a negative error code; nothing throws.
+ * ZEN_ERR_GEOMETRY is returned wherever the reference throws zen::ZgException.
+ * There is no CPU fallback: without a usable CUDA device every call that
+ * computes returns ZEN_ERR_CUDA.
+ */
+#ifndef ZEN_B200_H
+#define ZEN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+	ZEN_OK = 0,
+	ZEN_ERR_GEOMETRY = -1, /* zen::ZgException in the reference */
+	ZEN_ERR_CUDA = -2,
+	ZEN_ERR_UNSUPPORTED = -3, /* size outside what the kernels are built for */
+	ZEN_ERR_ARG = -4
+};
+
+/* libzen/mfilt.h:27-31 MedianFilterDirection */
+enum { ZEN_TIME_CAUSAL = 0, ZEN_TIME_ANTICAUSAL = 1, ZEN_FREQUENCY = 2 };
+/* libzen/libzen/hps.h:25-27 */
+enum { ZEN_OUTPUT_HARMONIC = 1, ZEN_OUTPUT_PERCUSSIVE = 2, ZEN_OUTPUT_RESIDUAL = 4 };
+/* libzen/win.h:13-16 */
+enum { ZEN_WIN_SQRT_VON_HANN = 0, ZEN_WIN_VON_HANN = 1 };
+/* option bits for the batched / offline entry points */
+enum { ZEN_OPT_SSE = 1, ZEN_OPT_SOFT_MASK = 2, ZEN_OPT_NOCOPYBORD = 4 };
+
+const char* zen_b200_version(void);
+/* number of usable CUDA devices (0 => every compute call fails with ZEN_ERR_CUDA) */
+int zen_device_count(void);
+
+/* synchronous cudaMemcpy wrappers for hosts without their own CUDA runtime binding */
+int zen_copy_to_host(void* h_dst, const void* d_src, size_t bytes);
+int zen_copy_to_device(void* d_dst, const void* h_src, size_t bytes);
+
+/* ---- derived sizes: HPR<B>::HPR member initialisers, libzen/hps.h:216-285 ---- */
+typedef struct {
+	int hop, nwin, nfft, l_harm, l_perc, lag, stft_width;
+	float cola_factor;
+} zen_geometry;
+int zen_hpr_geometry(float fs, int hop, int causal, zen_geometry* out);
+
+/* ---- Window<T>, libzen/win.h:21-53 (computed on the host, as the reference does) ---- */
+int zen_window(int type, int n, float* h_out);
+
+/* ---- IOGPU, libzen/libzen/io.h:16-81: mapped pinned buffers + device aliases ---- */
+typedef struct {
+	float* host_in;
+	float* host_out;
+	float* device_in;
+	float* device_out;
+	size_t size;
+} zen_io;
+int zen_io_alloc(zen_io* io, size_t size);
+void zen_io_free(zen_io* io);
+
+/* ---- MedianFilterGPU, libzen/mfilt.h:33-268 ----
+ * One filter pass over a time x freq row-major float matrix on the device.
+ * Window / border rules are NPP's as driven by the reference (bit-exact):
+ * copy_bord != 0 -> centred circular window along the filtered axis;
+ * copy_bord == 0 -> shrunken ROI, cells outside it are left untouched.
+ * filter_len is made odd as the reference does; ZEN_ERR_GEOMETRY if it exceeds
+ * the filtered axis (checked before it is made odd). */
+int zen_median_filter(int time, int freq, int filter_len, int direction, int copy_bord,
+                      const float* d_src, float* d_dst, void* cuda_stream);
+/* ---- BoxFilterGPU, libzen/box.h:30-215: wrap-padded moving average ---- */
+int zen_box_filter(int time, int freq, int filter_len, int direction,
+                   const float* d_src, float* d_dst, void* cuda_stream);
+
+/* ---- FFTC2CWrapperGPU, libzen/fftw.h:20-49 ----
+ * In-place 1-D complex-to-complex FFT on interleaved float pairs, unnormalised
+ * in both directions; nfft a power of two in [2, 16384]. */
+int zen_fft_c2c(int nfft, float* d_inout, int inverse, void* cuda_stream);
+
+/* ---- HPR<Backend::GPU>, libzen/hps.h:152-322 + libzen/hps.cu:429-652 ----
+ * Streaming harmonic/percussive/residual separation, one hop per call. */
+typedef struct zen_hpr zen_hpr;
+int zen_hpr_create(zen_hpr** out, float fs, int hop, float beta, unsigned output_flags,
+                   int causality /* ZEN_TIME_CAUSAL | ZEN_TIME_ANTICAUSAL */, int copy_bord);
+void zen_hpr_destroy(zen_hpr* h);
+int zen_hpr_use_sse_filter(zen_hpr* h); /* hps.h:287 */
+int zen_hpr_use_soft_mask(zen_hpr* h);  /* hps.h:289 */
+int zen_hpr_reset_buffers(zen_hpr* h);  /* hps.h:296-321 */
+int zen_hpr_get_geometry(const zen_hpr* h, zen_geometry* out);
+/* HPR<B>::process_next_hop (hps.cu:429-486): consumes hop samples at d_in_hop.
+ * Asynchronous on the object's stream; results are ordered before any later
+ * call on the same object. */
+int zen_hpr_process_next_hop(zen_hpr* h, const float* d_in_hop);
+/* HPRRealtime<GPU>::copy_{harmonic,percussive,residual} (hps.cu:341-363): the
+ * first hop samples of the overlap-add buffer -> d_out_hop, then waits, so the
+ * destination is readable by the host on return (zen/fakert.h:229-234). */
+int zen_hpr_copy_harmonic(zen_hpr* h, float* d_out_hop);
+int zen_hpr_copy_percussive(zen_hpr* h, float* d_out_hop);
+int zen_hpr_copy_residual(zen_hpr* h, float* d_out_hop);
+/* process_next_hop + copy_* in ONE launch: outputs whose pointer is NULL are
+ * skipped.  This is the latency path (zen fakert's timed region). */
+int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* d_out_h, float* d_out_p, float* d_out_r);
+int zen_hpr_synchronize(zen_hpr* h);
+/* Device pointers to the streaming state that the reference exposes as public
+ * members of HPR<GPU> (hps.h:182-197): which = 0 input[nwin], 1 harmonic_out[nwin],
+ * 2 percussive_out[nwin], 3 residual_out[nwin], 4 window[nwin]. */
+float* zen_hpr_state_ptr(zen_hpr* h, int which);
+/* Materialise the reference's full stft_width x nfft debug matrices from the
+ * ring state (s_mag, harmonic_matrix, percussive_matrix, masks, sliding_stft as
+ * interleaved complex), each into caller-provided device memory (NULL = skip).
+ * Not on the per-hop path. */
+int zen_hpr_materialize(zen_hpr* h, float* d_sliding_stft, float* d_s_mag, float* d_harmonic_matrix,
+                        float* d_percussive_matrix, float* d_harmonic_mask, float* d_percussive_mask,
+                        float* d_residual_mask);
+
+/* ---- batched streams: many independent HPRRealtime<GPU> streams at once ----
+ * Equivalent to running, for every stream s, n_hops calls of
+ * process_next_hop(in + s*in_stride + i*hop) on a fresh HPR object and
+ * collecting the first hop samples of each enabled output after every call.
+ * d_in: n_streams rows of n_hops*hop samples (row stride in_stride floats);
+ * d_out_*: same layout (row stride out_stride), NULL for outputs not wanted.
+ * causality ZEN_TIME_CAUSAL reproduces HPRRealtime, ZEN_TIME_ANTICAUSAL the
+ * objects HPRIOffline drives.  options: ZEN_OPT_* bits. */
+typedef struct zen_hpr_batch zen_hpr_batch;
+int zen_hpr_batch_create(zen_hpr_batch** out, float fs, int hop, float beta, unsigned output_flags,
+                         int causality, int options, int max_streams, long max_hops_per_stream);
+void zen_hpr_batch_destroy(zen_hpr_batch* b);
+int zen_hpr_batch_process(zen_hpr_batch* b, const float* d_in, long in_stride, int n_streams, long n_hops,
+                          float* d_out_h, float* d_out_p, float* d_out_r, long out_stride, void* cuda_stream);
+/* same, host buffers (pinned or pageable): streams are cut into chunks that are
+ * copied in, processed and copied out on alternating CUDA streams */
+int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stride, int n_streams, long n_hops,
+                               float* h_out_h, float* h_out_p, float* h_out_r, long out_stride);
+/* number of kernels launched by the last zen_hpr_batch_process* call */
+long zen_hpr_batch_last_launches(const zen_hpr_batch* b);
+/* device time of the fused kernel(s) of the last zen_hpr_batch_process call, ms (CUDA events) */
+float zen_hpr_batch_last_kernel_ms(const zen_hpr_batch* b);
+
+/* ---- HPRIOffline<GPU>::process, libzen/hps.cu:21-221 ----
+ * Two-pass iterative HPR on a whole signal in host memory; returns
+ * {harmonic (pass 1), percussive (pass 2), residual (all zero — the reference's
+ * pass-2 object is built with OUTPUT_PERCUSSIVE only)} each of n samples.
+ * ZEN_ERR_GEOMETRY if hop_h % hop_p != 0 (hps.cu:33-36). */
+int zen_offline_process(float fs, int hop_h, int hop_p, float beta_h, float beta_p, int options,
+                        const float* h_audio, long n, float* h_harmonic, float* h_percussive, float* h_residual);
+/* same with device-resident input/outputs (no PCIe in the call) */
+int zen_offline_process_device(float fs, int hop_h, int hop_p, float beta_h, float beta_p, int options,
+                               const float* d_audio, long n, float* d_harmonic, float* d_percussive,
+                               float* d_residual, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEN_B200_H */

@@ -111,6 +111,7 @@ class OracleHPR:
             raise ValueError("ZgException")
         g = ZoGeom()
         lib().zo_hpr_geom(self._h, ctypes.byref(g))
+        self.beta = beta
         self.hop, self.nwin, self.nfft = g.hop, g.nwin, g.nfft
         self.l_harm, self.l_perc, self.lag, self.stft_width, self.cola = g.l_harm, g.l_perc, g.lag, g.stft_width, g.cola
 

@@ -1,0 +1,387 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and against
+golden vectors captured from the unmodified reference on a B200.
+
+Bars (BASELINE.json north_star): median filter bit-exact; separated audio
+max-abs <= 1e-4 and SNR >= 80 dB on peak-normalised output.
+"""
+import glob
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.golden_inputs import median_case_input
+from tests.util import flip_aware_compare, peak_norm_err
+from zen_b200.synth import synth_audio
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SENT = np.float32(-777.0)
+TOL_ABS, TOL_SNR = 1e-4, 80.0
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def zen():
+    from zen_b200 import hps
+    return hps
+
+
+# ------------------------------------------------------------------ median ---
+
+def _median_cases():
+    d = np.load(os.path.join(GOLD, "npp_median.npz"))
+    keys = sorted(set(re.match(r"(T\d+_F\d+_L\d+_d\d_cb\d)", k).group(1) for k in d.files))
+    return d, keys
+
+
+def test_median_bit_exact_vs_npp(torch, zen):
+    """MedianFilterGPU::filter == nppiFilterMedian_32f_C1R as driven by libzen/mfilt.h, incl. untouched cells."""
+    d, keys = _median_cases()
+    assert len(keys) == 90
+    n_checked = 0
+    for k in keys:
+        T, F, L, dr, cb = map(int, re.match(r"T(\d+)_F(\d+)_L(\d+)_d(\d)_cb(\d)", k).groups())
+        if k + "_zgexception" in d.files:
+            with pytest.raises(zen.ZgException):
+                zen.MedianFilterGPU(T, F, L, dr, bool(cb))
+            continue
+        src = d[k + "_src"] if k + "_src" in d.files else median_case_input(int(d[k + "_seed"]), T, F)
+        s = torch.from_numpy(src).cuda()
+        o = torch.full((T, F), float(SENT), dtype=torch.float32, device="cuda")
+        zen.MedianFilterGPU(T, F, L, dr, bool(cb)).filter(s, o)
+        got = o.cpu().numpy()
+        if k + "_dst" in d.files:
+            assert np.array_equal(got.view(np.uint32), d[k + "_dst"].view(np.uint32)), k
+        else:
+            sha = hashlib.sha256(np.ascontiguousarray(got).tobytes()).digest()
+            assert sha == d[k + "_dstsha"].tobytes(), k
+        n_checked += 1
+    assert n_checked >= 60
+
+
+@pytest.mark.parametrize("T,F,L,dr,cb", [(64, 300, 47, 2, 1), (5, 5000, 187, 2, 1), (5, 5000, 93, 2, 0), (300, 70, 21, 0, 1),
+                                          (300, 70, 21, 1, 0), (40, 33, 33, 2, 1), (1000, 1000, 11, 0, 0), (1000, 1000, 11, 2, 1),
+                                          (1, 64, 5, 2, 1), (7, 1, 1, 0, 1)])
+def test_median_bit_exact_vs_oracle(torch, zen, oracle, T, F, L, dr, cb):
+    rng = np.random.default_rng(T * 7 + F + L)
+    src = rng.standard_normal((T, F)).astype(np.float32)
+    src[rng.random((T, F)) < 0.05] = np.float32(0.5)
+    exp = oracle.median_filter(oracle.GEOM_GPU, src, L, dr, cb, dst_init=np.full((T, F), SENT, np.float32))
+    o = torch.full((T, F), float(SENT), dtype=torch.float32, device="cuda")
+    zen.MedianFilterGPU(T, F, L, dr, bool(cb)).filter(torch.from_numpy(src).cuda(), o)
+    assert np.array_equal(o.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+
+
+def test_median_on_reference_s_mag(torch, zen):
+    """bit-exact on identical magnitude inputs: the reference's own s_mag -> its harmonic / percussive matrices"""
+    n = 0
+    for f in sorted(glob.glob(os.path.join(GOLD, "ref_gpu_stages_*.npz"))):
+        d = np.load(f)
+        be, fs, hop, beta, flags, caus, cb, sse, soft, n_hops, seed = d["params"]
+        if sse:
+            continue
+        nwin, nfft, l_harm, l_perc, lag, W, cola = d["geom"]
+        s_mag = torch.from_numpy(d["final_s_mag"]).cuda()
+        for name, L, dr in (("final_harmonic_matrix", int(l_harm), int(caus)), ("final_percussive_matrix", int(l_perc), 2)):
+            o = torch.zeros_like(s_mag)
+            zen.MedianFilterGPU(int(W), int(nfft), L, dr, bool(cb)).filter(s_mag, o)
+            assert np.array_equal(o.cpu().numpy().view(np.uint32), d[name].view(np.uint32)), (f, name)
+            n += 1
+    assert n >= 8
+
+
+# --------------------------------------------------------------------- box ---
+
+def test_box_vs_npp(torch, zen):
+    d = np.load(os.path.join(GOLD, "npp_box.npz"))
+    keys = sorted(set(re.match(r"(T\d+_F\d+_L\d+_d\d_[a-z]+)", k).group(1) for k in d.files))
+    n = 0
+    for k in keys:
+        T, F, L, dr = map(int, re.match(r"T(\d+)_F(\d+)_L(\d+)_d(\d)", k).groups())
+        if k + "_zgexception" in d.files:
+            with pytest.raises(zen.ZgException):
+                zen.BoxFilterGPU(T, F, L, dr)
+            continue
+        o = torch.full((T, F), float(SENT), dtype=torch.float32, device="cuda")
+        zen.BoxFilterGPU(T, F, L, dr).filter(torch.from_numpy(d[k + "_src"]).cuda(), o)
+        got, ref = o.cpu().numpy(), d[k + "_dst"]
+        assert np.array_equal(np.isfinite(got), np.isfinite(ref)), k
+        assert np.array_equal(np.isinf(got), np.isinf(ref)), k
+        fin = np.isfinite(ref)
+        rel = np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])
+        assert rel.max() <= 2e-6, (k, rel.max())
+        n += 1
+    assert n >= 50
+
+
+# --------------------------------------------------------------------- fft ---
+
+@pytest.mark.parametrize("n", [64, 1024, 4096])
+def test_fft_vs_cufft_golden(torch, zen, n):
+    """libzen/fftw.test.cu tolerance: 2e-4 absolute on uniform(-1,1) inputs, unnormalised both ways"""
+    d = np.load(os.path.join(GOLD, "cufft.npz"))
+    x = d["n%d_x" % n]
+    for key, back in (("fwd", False), ("inv", True)):
+        f = zen.FFTC2CWrapperGPU(n)
+        f.fft_vec.copy_(torch.from_numpy(x).cuda())
+        f.backward() if back else f.forward()
+        got = f.fft_vec.cpu().numpy()
+        assert np.abs(got - d["n%d_%s" % (n, key)]).max() <= 2e-4
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_fft_vs_float64(torch, zen, n):
+    rng = np.random.default_rng(n)
+    x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+    for back in (False, True):
+        f = zen.FFTC2CWrapperGPU(n)
+        f.fft_vec.copy_(torch.from_numpy(x).cuda())
+        f.backward() if back else f.forward()
+        got = f.fft_vec.cpu().numpy().astype(np.complex128)
+        exp = np.fft.ifft(x.astype(np.complex128)) * n if back else np.fft.fft(x.astype(np.complex128))
+        assert np.abs(got - exp).max() <= 3e-7 * np.sqrt(n) * np.log2(max(n, 2)) * np.abs(exp).max() / np.sqrt(n) + 1e-6
+
+
+# --------------------------------------------------------------------- HPR ---
+
+HPR_CASES = [
+    # fs, hop, beta, flags, causal, copy_bord, sse, soft, n_hops
+    (44100.0, 1024, 2.5, 7, True, True, False, False, 40),
+    (44100.0, 1024, 2.5, 2, True, True, False, False, 40),
+    (44100.0, 1024, 2.5, 7, True, False, False, False, 40),
+    (48000.0, 256, 2.0, 7, True, True, False, False, 100),
+    (48000.0, 256, 2.0, 7, True, False, False, False, 100),
+    (48000.0, 256, 2.0, 7, False, True, False, False, 100),
+    (48000.0, 256, 2.0, 7, False, False, False, False, 100),
+    (44100.0, 512, 2.5, 7, True, True, True, True, 60),
+    (44100.0, 512, 2.5, 7, True, True, False, True, 60),
+    (44100.0, 512, 2.5, 5, True, False, False, False, 60),
+    (44100.0, 2048, 2.5, 7, True, True, False, False, 12),
+    (44100.0, 2048, 2.5, 7, True, False, False, False, 12),
+    (44100.0, 4096, 2.5, 7, True, True, False, False, 10),
+    (44100.0, 4096, 2.5, 7, False, False, False, False, 10),
+    (48000.0, 128, 2.0, 7, True, True, False, False, 120),
+    (48000.0, 64, 2.0, 3, True, True, False, False, 150),
+]
+
+
+def _oracle_run(oracle, fs, hop, beta, flags, causal, cb, sse, soft, audio):
+    o = oracle.OracleHPR(oracle.GEOM_GPU, fs, hop, beta, flags, oracle.CAUSAL if causal else oracle.ANTICAUSAL, cb)
+    if sse:
+        o.use_sse_filter()
+    if soft:
+        o.use_soft_mask()
+    return o, o.run(audio)
+
+
+def _assert_audio(got, ref, what):
+    for name, a, b in zip("HPR", got, ref):
+        err, snr = peak_norm_err(a, b)
+        assert err <= TOL_ABS and snr >= TOL_SNR, (what, name, err, snr)
+
+
+@pytest.mark.parametrize("fs,hop,beta,flags,causal,cb,sse,soft,n_hops", HPR_CASES)
+def test_hpr_streaming_vs_oracle(torch, zen, oracle, fs, hop, beta, flags, causal, cb, sse, soft, n_hops):
+    """HPR<GPU>::process_next_hop, hop by hop, against the oracle's GPU-geometry restatement.
+    Hard-mask threshold flips (tests/util.py:flip_aware_compare) are identified bin by bin, must be
+    borderline decisions, and must be rare; every other hop has to meet the north-star tolerance."""
+    audio = synth_audio(n_hops * hop, seed=hop + 3 * int(cb) + int(causal), fs=int(fs))
+    o = oracle.OracleHPR(oracle.GEOM_GPU, fs, hop, beta, flags, oracle.CAUSAL if causal else oracle.ANTICAUSAL, cb)
+    h = zen.HPR(fs, hop, beta, flags, 0 if causal else 1, cb)
+    assert (h.nwin, h.nfft, h.l_harm, h.l_perc, h.lag, h.stft_width) == (o.nwin, o.nfft, o.l_harm, o.l_perc, o.lag, o.stft_width)
+    assert np.float32(h.COLA_factor) == np.float32(o.cola)
+    if sse:
+        o.use_sse_filter()
+        h.use_sse_filter()
+    if soft:
+        o.use_soft_mask()
+        h.use_soft_mask()
+    r = flip_aware_compare(h, o, audio, hop, flags, hard_mask=not (sse or soft))
+    assert r["margin_ok"], ("mask mismatch on a non-borderline bin", r["worst_margin"])
+    assert np.count_nonzero(r["flips"]) <= max(1, n_hops // 10), r["flips"]
+    assert r["hops_checked"] >= n_hops * 0.8
+    for name, e, snr in zip("HPR", r["err"], r["snr"]):
+        assert e <= TOL_ABS and snr >= TOL_SNR, (name, e, snr)
+    # the *_out members hold [emitted hop | overlap-add tail] like the reference's (hps.h:195-197)
+    if not np.count_nonzero(r["flips"][-2:]):
+        for name, mine in (("harmonic_out", h.harmonic_out), ("percussive_out", h.percussive_out), ("residual_out", h.residual_out)):
+            ref = o.get(name)
+            assert np.abs(mine - ref).max() <= TOL_ABS * max(np.abs(r["ref"]["HPR".index(name[0].upper())]).max(), 1e-30), name
+    h.close()
+
+
+@pytest.mark.parametrize("fs,hop,beta,flags,causal,cb,sse,soft,n_hops", HPR_CASES)
+def test_hpr_batch_equals_streaming(torch, zen, fs, hop, beta, flags, causal, cb, sse, soft, n_hops):
+    """tiles with halo recompute == hop-by-hop streaming, bit for bit; several streams, ragged tile count"""
+    n_hops = n_hops * 3 + 1
+    n_streams = 3
+    audio = np.stack([synth_audio(n_hops * hop, seed=100 + s, fs=int(fs)) for s in range(n_streams)])
+    b = zen.HPRBatch(fs, hop, beta, flags, causal=causal, nocopybord=not cb, sse=sse, soft=soft)
+    x = torch.from_numpy(audio).cuda()
+    outs = b.process(x)
+    torch.cuda.synchronize()
+    for s in range(n_streams):
+        h = zen.HPR(fs, hop, beta, flags, 0 if causal else 1, cb)
+        if sse:
+            h.use_sse_filter()
+        if soft:
+            h.use_soft_mask()
+        ref = h.run(audio[s])
+        h.close()
+        for o in range(3):
+            if outs[o] is None or (o == 2 and (sse or soft)):
+                continue
+            assert np.array_equal(outs[o][s].cpu().numpy(), ref[o]), (s, o)
+    b.close()
+
+
+def test_hpr_vs_reference_gpu_golden(torch, zen):
+    """separated audio vs the UNMODIFIED reference GPU path (deterministic configs, stft_width == 2)"""
+    files = sorted(glob.glob(os.path.join(GOLD, "ref_gpu_audio_*.npz")))
+    assert len(files) >= 4
+    for f in files:
+        d = np.load(f)
+        assert d["deterministic"].all()
+        be, fs, hop, beta, flags, caus, cb, sse, soft, n_hops, seed = d["params"]
+        hop, n_hops = int(hop), int(n_hops)
+        audio = synth_audio(n_hops * hop, seed=int(seed), fs=int(fs))
+        assert hashlib.sha256(audio.tobytes()).digest() == d["audio_sha"].tobytes()
+        h = zen.HPR(float(fs), hop, float(beta), int(flags), int(caus), bool(cb))
+        got = h.run(audio)
+        h.close()
+        _assert_audio(got, [d["harmonic"], d["percussive"], d["residual"]], os.path.basename(f))
+
+
+def test_hpr_materialize_vs_oracle(torch, zen, oracle):
+    """the reference's public stft_width x nfft matrices, rebuilt on demand"""
+    for (fs, hop, beta, flags, causal, cb, sse, soft, n_hops) in [HPR_CASES[0], HPR_CASES[2], HPR_CASES[6], HPR_CASES[7]]:
+        audio = synth_audio(n_hops * hop, seed=5, fs=int(fs))
+        o, _ = _oracle_run(oracle, fs, hop, beta, flags, causal, cb, sse, soft, audio)
+        h = zen.HPR(fs, hop, beta, flags, 0 if causal else 1, cb)
+        if sse:
+            h.use_sse_filter()
+        if soft:
+            h.use_soft_mask()
+        h.run(audio)
+        m = h.materialize()
+        h.close()
+        stft_o = o.get("sliding_stft")
+        scale = np.abs(stft_o).max()
+        assert np.abs(m["sliding_stft"] - stft_o).max() <= 2e-6 * scale
+        smag_o = o.get("s_mag")
+        assert np.abs(m["s_mag"] - smag_o).max() <= 4e-6 * smag_o.max()
+        if not sse:
+            # medians are selections: identical up to the tiny FFT differences of the selected element
+            for nm in ("harmonic_matrix", "percussive_matrix"):
+                assert np.abs(m[nm] - o.get(nm)).max() <= 4e-6 * smag_o.max(), nm
+            for nm in ("harmonic_mask", "percussive_mask", "residual_mask"):
+                assert np.mean(m[nm] != o.get(nm)) <= 2e-3, nm
+
+
+def test_hps_test_cu_properties(torch, zen):
+    """libzen/hps.test.cu:160-372 restated: outputs != input, copybord != nocopybord on the GPU,
+    percussive-only leaves harmonic/residual at 0, reset_buffers() reproduces the first hop bit for bit"""
+    fs, hop, n_hops = 48000.0, 256, 100
+    rng = np.random.default_rng(0)
+    data = rng.uniform(-1, 1, n_hops * hop).astype(np.float32)
+    a = zen.HPR(fs, hop, 2.0, 7, 0, True)
+    b = zen.HPR(fs, hop, 2.0, 7, 0, False)
+    oa, ob = a.run(data), b.run(data)
+    for o in oa:
+        assert not np.array_equal(o, data)
+    assert any(not np.array_equal(x, y) for x, y in zip(oa, ob))
+    c = zen.HPR(fs, hop, 2.0, zen.OUTPUT_PERCUSSIVE, 0, True)
+    oc = c.run(data)
+    assert np.all(oc[0] == 0) and np.all(oc[2] == 0) and np.any(oc[1] != 0)
+    assert np.all(c.harmonic_out == 0) and np.all(c.residual_out == 0)
+    first = a.run(data[:hop], 1)
+    a.reset_buffers()
+    x1 = a.run(data[:hop], 1)
+    a.reset_buffers()
+    x2 = a.run(data[:hop], 1)
+    assert all(np.array_equal(p, q) for p, q in zip(x1, x2))
+    assert not all(np.array_equal(p, q) for p, q in zip(first, x1))
+    for h in (a, b, c):
+        h.close()
+
+
+def test_realtime_api_and_io(torch, zen, oracle):
+    """HPRRealtime + IOGPU driven exactly like zen/fakert.h:217-251 (mapped in, mapped out)"""
+    fs, hop, n_hops = 44100.0, 1024, 30
+    audio = synth_audio(n_hops * hop, seed=9)
+    _, ref = _oracle_run(oracle, fs, hop, 2.5, 2, True, True, False, False, audio)
+    hp = zen.HPRRealtime(fs, hop, 2.5, zen.OUTPUT_PERCUSSIVE)
+    io = zen.IOGPU(hop)
+    hp.warmup(io, test_iters=20)
+    out = np.zeros_like(audio)
+    for i in range(n_hops):
+        io.host_in[:] = audio[i * hop:(i + 1) * hop]
+        hp.process_next_hop(io.device_in)
+        hp.copy_percussive(io.device_out)
+        out[i * hop:(i + 1) * hop] = io.host_out
+    err, snr = peak_norm_err(out, ref[1])
+    assert err <= TOL_ABS and snr >= TOL_SNR, (err, snr)
+    io.close()
+
+
+def test_constructor_errors(torch, zen):
+    with pytest.raises(zen.ZgException):
+        zen.HPRIOffline(44100.0, 4096, 300, 2.0, 2.0)     # hps.cu:33-36
+    with pytest.raises(zen.ZgException):
+        zen.MedianFilterGPU(9, 9, 10, 0)                  # mfilt.test.cu:235-244
+    with pytest.raises(zen.ZgException):
+        zen.MedianFilterGPU(9, 9, 10, 2, True)
+    with pytest.raises(zen.ZgException):
+        zen.BoxFilterGPU(9, 9, 10, 1)
+
+
+# ----------------------------------------------------------------- offline ---
+
+@pytest.mark.parametrize("nocb,sse,soft", [(False, False, False), (True, False, False), (False, False, True), (False, True, False)])
+def test_offline_vs_oracle(torch, zen, oracle, nocb, sse, soft):
+    """HPRIOffline<GPU>::process: padded sizes as in hps_gpu_public.test.cu:60-80 (n not a multiple of the hop)"""
+    n = 10 * 4096 + 11
+    audio = synth_audio(n, seed=21)
+    ref = oracle.offline_process(oracle.GEOM_GPU, 44100.0, 4096, 256, 2.5, 2.5, audio, nocopybord=nocb, sse=sse, soft=soft)
+    off = zen.HPRIOffline(44100.0, 4096, 256, 2.5, 2.5, nocopybord=nocb)
+    if sse:
+        off.use_sse_filter()
+    if soft:
+        off.use_soft_mask()
+    got = off.process(audio)
+    assert all(g.size == n for g in got)
+    assert np.all(got[2] == 0)                 # reference quirk: residual is all zeros (hps.cu:45-48, 200-204)
+    _assert_audio(got[:2], ref[:2], "offline")
+
+
+def test_offline_vs_reference_gpu_golden(torch, zen):
+    """pass 1 (hop 4096, stft_width 2) of the reference GPU path is deterministic: harmonic must match"""
+    audio = synth_audio(10 * 4096 + 11, seed=21)
+    for name, nocb in (("ref_offline_gpu.npz", False), ("ref_offline_gpu_nocb.npz", True)):
+        d = np.load(os.path.join(GOLD, name))
+        got = zen.HPRIOffline(44100.0, 4096, 256, 2.5, 2.5, nocopybord=nocb).process(audio)
+        err, snr = peak_norm_err(got[0], d["harmonic"])
+        assert err <= TOL_ABS and (snr >= TOL_SNR or np.all(d["harmonic"] == 0)), (name, err, snr)
+        assert int(d["residual_all_zero"]) == 1 and np.all(got[2] == 0)
+
+
+def test_batch_host_path(torch, zen):
+    """host-buffer entry point (chunked H2D / compute / D2H) == device-resident entry point"""
+    fs, hop, n_hops, n_streams = 44100.0, 1024, 50, 5
+    audio = np.stack([synth_audio(n_hops * hop, seed=300 + s) for s in range(n_streams)])
+    b = zen.HPRBatch(fs, hop, 2.5, zen.OUTPUT_PERCUSSIVE)
+    dev = b.process(torch.from_numpy(audio).cuda())[1].cpu().numpy()
+    host_out = np.zeros_like(audio)
+    b.process_host(audio, [None, host_out, None])
+    assert np.array_equal(dev, host_out)
+    assert b.last_launches >= 1
+    b.close()

@@ -1,0 +1,137 @@
+// Shared-memory Stockham FFT (radix 8/4/2, autosort, in place through registers)
+// used by every kernel in this library.  Replaces cuFFT as driven by
+// FFTC2CWrapperGPU (libzen/fftw.h:20-49): unnormalised in both directions.
+//
+// Layout: complex values as float2 in shared memory, index padded by one slot
+// every 16 (fpad) so the stride-R stores of the early stages spread over banks.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace zen_b200 {
+
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int fpad_size(int n) { return n + (n >> 4) + 1; }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// multiply by S*i  (S = -1 forward, +1 inverse)
+template <int S>
+__device__ __forceinline__ float2 mul_si(float2 a)
+{
+	return S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <int S>
+__device__ __forceinline__ void dft2(float2* v)
+{
+	float2 t = v[0];
+	v[0] = cadd(t, v[1]);
+	v[1] = csub(t, v[1]);
+}
+
+template <int S>
+__device__ __forceinline__ void dft4(float2* v)
+{
+	float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+	float2 a2 = cadd(v[1], v[3]), a3 = mul_si<S>(csub(v[1], v[3]));
+	v[0] = cadd(a0, a2);
+	v[2] = csub(a0, a2);
+	v[1] = cadd(a1, a3);
+	v[3] = csub(a1, a3);
+}
+
+template <int S>
+__device__ __forceinline__ void dft8(float2* v)
+{
+	float2 e[4] = {v[0], v[2], v[4], v[6]};
+	float2 o[4] = {v[1], v[3], v[5], v[7]};
+	dft4<S>(e);
+	dft4<S>(o);
+	const float h = 0.70710678118654752440f;
+	const float s = (float)S;
+	float2 o1 = make_float2(h * (o[1].x - s * o[1].y), h * (s * o[1].x + o[1].y));
+	float2 o2 = mul_si<S>(o[2]);
+	float2 o3 = make_float2(h * (-o[3].x - s * o[3].y), h * (s * o[3].x - o[3].y));
+	v[0] = cadd(e[0], o[0]);
+	v[4] = csub(e[0], o[0]);
+	v[1] = cadd(e[1], o1);
+	v[5] = csub(e[1], o1);
+	v[2] = cadd(e[2], o2);
+	v[6] = csub(e[2], o2);
+	v[3] = cadd(e[3], o3);
+	v[7] = csub(e[3], o3);
+}
+
+template <int S, int R>
+__device__ __forceinline__ void dftR(float2* v)
+{
+	if constexpr (R == 8)
+		dft8<S>(v);
+	else if constexpr (R == 4)
+		dft4<S>(v);
+	else
+		dft2<S>(v);
+}
+
+// One Stockham decimation-in-time stage of radix R on an M-point transform
+// whose already-combined sub-transforms have length NS.  tw[t] = exp(-2*pi*i*t/M).
+template <int M, int NT, int S, int R, int NS>
+__device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ tw, int tid)
+{
+	constexpr int NB = M / R;
+	constexpr int PER = (NB + NT - 1) / NT;
+	float2 v[PER][R];
+#pragma unroll
+	for (int b = 0; b < PER; ++b) {
+		int j = tid + b * NT;
+		if ((NB % NT == 0) || j < NB) {
+			int k = j & (NS - 1);
+#pragma unroll
+			for (int r = 0; r < R; ++r)
+				v[b][r] = buf[fpad(j + r * NB)];
+			if constexpr (NS > 1) {
+#pragma unroll
+				for (int r = 1; r < R; ++r) {
+					float2 w = __ldg(&tw[(r * k) * (M / (NS * R))]);
+					if (S > 0)
+						w.y = -w.y;
+					v[b][r] = cmul(v[b][r], w);
+				}
+			}
+			dftR<S, R>(v[b]);
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int b = 0; b < PER; ++b) {
+		int j = tid + b * NT;
+		if ((NB % NT == 0) || j < NB) {
+			int k = j & (NS - 1);
+			int j0 = (j - k) * R + k;
+#pragma unroll
+			for (int r = 0; r < R; ++r)
+				buf[fpad(j0 + r * NS)] = v[b][r];
+		}
+	}
+	__syncthreads();
+}
+
+// M-point complex FFT in shared memory, all NT threads of the CTA participate.
+// The caller must have synchronised after filling buf.  Ends synchronised.
+template <int M, int NT, int S, int NS = 1>
+__device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
+{
+	if constexpr (NS < M) {
+		constexpr int rem = M / NS;
+		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		fft_stage<M, NT, S, R, NS>(buf, tw, tid);
+		fft_smem<M, NT, S, NS * R>(buf, tw, tid);
+	}
+}
+
+}  // namespace zen_b200

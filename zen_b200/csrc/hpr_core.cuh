@@ -1,0 +1,350 @@
+// The fused per-hop HPR step: sqrt-Hann window -> real FFT -> |X| ring ->
+// time-axis + frequency-axis median (or SSE box means) of the ONE consumed row
+// -> hard / soft / SSE masks -> inverse real FFT -> COLA overlap-add.
+//
+// It restates, for one hop, HPR<GPU>::process_next_hop + apply_median_filter /
+// apply_sse_filter (libzen/hps.cu:429-652), but computes only the row the
+// reference consumes (row stft_width - lag, hps.cu:501-504) instead of
+// filtering the whole stft_width x nfft matrix, and works on the nfft/2+1
+// independent bins of the real-input spectrum:
+//   * frequency windows index the mirrored half spectrum (|X[nfft-k]| = |X[k]|);
+//   * with --nocopybord the reference's masks at bins k and nfft-k differ
+//     (forward-looking ROI, mfilt.h:152-158); their effect on Re(ifft) is the
+//     half-spectrum mask (M[k] + M[nfft-k]) / 2, which is what we apply.
+// tests/test_halfspec_model.py proves this algebra against the oracle on CPU.
+#pragma once
+#include "fft_smem.cuh"
+#include "median_select.cuh"
+#include "zen_common.cuh"
+
+namespace zen_b200 {
+
+constexpr int ZEN_MAX_TAPS = 128;
+
+struct HprDev {
+	int hop, W, lag;
+	int n_taps;          // time-axis taps (0: the reference never writes the consumed row -> H = 0)
+	int Lp, midp, Kp;    // frequency window (odd), its half, registers per lane of the sliding window
+	int copy_bord;       // frequency windows centred+circular (1) or forward-looking (0)
+	int out_flags, soft, sse;
+	float power;         // (float)(int)beta, soft-mask exponent (hps.h:116-129)
+	float beta, beta_h;  // beta, beta - eps (hps.cu:505, 540)
+	float cola;
+	float lh1, lp1;      // l_harm + 1, l_perc + 1 (hps.cu:599-604)
+	float inv_lp;        // 1 / Lp for the box mean
+	const float* window;   // nwin
+	const float2* tw;      // exp(-2 pi i t / M), t < M        (M = nfft/2)
+	const float2* twr;     // exp(-2 pi i k / nfft), k <= M/2
+	short tap_age[ZEN_MAX_TAPS];
+};
+
+// per-CTA streaming state (global memory)
+struct HprState {
+	float* mag_ring;   // W rows of (M+1): |X| (or |X|^2 with SSE), slot = frame index mod W
+	float2* x_ring;    // xdepth rows of (M+1); may be null when xdepth == 0
+	int xdepth;
+	float* tail[3];    // hop floats each (H, P, R): second half of the previous frame * COLA
+};
+
+struct HprEmit {
+	float* a[3];  // first destination of the emitted hop per output (H, P, R) or null
+	float* b[3];  // optional second destination
+};
+
+template <int NFFT>
+struct HprSmem {
+	static constexpr int M = NFFT / 2;
+	float2* zbuf;  // fpad_size(M)
+	float2* xbuf;  // M + 1
+	float* erow;   // M + 1 + Lp + 3   (extended magnitude row, later the H row)
+	float* prow;   // M + 1
+	static __host__ __device__ size_t bytes(int Lp)
+	{
+		size_t z = sizeof(float2) * (size_t)fpad_size(M);
+		size_t x = sizeof(float2) * (size_t)(M + 2);
+		size_t e = sizeof(float) * (size_t)((M + 1 + Lp + 3 + 3) & ~3);
+		size_t p = sizeof(float) * (size_t)((M + 1 + 3) & ~3);
+		return z + x + e + p;
+	}
+	__device__ void carve(unsigned char* base, int Lp)
+	{
+		zbuf = reinterpret_cast<float2*>(base);
+		xbuf = zbuf + fpad_size(M);
+		erow = reinterpret_cast<float*>(xbuf + (M + 2));
+		prow = erow + ((M + 1 + Lp + 3 + 3) & ~3);
+	}
+};
+
+__device__ __forceinline__ float mask_hard(float x, float y, float beta)
+{
+	return (x / (y + ZEN_EPS)) >= beta ? 1.0f : 0.0f;  // hps.h:100-113
+}
+__device__ __forceinline__ float mask_soft(float x, float y, float power)
+{
+	float px = powf(x, power), py = powf(y, power);    // hps.h:116-129
+	return px / (px + py + ZEN_EPS);
+}
+__device__ __forceinline__ float mask_sse(float x, float y)
+{
+	return x * x / (x * x + y * y + ZEN_EPS);          // hps.h:132-140
+}
+
+// masks of the percussive (mp) and harmonic (mh) outputs at half-spectrum bin k
+template <int NFFT>
+__device__ __forceinline__ void hpr_masks(const HprDev& P, const float* prow, const float* hrow, int k, float& mp, float& mh)
+{
+	constexpr int M = NFFT / 2;
+	const float H = hrow[k];
+	const float Pf = prow[k];
+	const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
+	const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
+	mp = 0.0f;
+	mh = 0.0f;
+	if (P.sse) {
+		if (want_p) mp = mask_sse(Pf, H);
+		if (want_h) mh = mask_sse(H, Pf);
+		return;
+	}
+	float Pb = Pf;
+	bool two = false;
+	if (!P.copy_bord && k != 0 && k != M) {
+		two = true;
+		Pb = (k > P.Lp) ? prow[k - P.Lp + 1] : 0.0f;
+	}
+	if (P.soft) {
+		if (want_p) mp = two ? 0.5f * (mask_soft(Pf, H, P.power) + mask_soft(Pb, H, P.power)) : mask_soft(Pf, H, P.power);
+		if (want_h) mh = two ? 0.5f * (mask_soft(H, Pf, P.power) + mask_soft(H, Pb, P.power)) : mask_soft(H, Pf, P.power);
+	}
+	else {
+		if (want_p) mp = two ? 0.5f * (mask_hard(Pf, H, P.beta) + mask_hard(Pb, H, P.beta)) : mask_hard(Pf, H, P.beta);
+		if (want_h) mh = two ? 0.5f * (mask_hard(H, Pf, P.beta_h) + mask_hard(H, Pb, P.beta_h)) : mask_hard(H, Pf, P.beta_h);
+	}
+}
+
+template <int L, typename Get>
+__device__ __forceinline__ float median_fixed(Get get)
+{
+	float v[L];
+#pragma unroll
+	for (int t = 0; t < L; ++t)
+		v[t] = get(t);
+	return median_regs<L>(v);
+}
+
+// One hop.  `full` == false: analysis only (fills the rings; halo iterations of a tile).
+// All NT threads of the CTA must call it with identical arguments.
+template <int NFFT, int NT>
+__device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, long i,
+                                              const float* __restrict__ prev, const float* __restrict__ cur,
+                                              bool full, bool fresh_tail, const HprEmit& em)
+{
+	constexpr int M = NFFT / 2;   // complex FFT length; also nwin
+	constexpr int HOP = M / 2;
+	const int tid = threadIdx.x;
+	const int W = P.W;
+	const int eoff = (P.copy_bord || P.sse) ? P.midp : 0;
+
+	// ---- A. window the 2-hop frame, pack even/odd samples as one complex value (hps.cu:452-462)
+	for (int n = tid; n < M; n += NT) {
+		float2 z = make_float2(0.0f, 0.0f);
+		if (n < HOP) {
+			float2 x;
+			if (n < HOP / 2)
+				x = prev ? reinterpret_cast<const float2*>(prev)[n] : make_float2(0.0f, 0.0f);
+			else
+				x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
+			float2 w = __ldg(reinterpret_cast<const float2*>(P.window) + n);
+			z = make_float2(x.x * w.x, x.y * w.y);
+		}
+		sm.zbuf[fpad(n)] = z;
+	}
+	__syncthreads();
+
+	// ---- B. forward FFT (hps.cu:465)
+	fft_smem<M, NT, -1>(sm.zbuf, P.tw, tid);
+
+	// ---- C. split into the real-input spectrum X[0..M], magnitudes into the ring (hps.cu:469-472, 492-493)
+	{
+		float* mag_row = st.mag_ring + (size_t)(i % W) * (M + 1);
+		float2* xg = st.xdepth > 0 ? st.x_ring + (size_t)(i % st.xdepth) * (M + 1) : nullptr;
+		const bool direct = (P.lag == 1);
+		for (int k = tid; k <= M / 2; k += NT) {
+			float2 Xa, Xb;
+			int ka = k, kb = M - k;
+			if (k == 0) {
+				float2 Z0 = sm.zbuf[fpad(0)];
+				Xa = make_float2(Z0.x + Z0.y, 0.0f);
+				Xb = make_float2(Z0.x - Z0.y, 0.0f);
+			}
+			else if (k == M / 2) {
+				Xa = cconj(sm.zbuf[fpad(M / 2)]);
+				Xb = Xa;
+			}
+			else {
+				float2 A = sm.zbuf[fpad(k)];
+				float2 B = cconj(sm.zbuf[fpad(M - k)]);
+				float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
+				float2 O = cmul(__ldg(&P.twr[k]), csub(A, B));
+				float2 D = make_float2(0.5f * O.y, -0.5f * O.x);
+				Xa = cadd(E, D);
+				Xb = cconj(csub(E, D));
+			}
+			float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
+			if (P.sse) {
+				ma = powf(ma, 2.0f);  // hps.h:91-98
+				mb = powf(mb, 2.0f);
+			}
+			mag_row[ka] = ma;
+			if (kb != ka) mag_row[kb] = mb;
+			if (xg) {
+				xg[ka] = Xa;
+				if (kb != ka) xg[kb] = Xb;
+			}
+			if (direct) {
+				sm.xbuf[ka] = Xa;
+				sm.erow[eoff + ka] = P.sse ? 1.0f / ma : ma;
+				if (kb != ka) {
+					sm.xbuf[kb] = Xb;
+					sm.erow[eoff + kb] = P.sse ? 1.0f / mb : mb;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	if (!full)
+		return;
+
+	// ---- D. the consumed frame: row stft_width - lag (hps.cu:501-504, 517-519)
+	const long jc = i - P.lag + 1;
+	if (P.lag > 1) {
+		const float* mrow = st.mag_ring + (size_t)((jc >= 0 ? jc : 0) % W) * (M + 1);
+		const float2* xrow = st.x_ring + (size_t)((jc >= 0 ? jc : 0) % st.xdepth) * (M + 1);
+		for (int k = tid; k <= M; k += NT) {
+			float m = jc >= 0 ? mrow[k] : 0.0f;
+			sm.erow[eoff + k] = P.sse ? 1.0f / m : m;
+			sm.xbuf[k] = jc >= 0 ? xrow[k] : make_float2(0.0f, 0.0f);
+		}
+		__syncthreads();
+	}
+	// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]|
+	if (eoff > 0) {
+		for (int t = tid; t < P.midp; t += NT) {
+			sm.erow[eoff - 1 - t] = sm.erow[eoff + 1 + t];
+			sm.erow[eoff + M + 1 + t] = sm.erow[eoff + M - 1 - t];
+		}
+	}
+	else {
+		for (int t = tid; t < P.Lp - 1; t += NT)
+			sm.erow[M + 1 + t] = sm.erow[M - 1 - t];
+	}
+	__syncthreads();
+
+	// ---- E. frequency axis: prow[s] = median / mean of erow[s .. s+Lp)
+	if (!P.sse) {
+		constexpr int NW = NT / 32;
+		const int wid = tid >> 5, lane = tid & 31;
+		const int R = (M + 1 + NW - 1) / NW;
+		const int s0 = wid * R;
+		const int s1 = min(M + 1, s0 + R);
+		warp_sliding_median_dyn<float>(P.Kp, sm.erow, sm.prow, s0, s1, P.Lp, lane);
+	}
+	else {
+		for (int k = tid; k <= M; k += NT) {
+			float acc = 0.0f;
+			for (int t = 0; t < P.Lp; ++t)
+				acc += sm.erow[k + t];
+			float mean = acc * P.inv_lp;
+			sm.prow[k] = (1.0f / mean) * P.lp1;  // hps.cu:599-601
+		}
+	}
+	__syncthreads();
+
+	// ---- F. time axis: H row (into erow, whose magnitudes are no longer needed)
+	{
+		const int nt = P.n_taps;
+		auto tap = [&](int t, int k) -> float {
+			long j = i - P.tap_age[t];
+			return j >= 0 ? st.mag_ring[(size_t)(j % W) * (M + 1) + k] : 0.0f;
+		};
+		for (int k = tid; k <= M; k += NT) {
+			float H;
+			if (P.sse) {
+				float acc = 0.0f;
+				for (int t = 0; t < nt; ++t)
+					acc += 1.0f / tap(t, k);
+				float mean = acc / (float)nt;
+				H = (1.0f / mean) * P.lh1;  // hps.cu:602-604
+			}
+			else {
+				switch (nt) {
+				case 0: H = 0.0f; break;
+				case 1: H = tap(0, k); break;
+				case 3: H = median_fixed<3>([&](int t) { return tap(t, k); }); break;
+				case 5: H = median_fixed<5>([&](int t) { return tap(t, k); }); break;
+				case 7: H = median_fixed<7>([&](int t) { return tap(t, k); }); break;
+				case 9: H = median_fixed<9>([&](int t) { return tap(t, k); }); break;
+				case 11: H = median_fixed<11>([&](int t) { return tap(t, k); }); break;
+				case 13: H = median_fixed<13>([&](int t) { return tap(t, k); }); break;
+				default: H = median_generic([&](int t) { return tap(t, k); }, nt); break;
+				}
+			}
+			sm.erow[k] = H;
+		}
+	}
+	__syncthreads();
+
+	// ---- G. per output: mask, inverse real FFT, overlap-add (hps.cu:498-579, 607-651)
+	// order P, H, R as in the reference; output index 0 = H, 1 = P, 2 = R
+	const int order[3] = {1, 0, 2};
+#pragma unroll 1
+	for (int oi = 0; oi < 3; ++oi) {
+		const int o = order[oi];
+		if (!(P.out_flags & (1 << o)))
+			continue;
+		if (o == 2 && (P.soft || P.sse))
+			continue;  // residual only exists for the hard mask (hps.cu:562)
+		for (int k = tid; k <= M / 2; k += NT) {
+			const int kb = M - k;
+			float mpa, mha, mpb, mhb;
+			hpr_masks<NFFT>(P, sm.prow, sm.erow, k, mpa, mha);
+			hpr_masks<NFFT>(P, sm.prow, sm.erow, kb, mpb, mhb);
+			float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
+			float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
+			float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];
+			float2 A = make_float2(Xa.x * ma, Xa.y * ma);   // hps.h:58-66
+			float2 Yb = make_float2(Xb.x * mb, Xb.y * mb);
+			if (k == 0) {
+				sm.zbuf[fpad(0)] = make_float2(A.x + Yb.x, A.x - Yb.x);
+			}
+			else if (k == M / 2) {
+				sm.zbuf[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
+			}
+			else {
+				float2 B = cconj(Yb);
+				float2 E2 = cadd(A, B);
+				float2 O2 = cmul(cconj(__ldg(&P.twr[k])), csub(A, B));
+				sm.zbuf[fpad(k)] = make_float2(E2.x - O2.y, E2.y + O2.x);
+				sm.zbuf[fpad(kb)] = make_float2(E2.x + O2.y, O2.x - E2.y);
+			}
+		}
+		__syncthreads();
+		fft_smem<M, NT, +1>(sm.zbuf, P.tw, tid);
+		// overlap-add: out = tail + Re(y[0:hop]) * COLA ; tail' = Re(y[hop:nwin]) * COLA   (hps.h:68-80)
+		float* tail = st.tail[o];
+		for (int n = tid; n < HOP / 2; n += NT) {
+			float2 v = sm.zbuf[fpad(n)];
+			float2 t = fresh_tail ? make_float2(0.0f, 0.0f) : reinterpret_cast<const float2*>(tail)[n];
+			float2 r = make_float2(fmaf(v.x, P.cola, t.x), fmaf(v.y, P.cola, t.y));
+			if (em.a[o]) reinterpret_cast<float2*>(em.a[o])[n] = r;
+			if (em.b[o]) reinterpret_cast<float2*>(em.b[o])[n] = r;
+		}
+		__syncthreads();
+		for (int n = HOP / 2 + tid; n < HOP; n += NT) {
+			float2 v = sm.zbuf[fpad(n)];
+			reinterpret_cast<float2*>(tail)[n - HOP / 2] = make_float2(v.x * P.cola, v.y * P.cola);
+		}
+		__syncthreads();
+	}
+}
+
+}  // namespace zen_b200

@@ -1,0 +1,928 @@
+// Kernels + C ABI of the streaming / batched / offline HPR path.
+// Reference: libzen/hps.h, libzen/hps.cu (HPR<GPU>, HPRRealtime<GPU>, HPRIOffline<GPU>).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "hpr_core.cuh"
+
+using namespace zen_b200;
+
+// ----------------------------------------------------------------- kernels ---
+
+// One CTA = one stream x one tile of consecutive hops.  The CTA walks its hops
+// in order; the W-1 hops before the tile are analysed only (ring fill) and the
+// hop just before the tile is synthesised without being emitted (its second
+// half is the first overlap-add tail of the tile).  Frames are independent
+// given that halo, so tiles need no communication.
+template <int NFFT, int NT>
+__global__ void __launch_bounds__(NT) hpr_tile_kernel(const __grid_constant__ HprDev P,
+                                                      const float* __restrict__ in, long in_stride,
+                                                      float* out_h, float* out_p, float* out_r, long out_stride,
+                                                      long n_hops, int tile_hops,
+                                                      float* scratch, size_t scratch_per_cta)
+{
+	constexpr int M = NFFT / 2, HOP = M / 2;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	HprSmem<NFFT> sm;
+	sm.carve(smem_raw, P.Lp);
+
+	const int tile = blockIdx.x, stream = blockIdx.y;
+	const size_t cta = (size_t)stream * gridDim.x + tile;
+	float* sc = scratch + cta * scratch_per_cta;
+	HprState st;
+	st.mag_ring = sc;
+	sc += (size_t)P.W * (M + 1) + ((P.W * (M + 1)) & 1);
+	st.xdepth = P.lag > 1 ? P.lag : 0;
+	st.x_ring = reinterpret_cast<float2*>(sc);
+	sc += 2 * (size_t)st.xdepth * (M + 1);
+	for (int o = 0; o < 3; ++o)
+		st.tail[o] = sc + (size_t)o * HOP;
+
+	const float* sin = in + (size_t)stream * in_stride;
+	const long e0 = (long)tile * tile_hops;
+	const long e1 = min(n_hops, e0 + (long)tile_hops);
+	const long i_begin = max(0L, e0 - P.W);
+	const long i_full = max(0L, e0 - 1);
+	for (long i = i_begin; i < e1; ++i) {
+		const float* cur = sin + (size_t)i * HOP;
+		const float* prev = i > 0 ? cur - HOP : nullptr;
+		HprEmit em;
+		const bool emit = i >= e0;
+		em.a[0] = (emit && out_h) ? out_h + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+		em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+		em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+		em.b[0] = em.b[1] = em.b[2] = nullptr;
+		hpr_iteration<NFFT, NT>(P, sm, st, i, prev, cur, i >= i_full, i == i_full, em);
+	}
+}
+
+// One hop of one persistent stream (HPR<GPU>::process_next_hop): state lives in
+// the zen_hpr object between launches.  ola[o] is the reference's *_out vector:
+// [0:hop] the emitted hop, [hop:nwin] the overlap-add tail.
+template <int NFFT, int NT>
+__global__ void __launch_bounds__(NT) hpr_hop_kernel(const __grid_constant__ HprDev P, HprState st, long i,
+                                                     float* input /* nwin: previous hop | current hop */,
+                                                     const float* __restrict__ in_hop,
+                                                     float* ola_h, float* ola_p, float* ola_r,
+                                                     float* ext_h, float* ext_p, float* ext_r)
+{
+	constexpr int M = NFFT / 2, HOP = M / 2;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	HprSmem<NFFT> sm;
+	sm.carve(smem_raw, P.Lp);
+	// input = input[hop:] ++ in_hop   (hps.cu:452-453)
+	for (int n = threadIdx.x; n < HOP; n += NT) {
+		input[n] = input[HOP + n];
+	}
+	__syncthreads();
+	for (int n = threadIdx.x; n < HOP; n += NT)
+		input[HOP + n] = in_hop[n];
+	__syncthreads();
+	float* ola[3] = {ola_h, ola_p, ola_r};
+	float* ext[3] = {ext_h, ext_p, ext_r};
+	HprEmit em;
+	for (int o = 0; o < 3; ++o) {
+		st.tail[o] = ola[o] + HOP;
+		em.a[o] = (P.out_flags & (1 << o)) ? ola[o] : nullptr;
+		em.b[o] = (P.out_flags & (1 << o)) ? ext[o] : nullptr;
+	}
+	hpr_iteration<NFFT, NT>(P, sm, st, i, input, input + HOP, true, false, em);
+	// outputs that the masks never reach still advance like the reference's
+	// rotate-and-zero (hps.cu:435-449): residual with soft mask / SSE
+	if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse)) {
+		for (int n = threadIdx.x; n < HOP; n += NT) {
+			float t = ola_r[HOP + n];
+			ola_r[n] = t;
+			ola_r[HOP + n] = 0.0f;
+			if (ext_r) ext_r[n] = t;
+		}
+	}
+}
+
+__global__ void copy_hop_kernel(const float* __restrict__ src, float* __restrict__ dst, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		dst[i] = src[i];
+}
+
+// intermediate = percussive + residual of pass 1, un-lagged (hps.cu:154-176).
+// The reference reads pass-2 hops past the truncated size from the same
+// allocation, where the un-shifted tail still sits; restated here.
+__global__ void offline_intermediate_kernel(const float* __restrict__ p1, const float* __restrict__ r1,
+                                            float* __restrict__ inter, long padded1, long shift1, long padded2)
+{
+	long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= padded2)
+		return;
+	long src = (j + shift1 < padded1) ? j + shift1 : j;
+	inter[j] = src < padded1 ? p1[src] + r1[src] : 0.0f;
+}
+
+// ------------------------------------------------------------------- host ---
+
+namespace {
+
+template <int NFFT>
+constexpr int nt_for()
+{
+	return (NFFT / 16) < 64 ? 64 : ((NFFT / 16) > 512 ? 512 : (NFFT / 16));
+}
+
+struct Plan {
+	HprDev dev;
+	zen_geometry geom;
+	int nfft;
+	int causality;
+	float* d_window = nullptr;
+	float2* d_tw = nullptr;
+	float2* d_twr = nullptr;
+	size_t smem_bytes = 0;
+};
+
+int build_plan(Plan& pl, float fs, int hop, float beta, unsigned flags, int causality, int copy_bord, bool sse, bool soft)
+{
+	if (hop < 32 || hop > 4096 || !is_pow2(hop))
+		return ZEN_ERR_UNSUPPORTED;
+	if (zen_hpr_geometry(fs, hop, causality == ZEN_TIME_CAUSAL, &pl.geom) != ZEN_OK)
+		return ZEN_ERR_ARG;
+	const zen_geometry& g = pl.geom;
+	// the four filter constructors of HPR<B> throw when the filter is longer than its axis
+	// (mfilt.h:80-87, box.h:71-78)
+	if (g.stft_width < 1 || g.l_harm > g.stft_width || g.l_perc > g.nfft)
+		return ZEN_ERR_GEOMETRY;
+	pl.nfft = g.nfft;
+	pl.causality = causality;
+	HprDev& d = pl.dev;
+	std::memset(&d, 0, sizeof(d));
+	const int M = g.nfft / 2;
+	d.hop = hop;
+	d.W = g.stft_width;
+	d.lag = g.lag;
+	d.Lp = odd_len(g.l_perc);
+	d.midp = d.Lp / 2;
+	d.Kp = sliding_K_for(d.Lp);
+	if (d.Kp == 0 || d.Lp > M)
+		return ZEN_ERR_UNSUPPORTED;
+	d.copy_bord = copy_bord ? 1 : 0;
+	d.out_flags = (int)(flags & 7u);
+	d.soft = soft ? 1 : 0;
+	d.sse = sse ? 1 : 0;
+	d.power = (float)(int)beta;
+	d.beta = beta;
+	d.beta_h = beta - ZEN_EPS;
+	d.cola = g.cola_factor;
+	d.lh1 = (float)g.l_harm + 1.0f;
+	d.lp1 = (float)g.l_perc + 1.0f;
+	d.inv_lp = 1.0f / (float)d.Lp;
+	// time-axis taps of the consumed row r = W - lag, as ages behind the newest frame
+	// (SURVEY.md section 8(a'); mfilt.h:111-189)
+	{
+		const int Lh = odd_len(g.l_harm), mid = Lh / 2, W = g.stft_width, r = W - g.lag;
+		std::vector<int> rows;
+		const bool wrap = copy_bord || sse;  // BoxFilterGPU always wrap-pads (box.h:194-205)
+		if (wrap) {
+			for (int t = 0; t < Lh; ++t)
+				rows.push_back(((r - mid + t) % W + W) % W);
+		}
+		else if (causality == ZEN_TIME_CAUSAL) {
+			if (r >= Lh && r < W)
+				for (int t = 0; t < Lh; ++t)
+					rows.push_back(r - Lh + t);
+		}
+		else {
+			if (r >= mid && r < mid + W - Lh)
+				for (int t = 0; t < Lh; ++t)
+					rows.push_back(r - mid + t);
+		}
+		if ((int)rows.size() > ZEN_MAX_TAPS)
+			return ZEN_ERR_UNSUPPORTED;
+		d.n_taps = (int)rows.size();
+		for (size_t t = 0; t < rows.size(); ++t)
+			d.tap_age[t] = (short)(W - 1 - rows[t]);
+	}
+	// tables
+	std::vector<float> win(g.nwin);
+	zen_window(ZEN_WIN_SQRT_VON_HANN, g.nwin, win.data());
+	std::vector<float2> tw(M), twr(M / 2 + 1);
+	const double two_pi = 6.283185307179586476925286766559;
+	for (int t = 0; t < M; ++t)
+		tw[t] = make_float2((float)std::cos(two_pi * t / M), (float)-std::sin(two_pi * t / M));
+	for (int k = 0; k <= M / 2; ++k)
+		twr[k] = make_float2((float)std::cos(two_pi * k / g.nfft), (float)-std::sin(two_pi * k / g.nfft));
+	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_window, sizeof(float) * g.nwin));
+	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_tw, sizeof(float2) * M));
+	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_twr, sizeof(float2) * (M / 2 + 1)));
+	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_window, win.data(), sizeof(float) * g.nwin, cudaMemcpyHostToDevice));
+	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_twr, twr.data(), sizeof(float2) * (M / 2 + 1), cudaMemcpyHostToDevice));
+	d.window = pl.d_window;
+	d.tw = pl.d_tw;
+	d.twr = pl.d_twr;
+	return ZEN_OK;
+}
+
+void free_plan(Plan& pl)
+{
+	cudaFree(pl.d_window);
+	cudaFree(pl.d_tw);
+	cudaFree(pl.d_twr);
+	pl.d_window = nullptr;
+	pl.d_tw = nullptr;
+	pl.d_twr = nullptr;
+}
+
+size_t tile_scratch_floats(const Plan& pl)
+{
+	const int M = pl.nfft / 2;
+	size_t ring = (size_t)pl.dev.W * (M + 1);
+	ring += ring & 1;
+	size_t xr = pl.dev.lag > 1 ? 2 * (size_t)pl.dev.lag * (M + 1) : 0;
+	size_t tails = 3 * (size_t)pl.dev.hop;
+	return (ring + xr + tails + 3) & ~(size_t)3;
+}
+
+template <int NFFT>
+int launch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
+                int n_streams, long n_hops, int tile_hops, float* scratch, cudaStream_t s)
+{
+	constexpr int NT = nt_for<NFFT>();
+	auto kern = hpr_tile_kernel<NFFT, NT>;
+	size_t smem = HprSmem<NFFT>::bytes(pl.dev.Lp);
+	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int n_tiles = (int)((n_hops + tile_hops - 1) / tile_hops);
+	dim3 grid(n_tiles, n_streams);
+	kern<<<grid, NT, smem, s>>>(pl.dev, in, in_stride, oh, op, orr, out_stride, n_hops, tile_hops, scratch,
+	                            tile_scratch_floats(pl));
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	return ZEN_OK;
+}
+
+int dispatch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
+                  int n_streams, long n_hops, int tile_hops, float* scratch, cudaStream_t s)
+{
+	switch (pl.nfft) {
+	case 128: return launch_tile<128>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 256: return launch_tile<256>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 512: return launch_tile<512>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 1024: return launch_tile<1024>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 2048: return launch_tile<2048>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 4096: return launch_tile<4096>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 8192: return launch_tile<8192>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 16384: return launch_tile<16384>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	}
+	return ZEN_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// ------------------------------------------------------ streaming object ---
+
+struct zen_hpr {
+	Plan plan;
+	float fs, beta;
+	unsigned flags;
+	int hop, causality, copy_bord;
+	bool sse = false, soft = false;
+	bool plan_dirty = false;
+	long iter = 0;
+	cudaStream_t stream = nullptr;
+	// state
+	float* d_input = nullptr;   // nwin
+	float* d_ola[3] = {nullptr, nullptr, nullptr};  // nwin each (harmonic_out, percussive_out, residual_out)
+	float* d_mag_ring = nullptr;
+	float2* d_x_ring = nullptr;
+};
+
+namespace {
+
+template <int NFFT>
+int launch_hop(zen_hpr* h, const float* in_hop, float* eh, float* ep, float* er)
+{
+	constexpr int NT = nt_for<NFFT>();
+	auto kern = hpr_hop_kernel<NFFT, NT>;
+	size_t smem = HprSmem<NFFT>::bytes(h->plan.dev.Lp);
+	static thread_local const void* configured = nullptr;
+	if (configured != (const void*)kern) {
+		ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = (const void*)kern;
+	}
+	HprState st;
+	st.mag_ring = h->d_mag_ring;
+	st.x_ring = h->d_x_ring;
+	st.xdepth = h->plan.dev.W;
+	st.tail[0] = st.tail[1] = st.tail[2] = nullptr;
+	kern<<<1, NT, smem, h->stream>>>(h->plan.dev, st, h->iter, h->d_input, in_hop, h->d_ola[0], h->d_ola[1], h->d_ola[2],
+	                                 eh, ep, er);
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	h->iter++;
+	return ZEN_OK;
+}
+
+int rebuild_plan(zen_hpr* h)
+{
+	free_plan(h->plan);
+	int rc = build_plan(h->plan, h->fs, h->hop, h->beta, h->flags, h->causality, h->copy_bord, h->sse, h->soft);
+	h->plan_dirty = false;
+	return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zen_hpr_create(zen_hpr** out, float fs, int hop, float beta, unsigned flags, int causality, int copy_bord)
+{
+	if (!out || (causality != ZEN_TIME_CAUSAL && causality != ZEN_TIME_ANTICAUSAL))
+		return ZEN_ERR_ARG;
+	*out = nullptr;
+	if (zen_device_count() <= 0)
+		return ZEN_ERR_CUDA;
+	zen_hpr* h = new (std::nothrow) zen_hpr();
+	if (!h)
+		return ZEN_ERR_ARG;
+	h->fs = fs;
+	h->beta = beta;
+	h->flags = flags;
+	h->hop = hop;
+	h->causality = causality;
+	h->copy_bord = copy_bord;
+	int rc = build_plan(h->plan, fs, hop, beta, flags, causality, copy_bord, false, false);
+	if (rc != ZEN_OK) {
+		free_plan(h->plan);
+		delete h;
+		return rc;
+	}
+	const zen_geometry& g = h->plan.geom;
+	const int M = g.nfft / 2;
+	cudaError_t e = cudaStreamCreate(&h->stream);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_input, sizeof(float) * g.nwin);
+	for (int o = 0; o < 3 && e == cudaSuccess; ++o)
+		e = cudaMalloc(&h->d_ola[o], sizeof(float) * g.nwin);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_mag_ring, sizeof(float) * (size_t)g.stft_width * (M + 1));
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_x_ring, sizeof(float2) * (size_t)g.stft_width * (M + 1));
+	if (e != cudaSuccess) {
+		std::fprintf(stderr, "zen_b200: allocation failed: %s\n", cudaGetErrorString(e));
+		zen_hpr_destroy(h);
+		return ZEN_ERR_CUDA;
+	}
+	*out = h;
+	return zen_hpr_reset_buffers(h);
+}
+
+void zen_hpr_destroy(zen_hpr* h)
+{
+	if (!h)
+		return;
+	if (h->stream) cudaStreamSynchronize(h->stream);
+	free_plan(h->plan);
+	cudaFree(h->d_input);
+	for (int o = 0; o < 3; ++o)
+		cudaFree(h->d_ola[o]);
+	cudaFree(h->d_mag_ring);
+	cudaFree(h->d_x_ring);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+}
+
+int zen_hpr_use_sse_filter(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	h->sse = true;
+	h->plan_dirty = true;
+	return ZEN_OK;
+}
+
+int zen_hpr_use_soft_mask(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	h->soft = true;
+	h->plan_dirty = true;
+	return ZEN_OK;
+}
+
+int zen_hpr_reset_buffers(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	const zen_geometry& g = h->plan.geom;
+	const int M = g.nfft / 2;
+	ZEN_CUDA_CHECK(cudaMemsetAsync(h->d_input, 0, sizeof(float) * g.nwin, h->stream));
+	for (int o = 0; o < 3; ++o)
+		ZEN_CUDA_CHECK(cudaMemsetAsync(h->d_ola[o], 0, sizeof(float) * g.nwin, h->stream));
+	ZEN_CUDA_CHECK(cudaMemsetAsync(h->d_mag_ring, 0, sizeof(float) * (size_t)g.stft_width * (M + 1), h->stream));
+	ZEN_CUDA_CHECK(cudaMemsetAsync(h->d_x_ring, 0, sizeof(float2) * (size_t)g.stft_width * (M + 1), h->stream));
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+	h->iter = 0;
+	return ZEN_OK;
+}
+
+int zen_hpr_get_geometry(const zen_hpr* h, zen_geometry* out)
+{
+	if (!h || !out) return ZEN_ERR_ARG;
+	*out = h->plan.geom;
+	return ZEN_OK;
+}
+
+int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* eh, float* ep, float* er)
+{
+	if (!h || !d_in_hop) return ZEN_ERR_ARG;
+	if (h->plan_dirty) {
+		int rc = rebuild_plan(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	switch (h->plan.nfft) {
+	case 128: return launch_hop<128>(h, d_in_hop, eh, ep, er);
+	case 256: return launch_hop<256>(h, d_in_hop, eh, ep, er);
+	case 512: return launch_hop<512>(h, d_in_hop, eh, ep, er);
+	case 1024: return launch_hop<1024>(h, d_in_hop, eh, ep, er);
+	case 2048: return launch_hop<2048>(h, d_in_hop, eh, ep, er);
+	case 4096: return launch_hop<4096>(h, d_in_hop, eh, ep, er);
+	case 8192: return launch_hop<8192>(h, d_in_hop, eh, ep, er);
+	case 16384: return launch_hop<16384>(h, d_in_hop, eh, ep, er);
+	}
+	return ZEN_ERR_UNSUPPORTED;
+}
+
+int zen_hpr_process_next_hop(zen_hpr* h, const float* d_in_hop)
+{
+	return zen_hpr_process_hop_io(h, d_in_hop, nullptr, nullptr, nullptr);
+}
+
+static int copy_out(zen_hpr* h, int o, float* d_out)
+{
+	if (!h || !d_out) return ZEN_ERR_ARG;
+	int hop = h->hop;
+	copy_hop_kernel<<<(hop + 255) / 256, 256, 0, h->stream>>>(h->d_ola[o], d_out, hop);
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+	return ZEN_OK;
+}
+
+int zen_hpr_copy_harmonic(zen_hpr* h, float* d_out) { return copy_out(h, 0, d_out); }
+int zen_hpr_copy_percussive(zen_hpr* h, float* d_out) { return copy_out(h, 1, d_out); }
+int zen_hpr_copy_residual(zen_hpr* h, float* d_out) { return copy_out(h, 2, d_out); }
+
+int zen_hpr_synchronize(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+	return ZEN_OK;
+}
+
+float* zen_hpr_state_ptr(zen_hpr* h, int which)
+{
+	if (!h) return nullptr;
+	switch (which) {
+	case 0: return h->d_input;
+	case 1: return h->d_ola[0];
+	case 2: return h->d_ola[1];
+	case 3: return h->d_ola[2];
+	case 4: return h->plan.d_window;
+	}
+	return nullptr;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------ debug-view materialise ---
+// The reference recomputes the whole stft_width x nfft matrices every hop and
+// exposes them as public members (hps.h:185-194); hps.test.cu style callers may
+// read them.  We rebuild them on demand from the ring state with the same
+// formulas, off the per-hop path.
+
+namespace {
+
+__global__ void expand_ring_kernel(const float2* __restrict__ x_ring, const float* __restrict__ mag_ring, long iter, int W, int M,
+                                   float2* __restrict__ stft, float* __restrict__ s_mag, float* __restrict__ recip, int sse)
+{
+	const int nfft = 2 * M;
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	const int row = blockIdx.y;
+	if (k >= nfft)
+		return;
+	const long j = (iter - 1) - (W - 1 - row);  // frame held by this row, newest frame in the last row
+	const int kk = k <= M ? k : nfft - k;
+	float2 X = make_float2(0.0f, 0.0f);
+	float m = 0.0f;
+	if (j >= 0) {
+		X = x_ring[(size_t)(j % W) * (M + 1) + kk];
+		if (k > M) X.y = -X.y;
+		m = mag_ring[(size_t)(j % W) * (M + 1) + kk];
+	}
+	const size_t idx = (size_t)row * nfft + k;
+	if (stft) stft[idx] = X;
+	if (s_mag) s_mag[idx] = m;
+	if (recip) recip[idx] = sse ? (1.0f / m) * 1.0f : 0.0f;
+}
+
+__global__ void scale_recip_kernel(float* __restrict__ m, size_t n, float factor)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		m[i] = (1.0f / m[i]) * factor;  // hps.h:45-56 reciprocal_functor
+}
+
+__global__ void mask_rows_kernel(const HprDev P, int nfft, const float* __restrict__ hm, const float* __restrict__ pm,
+                                 float* __restrict__ hmask, float* __restrict__ pmask, float* __restrict__ rmask)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nfft)
+		return;
+	const size_t off = (size_t)(P.W - P.lag) * nfft + k;
+	const float H = hm[off], Pv = pm[off];
+	float mp = 0.0f, mh = 0.0f;
+	if (P.sse) {
+		mp = mask_sse(Pv, H);
+		mh = mask_sse(H, Pv);
+	}
+	else if (P.soft) {
+		mp = mask_soft(Pv, H, P.power);
+		mh = mask_soft(H, Pv, P.power);
+	}
+	else {
+		mp = mask_hard(Pv, H, P.beta);
+		mh = mask_hard(H, Pv, P.beta_h);
+	}
+	if (!(P.out_flags & ZEN_OUTPUT_PERCUSSIVE)) mp = 0.0f;
+	if (!(P.out_flags & ZEN_OUTPUT_HARMONIC)) mh = 0.0f;
+	if (pmask) pmask[off] = mp;
+	if (hmask) hmask[off] = mh;
+	if (rmask && (P.out_flags & ZEN_OUTPUT_RESIDUAL) && !P.soft && !P.sse) {
+		// residual_mask is recomputed over the whole matrix (hps.cu:565-567); rows other
+		// than the consumed one only ever hold 1 - (0 + 0)
+		for (int r = 0; r < P.W; ++r)
+			rmask[(size_t)r * nfft + k] = r == P.W - P.lag ? 1.0f - (mh + mp) : 1.0f;
+	}
+}
+
+}  // namespace
+
+extern "C" int zen_hpr_materialize(zen_hpr* h, float* d_stft, float* d_s_mag, float* d_hm, float* d_pm,
+                                   float* d_hmask, float* d_pmask, float* d_rmask)
+{
+	if (!h)
+		return ZEN_ERR_ARG;
+	if (h->plan_dirty) {
+		int rc = rebuild_plan(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	const zen_geometry& g = h->plan.geom;
+	const int W = g.stft_width, nfft = g.nfft, M = nfft / 2;
+	const size_t n = (size_t)W * nfft;
+	const bool need_filters = d_hm || d_pm || d_hmask || d_pmask || d_rmask;
+	float *tmp_mag = nullptr, *tmp_rec = nullptr, *tmp_h = nullptr, *tmp_p = nullptr;
+	auto cleanup = [&]() { cudaFree(tmp_mag); cudaFree(tmp_rec); cudaFree(tmp_h); cudaFree(tmp_p); };
+	float* s_mag = d_s_mag;
+	if (!s_mag && need_filters) {
+		ZEN_CUDA_CHECK(cudaMalloc(&tmp_mag, sizeof(float) * n));
+		s_mag = tmp_mag;
+	}
+	if (h->sse && need_filters)
+		ZEN_CUDA_CHECK(cudaMalloc(&tmp_rec, sizeof(float) * n));
+	dim3 grid((nfft + 255) / 256, W);
+	expand_ring_kernel<<<grid, 256, 0, h->stream>>>(h->d_x_ring, h->d_mag_ring, h->iter, W, M, reinterpret_cast<float2*>(d_stft),
+	                                               s_mag, tmp_rec, h->sse ? 1 : 0);
+	int rc = ZEN_OK;
+	if (need_filters) {
+		float* hm = d_hm;
+		float* pm = d_pm;
+		if (!hm) {
+			if (cudaMalloc(&tmp_h, sizeof(float) * n) != cudaSuccess || cudaMemsetAsync(tmp_h, 0, sizeof(float) * n, h->stream) != cudaSuccess) {
+				cleanup();
+				return ZEN_ERR_CUDA;
+			}
+			hm = tmp_h;
+		}
+		if (!pm) {
+			if (cudaMalloc(&tmp_p, sizeof(float) * n) != cudaSuccess || cudaMemsetAsync(tmp_p, 0, sizeof(float) * n, h->stream) != cudaSuccess) {
+				cleanup();
+				return ZEN_ERR_CUDA;
+			}
+			pm = tmp_p;
+		}
+		if (!h->sse) {
+			rc = zen_median_filter(W, nfft, g.l_harm, h->causality, h->copy_bord, s_mag, hm, h->stream);
+			if (rc == ZEN_OK)
+				rc = zen_median_filter(W, nfft, g.l_perc, ZEN_FREQUENCY, h->copy_bord, s_mag, pm, h->stream);
+		}
+		else {
+			rc = zen_box_filter(W, nfft, g.l_harm, h->causality, tmp_rec, hm, h->stream);
+			if (rc == ZEN_OK)
+				rc = zen_box_filter(W, nfft, g.l_perc, ZEN_FREQUENCY, tmp_rec, pm, h->stream);
+			if (rc == ZEN_OK) {
+				scale_recip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(pm, n, (float)g.l_perc + 1.0f);
+				scale_recip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(hm, n, (float)g.l_harm + 1.0f);
+			}
+		}
+		if (rc == ZEN_OK && (d_hmask || d_pmask || d_rmask))
+			mask_rows_kernel<<<(nfft + 255) / 256, 256, 0, h->stream>>>(h->plan.dev, nfft, hm, pm, d_hmask, d_pmask, d_rmask);
+	}
+	cudaError_t e = cudaStreamSynchronize(h->stream);
+	cleanup();
+	if (e != cudaSuccess || cudaGetLastError() != cudaSuccess)
+		return ZEN_ERR_CUDA;
+	return rc;
+}
+
+// --------------------------------------------------------------- batched ---
+
+struct zen_hpr_batch {
+	Plan plan;
+	int max_streams;
+	long max_hops;
+	int tile_hops;
+	float* d_scratch = nullptr;
+	size_t scratch_ctas = 0;
+	long last_launches = 0;
+	float last_kernel_ms = 0.0f;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// host pipeline
+	cudaStream_t streams[2] = {nullptr, nullptr};
+	float* d_stage_in[2] = {nullptr, nullptr};
+	float* d_stage_out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+	int stage_streams = 0;
+};
+
+namespace {
+
+// tile length: enough CTAs to fill the GPU a few times over, but long enough
+// that the W-hop halo stays a small fraction of the work
+int choose_tile_hops(const Plan& pl, int n_streams, long n_hops)
+{
+	int sms = 148;
+	int dev = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess) {
+		int v = 0;
+		if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+			sms = v;
+	}
+	const long target_ctas = 8L * sms;
+	long min_tile = 8L * pl.dev.W;  // halo <= 12.5 % of the tile
+	if (min_tile < 16) min_tile = 16;
+	long tiles_wanted = (target_ctas + n_streams - 1) / n_streams;
+	if (tiles_wanted < 1) tiles_wanted = 1;
+	long tile = (n_hops + tiles_wanted - 1) / tiles_wanted;
+	if (tile < min_tile) tile = min_tile;
+	if (tile > n_hops) tile = n_hops;
+	if (tile < 1) tile = 1;
+	return (int)tile;
+}
+
+int ensure_scratch(zen_hpr_batch* b, size_t ctas)
+{
+	if (ctas <= b->scratch_ctas)
+		return ZEN_OK;
+	cudaFree(b->d_scratch);
+	b->d_scratch = nullptr;
+	b->scratch_ctas = 0;
+	ZEN_CUDA_CHECK(cudaMalloc(&b->d_scratch, sizeof(float) * tile_scratch_floats(b->plan) * ctas));
+	b->scratch_ctas = ctas;
+	return ZEN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int zen_hpr_batch_create(zen_hpr_batch** out, float fs, int hop, float beta, unsigned flags, int causality,
+                         int options, int max_streams, long max_hops)
+{
+	if (!out || max_streams < 1 || max_hops < 1)
+		return ZEN_ERR_ARG;
+	*out = nullptr;
+	if (zen_device_count() <= 0)
+		return ZEN_ERR_CUDA;
+	zen_hpr_batch* b = new (std::nothrow) zen_hpr_batch();
+	if (!b)
+		return ZEN_ERR_ARG;
+	int rc = build_plan(b->plan, fs, hop, beta, flags, causality, !(options & ZEN_OPT_NOCOPYBORD),
+	                    (options & ZEN_OPT_SSE) != 0, (options & ZEN_OPT_SOFT_MASK) != 0);
+	if (rc != ZEN_OK) {
+		free_plan(b->plan);
+		delete b;
+		return rc;
+	}
+	b->max_streams = max_streams;
+	b->max_hops = max_hops;
+	cudaEventCreate(&b->ev0);
+	cudaEventCreate(&b->ev1);
+	*out = b;
+	return ZEN_OK;
+}
+
+void zen_hpr_batch_destroy(zen_hpr_batch* b)
+{
+	if (!b)
+		return;
+	free_plan(b->plan);
+	cudaFree(b->d_scratch);
+	for (int s = 0; s < 2; ++s) {
+		cudaFree(b->d_stage_in[s]);
+		for (int o = 0; o < 3; ++o)
+			cudaFree(b->d_stage_out[s][o]);
+		if (b->streams[s]) cudaStreamDestroy(b->streams[s]);
+	}
+	if (b->ev0) cudaEventDestroy(b->ev0);
+	if (b->ev1) cudaEventDestroy(b->ev1);
+	delete b;
+}
+
+int zen_hpr_batch_process(zen_hpr_batch* b, const float* d_in, long in_stride, int n_streams, long n_hops,
+                          float* d_out_h, float* d_out_p, float* d_out_r, long out_stride, void* cuda_stream)
+{
+	if (!b || !d_in || n_streams < 1 || n_hops < 1)
+		return ZEN_ERR_ARG;
+	if ((in_stride & 1) || (out_stride & 1) || ((uintptr_t)d_in & 7))
+		return ZEN_ERR_ARG;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	int tile = choose_tile_hops(b->plan, n_streams, n_hops);
+	b->tile_hops = tile;
+	long n_tiles = (n_hops + tile - 1) / tile;
+	int rc = ensure_scratch(b, (size_t)n_tiles * n_streams);
+	if (rc != ZEN_OK)
+		return rc;
+	const unsigned f = b->plan.dev.out_flags;
+	cudaEventRecord(b->ev0, s);
+	rc = dispatch_tile(b->plan, d_in, in_stride, (f & 1) ? d_out_h : nullptr, (f & 2) ? d_out_p : nullptr,
+	                   (f & 4) ? d_out_r : nullptr, out_stride, n_streams, n_hops, tile, b->d_scratch, s);
+	cudaEventRecord(b->ev1, s);
+	b->last_launches = 1;
+	return rc;
+}
+
+long zen_hpr_batch_last_launches(const zen_hpr_batch* b) { return b ? b->last_launches : 0; }
+
+float zen_hpr_batch_last_kernel_ms(const zen_hpr_batch* b)
+{
+	if (!b)
+		return 0.0f;
+	float ms = 0.0f;
+	if (cudaEventSynchronize(b->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess)
+		return -1.0f;
+	return ms;
+}
+
+int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stride, int n_streams, long n_hops,
+                               float* h_out_h, float* h_out_p, float* h_out_r, long out_stride)
+{
+	if (!b || !h_in || n_streams < 1 || n_hops < 1)
+		return ZEN_ERR_ARG;
+	const int hop = b->plan.dev.hop;
+	const size_t row = (size_t)n_hops * hop;
+	const unsigned f = b->plan.dev.out_flags;
+	float* h_out[3] = {(f & 1) ? h_out_h : nullptr, (f & 2) ? h_out_p : nullptr, (f & 4) ? h_out_r : nullptr};
+	// chunk so that one chunk's input is ~256 MB
+	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, ((size_t)256 << 20) / (row * sizeof(float)) + 1));
+	if (chunk > b->stage_streams) {
+		for (int s = 0; s < 2; ++s) {
+			cudaFree(b->d_stage_in[s]);
+			b->d_stage_in[s] = nullptr;
+			for (int o = 0; o < 3; ++o) {
+				cudaFree(b->d_stage_out[s][o]);
+				b->d_stage_out[s][o] = nullptr;
+			}
+			if (!b->streams[s]) ZEN_CUDA_CHECK(cudaStreamCreateWithFlags(&b->streams[s], cudaStreamNonBlocking));
+			ZEN_CUDA_CHECK(cudaMalloc(&b->d_stage_in[s], row * sizeof(float) * chunk));
+			for (int o = 0; o < 3; ++o)
+				if (h_out[o]) ZEN_CUDA_CHECK(cudaMalloc(&b->d_stage_out[s][o], row * sizeof(float) * chunk));
+		}
+		b->stage_streams = chunk;
+	}
+	int tile = choose_tile_hops(b->plan, chunk, n_hops);
+	b->tile_hops = tile;
+	long n_tiles = (n_hops + tile - 1) / tile;
+	// both pipeline slots run concurrently: separate scratch halves
+	int rc = ensure_scratch(b, 2 * (size_t)n_tiles * chunk);
+	if (rc != ZEN_OK)
+		return rc;
+	const size_t scratch_half = tile_scratch_floats(b->plan) * (size_t)n_tiles * chunk;
+	long launches = 0;
+	int slot = 0;
+	for (int s0 = 0; s0 < n_streams; s0 += chunk, slot ^= 1) {
+		const int ns = std::min(chunk, n_streams - s0);
+		cudaStream_t st = b->streams[slot];
+		ZEN_CUDA_CHECK(cudaMemcpy2DAsync(b->d_stage_in[slot], row * sizeof(float), h_in + (size_t)s0 * in_stride,
+		                                 (size_t)in_stride * sizeof(float), row * sizeof(float), ns,
+		                                 cudaMemcpyHostToDevice, st));
+		rc = dispatch_tile(b->plan, b->d_stage_in[slot], (long)row, b->d_stage_out[slot][0], b->d_stage_out[slot][1],
+		                   b->d_stage_out[slot][2], (long)row, ns, n_hops, tile, b->d_scratch + slot * scratch_half, st);
+		if (rc != ZEN_OK)
+			return rc;
+		++launches;
+		for (int o = 0; o < 3; ++o)
+			if (h_out[o])
+				ZEN_CUDA_CHECK(cudaMemcpy2DAsync(h_out[o] + (size_t)s0 * out_stride, (size_t)out_stride * sizeof(float),
+				                                 b->d_stage_out[slot][o], row * sizeof(float), row * sizeof(float), ns,
+				                                 cudaMemcpyDeviceToHost, st));
+	}
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(b->streams[0]));
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(b->streams[1]));
+	b->last_launches = launches;
+	return ZEN_OK;
+}
+
+// ---------------------------------------------------------------- offline ---
+
+static int chunk_padder(long size, int hop, int lag, long* padded)
+{
+	// hps.cu:109-126, chunk count evaluated in float as written
+	int n_chunks = (int)std::ceil((float)size / (float)hop);
+	long pad = (long)n_chunks * hop - size;
+	pad += (long)lag * hop;
+	n_chunks += lag;
+	*padded = size + pad;
+	return n_chunks;
+}
+
+int zen_offline_process_device(float fs, int hop_h, int hop_p, float beta_h, float beta_p, int options,
+                               const float* d_audio, long n, float* d_h, float* d_p, float* d_r, void* cuda_stream)
+{
+	if (!d_audio || n < 1 || !d_h || !d_p || !d_r)
+		return ZEN_ERR_ARG;
+	if (hop_p <= 0 || hop_h % hop_p != 0)  // hps.cu:33-36
+		return ZEN_ERR_GEOMETRY;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	const int opt = options;
+	zen_hpr_batch *bh = nullptr, *bp = nullptr;
+	int rc = zen_hpr_batch_create(&bh, fs, hop_h, beta_h, ZEN_OUTPUT_HARMONIC | ZEN_OUTPUT_PERCUSSIVE | ZEN_OUTPUT_RESIDUAL,
+	                              ZEN_TIME_ANTICAUSAL, opt, 1, 1);
+	if (rc == ZEN_OK)
+		rc = zen_hpr_batch_create(&bp, fs, hop_p, beta_p, ZEN_OUTPUT_PERCUSSIVE, ZEN_TIME_ANTICAUSAL, opt, 1, 1);
+	float *a1 = nullptr, *h1 = nullptr, *p1 = nullptr, *r1 = nullptr, *a2 = nullptr, *p2 = nullptr;
+	auto cleanup = [&]() {
+		cudaFree(a1); cudaFree(h1); cudaFree(p1); cudaFree(r1); cudaFree(a2); cudaFree(p2);
+		zen_hpr_batch_destroy(bh);
+		zen_hpr_batch_destroy(bp);
+	};
+	if (rc != ZEN_OK) {
+		cleanup();
+		return rc;
+	}
+	long padded1 = 0, padded2 = 0;
+	const int n1 = chunk_padder(n, hop_h, bh->plan.geom.lag, &padded1);
+	const int n2 = chunk_padder(n, hop_p, bp->plan.geom.lag, &padded2);
+	const long shift1 = (long)bh->plan.geom.lag * hop_h, shift2 = (long)bp->plan.geom.lag * hop_p;
+	cudaError_t e = cudaMalloc(&a1, sizeof(float) * padded1);
+	if (e == cudaSuccess) e = cudaMalloc(&h1, sizeof(float) * padded1);
+	if (e == cudaSuccess) e = cudaMalloc(&p1, sizeof(float) * padded1);
+	if (e == cudaSuccess) e = cudaMalloc(&r1, sizeof(float) * padded1);
+	if (e == cudaSuccess) e = cudaMalloc(&a2, sizeof(float) * padded2);
+	if (e == cudaSuccess) e = cudaMalloc(&p2, sizeof(float) * padded2);
+	if (e == cudaSuccess) e = cudaMemsetAsync(a1, 0, sizeof(float) * padded1, s);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(a1, d_audio, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
+	// the soft-mask / SSE variants never write the residual: it stays zero (hps.cu:562)
+	if (e == cudaSuccess) e = cudaMemsetAsync(r1, 0, sizeof(float) * padded1, s);
+	if (e != cudaSuccess) {
+		std::fprintf(stderr, "zen_b200: offline allocation failed: %s\n", cudaGetErrorString(e));
+		cleanup();
+		return ZEN_ERR_CUDA;
+	}
+	rc = zen_hpr_batch_process(bh, a1, padded1, 1, n1, h1, p1, r1, padded1, s);
+	if (rc == ZEN_OK) {
+		offline_intermediate_kernel<<<(unsigned)((padded2 + 255) / 256), 256, 0, s>>>(p1, r1, a2, padded1, shift1, padded2);
+		rc = zen_hpr_batch_process(bp, a2, padded2, 1, n2, nullptr, p2, nullptr, padded2, s);
+	}
+	if (rc == ZEN_OK) {
+		e = cudaMemcpyAsync(d_h, h1 + shift1, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_p, p2 + shift2, sizeof(float) * n, cudaMemcpyDeviceToDevice, s);
+		if (e == cudaSuccess) e = cudaMemsetAsync(d_r, 0, sizeof(float) * n, s);  // hps.cu:200-204, 219-220
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess) {
+			std::fprintf(stderr, "zen_b200: offline failed: %s\n", cudaGetErrorString(e));
+			rc = ZEN_ERR_CUDA;
+		}
+	}
+	cleanup();
+	return rc;
+}
+
+int zen_offline_process(float fs, int hop_h, int hop_p, float beta_h, float beta_p, int options,
+                        const float* h_audio, long n, float* h_h, float* h_p, float* h_r)
+{
+	if (!h_audio || n < 1 || !h_h || !h_p || !h_r)
+		return ZEN_ERR_ARG;
+	if (hop_p <= 0 || hop_h % hop_p != 0)
+		return ZEN_ERR_GEOMETRY;
+	if (zen_device_count() <= 0)
+		return ZEN_ERR_CUDA;
+	float* d = nullptr;
+	ZEN_CUDA_CHECK(cudaMalloc(&d, sizeof(float) * 4 * (size_t)n));
+	cudaError_t e = cudaMemcpy(d, h_audio, sizeof(float) * n, cudaMemcpyHostToDevice);
+	int rc = e == cudaSuccess ? zen_offline_process_device(fs, hop_h, hop_p, beta_h, beta_p, options, d, n, d + n, d + 2 * n,
+	                                                      d + 3 * n, nullptr)
+	                          : ZEN_ERR_CUDA;
+	if (rc == ZEN_OK) {
+		e = cudaMemcpy(h_h, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess) e = cudaMemcpy(h_p, d + 2 * n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess) e = cudaMemcpy(h_r, d + 3 * n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+		if (e != cudaSuccess) rc = ZEN_ERR_CUDA;
+	}
+	cudaFree(d);
+	return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,336 @@
+"""Host-side mirror of the libzen API for the HPR path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference classes
+(libzen/libzen/hps.h, libzen/libzen/io.h, libzen/mfilt.h, box.h, fftw.h, win.h)
+so the parity tests read like the reference's own tests.  Device memory is
+held in torch CUDA tensors; every computation happens in libzen_b200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (OUTPUT_HARMONIC, OUTPUT_PERCUSSIVE, OUTPUT_RESIDUAL, ZgException,  # noqa: F401
+                   check)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.ZenCudaError("zen_b200 needs a CUDA device; there is no CPU fallback")
+    return torch
+
+
+def _dptr(x):
+    """device pointer of a torch tensor, or pass an int address through"""
+    if isinstance(x, int):
+        return x
+    return x.data_ptr()
+
+
+class MedianFilterDirection:
+    TimeCausal, TimeAnticausal, Frequency = 0, 1, 2
+
+
+def hpr_geometry(fs, hop, causal):
+    g = _lib.ZenGeometry()
+    check(_lib.lib().zen_hpr_geometry(fs, hop, int(causal), ctypes.byref(g)), "zen_hpr_geometry")
+    return g
+
+
+def window(n, sqrt=True):
+    """Window<T> (libzen/win.h:21-53)."""
+    w = np.zeros(n, dtype=np.float32)
+    check(_lib.lib().zen_window(0 if sqrt else 1, n, w.ctypes.data), "zen_window")
+    return w
+
+
+class IOGPU:
+    """zen::io::IOGPU (libzen/libzen/io.h:16-81): mapped pinned in/out buffers."""
+
+    def __init__(self, size):
+        self._io = _lib.ZenIO()
+        check(_lib.lib().zen_io_alloc(ctypes.byref(self._io), size), "zen_io_alloc")
+        self.size = size
+        self.host_in = np.ctypeslib.as_array(ctypes.cast(self._io.host_in, ctypes.POINTER(ctypes.c_float)), (size,))
+        self.host_out = np.ctypeslib.as_array(ctypes.cast(self._io.host_out, ctypes.POINTER(ctypes.c_float)), (size,))
+        self.device_in = self._io.device_in
+        self.device_out = self._io.device_out
+
+    def close(self):
+        if self._io is not None:
+            self.host_in = self.host_out = None
+            _lib.lib().zen_io_free(ctypes.byref(self._io))
+            self._io = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class MedianFilterGPU:
+    """libzen/mfilt.h:33-268.  filter(src, dst) on time x freq float32 CUDA tensors."""
+
+    def __init__(self, time, frequency, filter_len, direction, copy_bord=False):
+        if ((direction in (0, 1) and filter_len > time) or (direction == 2 and filter_len > frequency)):
+            raise ZgException("median filter bigger than matrix dimension")
+        self.time, self.frequency, self.filter_len = time, frequency, filter_len
+        self.mydir, self.copy_bord = direction, bool(copy_bord)
+
+    def filter(self, src, dst):
+        check(_lib.lib().zen_median_filter(self.time, self.frequency, self.filter_len, self.mydir, int(self.copy_bord),
+                                           _dptr(src), _dptr(dst), None), "zen_median_filter")
+
+
+class BoxFilterGPU:
+    """libzen/box.h:30-215."""
+
+    def __init__(self, time, frequency, filter_len, direction):
+        if ((direction in (0, 1) and filter_len > time) or (direction == 2 and filter_len > frequency)):
+            raise ZgException("box filter bigger than matrix dimension")
+        self.time, self.frequency, self.filter_len, self.mydir = time, frequency, filter_len, direction
+
+    def filter(self, src, dst):
+        check(_lib.lib().zen_box_filter(self.time, self.frequency, self.filter_len, self.mydir, _dptr(src), _dptr(dst), None),
+              "zen_box_filter")
+
+
+class FFTC2CWrapperGPU:
+    """libzen/fftw.h:20-49: owns fft_vec (complex64 CUDA tensor), in-place forward()/backward()."""
+
+    def __init__(self, nfft):
+        torch = _torch()
+        self.nfft = nfft
+        self.fft_vec = torch.zeros(nfft, dtype=torch.complex64, device="cuda")
+
+    def forward(self):
+        check(_lib.lib().zen_fft_c2c(self.nfft, self.fft_vec.data_ptr(), 0, None), "zen_fft_c2c")
+
+    def backward(self):
+        check(_lib.lib().zen_fft_c2c(self.nfft, self.fft_vec.data_ptr(), 1, None), "zen_fft_c2c")
+
+
+class HPR:
+    """zen::internal::hps::HPR<Backend::GPU> (libzen/hps.h:152-322)."""
+
+    def __init__(self, fs, hop, beta, output_flags, causality, copy_bord):
+        h = ctypes.c_void_p()
+        check(_lib.lib().zen_hpr_create(ctypes.byref(h), fs, hop, beta, output_flags, causality, int(copy_bord)), "zen_hpr_create")
+        self._h = h
+        g = _lib.ZenGeometry()
+        check(_lib.lib().zen_hpr_get_geometry(self._h, ctypes.byref(g)), "zen_hpr_get_geometry")
+        self.fs, self.hop, self.nwin, self.nfft, self.beta = fs, g.hop, g.nwin, g.nfft, beta
+        self.l_harm, self.l_perc, self.lag, self.stft_width = g.l_harm, g.l_perc, g.lag, g.stft_width
+        self.COLA_factor = g.cola_factor
+        self.output_harmonic = bool(output_flags & OUTPUT_HARMONIC)
+        self.output_percussive = bool(output_flags & OUTPUT_PERCUSSIVE)
+        self.output_residual = bool(output_flags & OUTPUT_RESIDUAL)
+        self.use_sse = self.soft_mask = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().zen_hpr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def use_sse_filter(self):
+        self.use_sse = True
+        check(_lib.lib().zen_hpr_use_sse_filter(self._h), "use_sse_filter")
+
+    def use_soft_mask(self):
+        self.soft_mask = True
+        check(_lib.lib().zen_hpr_use_soft_mask(self._h), "use_soft_mask")
+
+    def reset_buffers(self):
+        check(_lib.lib().zen_hpr_reset_buffers(self._h), "reset_buffers")
+
+    def process_next_hop(self, in_hop):
+        check(_lib.lib().zen_hpr_process_next_hop(self._h, _dptr(in_hop)), "process_next_hop")
+
+    def process_hop_io(self, in_hop, out_h=None, out_p=None, out_r=None):
+        check(_lib.lib().zen_hpr_process_hop_io(self._h, _dptr(in_hop), _dptr(out_h) if out_h is not None else None,
+                                                _dptr(out_p) if out_p is not None else None,
+                                                _dptr(out_r) if out_r is not None else None), "process_hop_io")
+
+    def synchronize(self):
+        check(_lib.lib().zen_hpr_synchronize(self._h), "synchronize")
+
+    def _state(self, which, n):
+        self.synchronize()
+        out = np.empty(n, dtype=np.float32)
+        ptr = _lib.lib().zen_hpr_state_ptr(self._h, which)
+        check(_lib.lib().zen_copy_to_host(out.ctypes.data, ptr, out.nbytes), "zen_copy_to_host")
+        return out
+
+    # the reference exposes these as public device_vectors (hps.h:182-197)
+    @property
+    def input(self):
+        return self._state(0, self.nwin)
+
+    @property
+    def harmonic_out(self):
+        return self._state(1, self.nwin)
+
+    @property
+    def percussive_out(self):
+        return self._state(2, self.nwin)
+
+    @property
+    def residual_out(self):
+        return self._state(3, self.nwin)
+
+    def materialize(self):
+        """dict of the reference's stft_width x nfft matrices, rebuilt from the ring state"""
+        torch = _torch()
+        n = self.stft_width * self.nfft
+        names = ["sliding_stft", "s_mag", "harmonic_matrix", "percussive_matrix", "harmonic_mask", "percussive_mask",
+                 "residual_mask"]
+        bufs = [torch.zeros(2 * n if nm == "sliding_stft" else n, dtype=torch.float32, device="cuda") for nm in names]
+        check(_lib.lib().zen_hpr_materialize(self._h, *[b.data_ptr() for b in bufs]), "zen_hpr_materialize")
+        out = {}
+        for nm, b in zip(names, bufs):
+            a = b.cpu().numpy()
+            out[nm] = a.view(np.complex64).reshape(self.stft_width, self.nfft) if nm == "sliding_stft" else a.reshape(
+                self.stft_width, self.nfft)
+        return out
+
+    def run(self, audio, n_hops=None):
+        """tests helper: feed host audio hop by hop, collect the first hop samples of each output"""
+        torch = _torch()
+        a = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).cuda()
+        if n_hops is None:
+            n_hops = a.numel() // self.hop
+        outs = [torch.zeros(n_hops * self.hop, dtype=torch.float32, device="cuda") for _ in range(3)]
+        hop = self.hop
+        for i in range(n_hops):
+            self.process_hop_io(a[i * hop:].data_ptr(), outs[0][i * hop:].data_ptr(), outs[1][i * hop:].data_ptr(),
+                                outs[2][i * hop:].data_ptr())
+        self.synchronize()
+        return [o.cpu().numpy() for o in outs]
+
+
+class HPRRealtime:
+    """zen::hps::HPRRealtime<Backend::GPU> (libzen/libzen/hps.h:74-118, libzen/hps.cu:282-427)."""
+
+    def __init__(self, fs, hop=256, beta=2.0, output_flags=OUTPUT_PERCUSSIVE, nocopybord=False):
+        self.p_impl = HPR(fs, hop, beta, output_flags, MedianFilterDirection.TimeCausal, not nocopybord)
+
+    def process_next_hop(self, in_hop):
+        self.p_impl.process_next_hop(in_hop)
+
+    def copy_harmonic(self, out_hop):
+        check(_lib.lib().zen_hpr_copy_harmonic(self.p_impl._h, _dptr(out_hop)), "copy_harmonic")
+
+    def copy_percussive(self, out_hop):
+        check(_lib.lib().zen_hpr_copy_percussive(self.p_impl._h, _dptr(out_hop)), "copy_percussive")
+
+    def copy_residual(self, out_hop):
+        check(_lib.lib().zen_hpr_copy_residual(self.p_impl._h, _dptr(out_hop)), "copy_residual")
+
+    def use_sse_filter(self):
+        self.p_impl.use_sse_filter()
+
+    def use_soft_mask(self):
+        self.p_impl.use_soft_mask()
+
+    def warmup(self, io, test_iters=1000):
+        """hps.cu:392-409: 1000 hops of iota data, then reset_buffers()."""
+        hop = self.p_impl.hop
+        for i in range(test_iters):
+            io.host_in[:hop] = np.arange(i * hop, (i + 1) * hop, dtype=np.float32)
+            self.p_impl.process_next_hop(io.device_in)
+        self.p_impl.synchronize()
+        self.p_impl.reset_buffers()
+
+
+class HPRIOffline:
+    """zen::hps::HPRIOffline<Backend::GPU> (libzen/libzen/hps.h:29-72, libzen/hps.cu:21-221)."""
+
+    def __init__(self, fs, hop_h=4096, hop_p=256, beta_h=2.0, beta_p=2.0, nocopybord=False):
+        if hop_h % hop_p != 0:
+            raise ZgException("hop_h and hop_p should be evenly divisible")
+        self.fs, self.hop_h, self.hop_p, self.beta_h, self.beta_p = fs, hop_h, hop_p, beta_h, beta_p
+        self.options = _lib.OPT_NOCOPYBORD if nocopybord else 0
+
+    def use_sse_filter(self):
+        self.options |= _lib.OPT_SSE
+
+    def use_soft_mask(self):
+        self.options |= _lib.OPT_SOFT_MASK
+
+    def process(self, audio):
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        outs = [np.zeros(a.size, dtype=np.float32) for _ in range(3)]
+        check(_lib.lib().zen_offline_process(self.fs, self.hop_h, self.hop_p, self.beta_h, self.beta_p, self.options,
+                                             a.ctypes.data, a.size, *[o.ctypes.data for o in outs]), "zen_offline_process")
+        return outs
+
+    def process_device(self, audio_t):
+        """device-resident variant: float32 CUDA tensor in, three CUDA tensors out"""
+        torch = _torch()
+        n = audio_t.numel()
+        outs = [torch.empty(n, dtype=torch.float32, device=audio_t.device) for _ in range(3)]
+        check(_lib.lib().zen_offline_process_device(self.fs, self.hop_h, self.hop_p, self.beta_h, self.beta_p, self.options,
+                                                    audio_t.data_ptr(), n, *[o.data_ptr() for o in outs],
+                                                    torch.cuda.current_stream().cuda_stream), "zen_offline_process_device")
+        return outs
+
+
+class HPRBatch:
+    """Many independent HPRRealtime / HPR streams in one launch (zen_hpr_batch_*)."""
+
+    def __init__(self, fs, hop, beta, output_flags, causal=True, nocopybord=False, sse=False, soft=False):
+        opts = (_lib.OPT_NOCOPYBORD if nocopybord else 0) | (_lib.OPT_SSE if sse else 0) | (_lib.OPT_SOFT_MASK if soft else 0)
+        b = ctypes.c_void_p()
+        check(_lib.lib().zen_hpr_batch_create(ctypes.byref(b), fs, hop, beta, output_flags,
+                                              _lib.TIME_CAUSAL if causal else _lib.TIME_ANTICAUSAL, opts, 1, 1),
+              "zen_hpr_batch_create")
+        self._b = b
+        self.hop, self.flags = hop, output_flags
+
+    def close(self):
+        if getattr(self, "_b", None):
+            _lib.lib().zen_hpr_batch_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def process(self, x, outs=None):
+        """x: [n_streams, n_hops*hop] float32 CUDA tensor. Returns (H, P, R) tensors (None where disabled)."""
+        torch = _torch()
+        n_streams, n = x.shape
+        n_hops = n // self.hop
+        if outs is None:
+            outs = [torch.empty_like(x) if self.flags & (1 << o) else None for o in range(3)]
+        ptr = [o.data_ptr() if o is not None else None for o in outs]
+        check(_lib.lib().zen_hpr_batch_process(self._b, x.data_ptr(), x.stride(0), n_streams, n_hops, ptr[0], ptr[1], ptr[2],
+                                               x.stride(0), torch.cuda.current_stream().cuda_stream), "zen_hpr_batch_process")
+        return outs
+
+    def process_host(self, x, outs):
+        """x, outs[*]: [n_streams, n_hops*hop] float32 host arrays (numpy or pinned torch tensors)."""
+        def addr(a):
+            return None if a is None else (a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        n_streams, n = x.shape
+        n_hops = n // self.hop
+        check(_lib.lib().zen_hpr_batch_process_host(self._b, addr(x), n, n_streams, n_hops, addr(outs[0]), addr(outs[1]),
+                                                    addr(outs[2]), n), "zen_hpr_batch_process_host")
+
+    @property
+    def last_kernel_ms(self):
+        return float(_lib.lib().zen_hpr_batch_last_kernel_ms(self._b))
+
+    @property
+    def last_launches(self):
+        return int(_lib.lib().zen_hpr_batch_last_launches(self._b))
