@@ -46,6 +46,9 @@ const char* zen_b200_version(void);
 /* number of usable CUDA devices (0 => every compute call fails with ZEN_ERR_CUDA) */
 int zen_device_count(void);
 
+/* page-locked host memory (cudaHostAlloc / cudaFreeHost); NULL on failure */
+void* zen_host_alloc(size_t bytes);
+void zen_host_free(void* p);
 /* synchronous cudaMemcpy wrappers for hosts without their own CUDA runtime binding */
 int zen_copy_to_host(void* h_dst, const void* d_src, size_t bytes);
 int zen_copy_to_device(void* d_dst, const void* h_src, size_t bytes);
@@ -124,6 +127,15 @@ float* zen_hpr_state_ptr(zen_hpr* h, int which);
 int zen_hpr_materialize(zen_hpr* h, float* d_sliding_stft, float* d_s_mag, float* d_harmonic_matrix,
                         float* d_percussive_matrix, float* d_harmonic_mask, float* d_percussive_mask,
                         float* d_residual_mask);
+
+/* ---- the real-time loop of `zen fakert` (zen/fakert.h:197-256) ----
+ * HPRRealtime<GPU>(fs, hop, beta, OUTPUT_PERCUSSIVE) + IOGPU(hop); warmup_iters
+ * hops of iota data then reset (hps.cu:392-409); then per hop the region the
+ * reference times: host copy-in -> process_next_hop -> copy_percussive -> host
+ * copy-out.  fused != 0 replaces the two calls by zen_hpr_process_hop_io.
+ * h_us_per_hop (optional) receives the wall time of each hop in microseconds. */
+int zen_fakert_run(float fs, int hop, float beta, int options, const float* h_audio, long n_hops,
+                   int warmup_iters, int fused, float* h_perc_out, double* h_us_per_hop);
 
 /* ---- batched streams: many independent HPRRealtime<GPU> streams at once ----
  * Equivalent to running, for every stream s, n_hops calls of

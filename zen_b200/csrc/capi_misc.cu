@@ -88,6 +88,22 @@ void zen_io_free(zen_io* io)
 	std::memset(io, 0, sizeof(*io));
 }
 
+// pinned (page-locked) host memory for the host-buffer entry points
+void* zen_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void zen_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
 // plain synchronous copies for hosts that have no CUDA runtime binding of their own
 int zen_copy_to_host(void* h_dst, const void* d_src, size_t bytes)
 {

@@ -24,7 +24,8 @@ constexpr int ZEN_MAX_TAPS = 128;
 struct HprDev {
 	int hop, W, lag;
 	int n_taps;          // time-axis taps (0: the reference never writes the consumed row -> H = 0)
-	int Lp, midp, Kp;    // frequency window (odd), its half, registers per lane of the sliding window
+	int Lp, midp, Kp;    // frequency window (odd), its half, registers per lane of the warp-resident sliding window
+	int Cp;              // register capacity of the per-thread sliding window (0: use the warp-resident one)
 	int copy_bord;       // frequency windows centred+circular (1) or forward-looking (0)
 	int out_flags, soft, sse;
 	float power;         // (float)(int)beta, soft-mask exponent (hps.h:116-129)
@@ -241,12 +242,20 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 
 	// ---- E. frequency axis: prow[s] = median / mean of erow[s .. s+Lp)
 	if (!P.sse) {
-		constexpr int NW = NT / 32;
-		const int wid = tid >> 5, lane = tid & 31;
-		const int R = (M + 1 + NW - 1) / NW;
-		const int s0 = wid * R;
-		const int s1 = min(M + 1, s0 + R);
-		warp_sliding_median_dyn<float>(P.Kp, sm.erow, sm.prow, s0, s1, P.Lp, lane);
+		if (P.Cp > 0) {
+			const int R = (M + 1 + NT - 1) / NT;
+			const int s0 = tid * R;
+			const int s1 = min(M + 1, s0 + R);
+			thread_sliding_median_dyn(P.Cp, sm.erow, sm.prow, s0, s1, P.Lp);
+		}
+		else {
+			constexpr int NW = NT / 32;
+			const int wid = tid >> 5, lane = tid & 31;
+			const int R = (M + 1 + NW - 1) / NW;
+			const int s0 = wid * R;
+			const int s1 = min(M + 1, s0 + R);
+			warp_sliding_median_dyn<float>(P.Kp, sm.erow, sm.prow, s0, s1, P.Lp, lane);
+		}
 	}
 	else {
 		for (int k = tid; k <= M; k += NT) {

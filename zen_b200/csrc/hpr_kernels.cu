@@ -7,101 +7,9 @@
 #include <new>
 #include <vector>
 
-#include "hpr_core.cuh"
+#include "hpr_launch.cuh"
 
 using namespace zen_b200;
-
-// ----------------------------------------------------------------- kernels ---
-
-// One CTA = one stream x one tile of consecutive hops.  The CTA walks its hops
-// in order; the W-1 hops before the tile are analysed only (ring fill) and the
-// hop just before the tile is synthesised without being emitted (its second
-// half is the first overlap-add tail of the tile).  Frames are independent
-// given that halo, so tiles need no communication.
-template <int NFFT, int NT>
-__global__ void __launch_bounds__(NT) hpr_tile_kernel(const __grid_constant__ HprDev P,
-                                                      const float* __restrict__ in, long in_stride,
-                                                      float* out_h, float* out_p, float* out_r, long out_stride,
-                                                      long n_hops, int tile_hops,
-                                                      float* scratch, size_t scratch_per_cta)
-{
-	constexpr int M = NFFT / 2, HOP = M / 2;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	HprSmem<NFFT> sm;
-	sm.carve(smem_raw, P.Lp);
-
-	const int tile = blockIdx.x, stream = blockIdx.y;
-	const size_t cta = (size_t)stream * gridDim.x + tile;
-	float* sc = scratch + cta * scratch_per_cta;
-	HprState st;
-	st.mag_ring = sc;
-	sc += (size_t)P.W * (M + 1) + ((P.W * (M + 1)) & 1);
-	st.xdepth = P.lag > 1 ? P.lag : 0;
-	st.x_ring = reinterpret_cast<float2*>(sc);
-	sc += 2 * (size_t)st.xdepth * (M + 1);
-	for (int o = 0; o < 3; ++o)
-		st.tail[o] = sc + (size_t)o * HOP;
-
-	const float* sin = in + (size_t)stream * in_stride;
-	const long e0 = (long)tile * tile_hops;
-	const long e1 = min(n_hops, e0 + (long)tile_hops);
-	const long i_begin = max(0L, e0 - P.W);
-	const long i_full = max(0L, e0 - 1);
-	for (long i = i_begin; i < e1; ++i) {
-		const float* cur = sin + (size_t)i * HOP;
-		const float* prev = i > 0 ? cur - HOP : nullptr;
-		HprEmit em;
-		const bool emit = i >= e0;
-		em.a[0] = (emit && out_h) ? out_h + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
-		em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
-		em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
-		em.b[0] = em.b[1] = em.b[2] = nullptr;
-		hpr_iteration<NFFT, NT>(P, sm, st, i, prev, cur, i >= i_full, i == i_full, em);
-	}
-}
-
-// One hop of one persistent stream (HPR<GPU>::process_next_hop): state lives in
-// the zen_hpr object between launches.  ola[o] is the reference's *_out vector:
-// [0:hop] the emitted hop, [hop:nwin] the overlap-add tail.
-template <int NFFT, int NT>
-__global__ void __launch_bounds__(NT) hpr_hop_kernel(const __grid_constant__ HprDev P, HprState st, long i,
-                                                     float* input /* nwin: previous hop | current hop */,
-                                                     const float* __restrict__ in_hop,
-                                                     float* ola_h, float* ola_p, float* ola_r,
-                                                     float* ext_h, float* ext_p, float* ext_r)
-{
-	constexpr int M = NFFT / 2, HOP = M / 2;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	HprSmem<NFFT> sm;
-	sm.carve(smem_raw, P.Lp);
-	// input = input[hop:] ++ in_hop   (hps.cu:452-453)
-	for (int n = threadIdx.x; n < HOP; n += NT) {
-		input[n] = input[HOP + n];
-	}
-	__syncthreads();
-	for (int n = threadIdx.x; n < HOP; n += NT)
-		input[HOP + n] = in_hop[n];
-	__syncthreads();
-	float* ola[3] = {ola_h, ola_p, ola_r};
-	float* ext[3] = {ext_h, ext_p, ext_r};
-	HprEmit em;
-	for (int o = 0; o < 3; ++o) {
-		st.tail[o] = ola[o] + HOP;
-		em.a[o] = (P.out_flags & (1 << o)) ? ola[o] : nullptr;
-		em.b[o] = (P.out_flags & (1 << o)) ? ext[o] : nullptr;
-	}
-	hpr_iteration<NFFT, NT>(P, sm, st, i, input, input + HOP, true, false, em);
-	// outputs that the masks never reach still advance like the reference's
-	// rotate-and-zero (hps.cu:435-449): residual with soft mask / SSE
-	if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse)) {
-		for (int n = threadIdx.x; n < HOP; n += NT) {
-			float t = ola_r[HOP + n];
-			ola_r[n] = t;
-			ola_r[HOP + n] = 0.0f;
-			if (ext_r) ext_r[n] = t;
-		}
-	}
-}
 
 __global__ void copy_hop_kernel(const float* __restrict__ src, float* __restrict__ dst, int n)
 {
@@ -126,12 +34,6 @@ __global__ void offline_intermediate_kernel(const float* __restrict__ p1, const 
 // ------------------------------------------------------------------- host ---
 
 namespace {
-
-template <int NFFT>
-constexpr int nt_for()
-{
-	return (NFFT / 16) < 64 ? 64 : ((NFFT / 16) > 512 ? 512 : (NFFT / 16));
-}
 
 struct Plan {
 	HprDev dev;
@@ -166,7 +68,8 @@ int build_plan(Plan& pl, float fs, int hop, float beta, unsigned flags, int caus
 	d.Lp = odd_len(g.l_perc);
 	d.midp = d.Lp / 2;
 	d.Kp = sliding_K_for(d.Lp);
-	if (d.Kp == 0 || d.Lp > M)
+	d.Cp = thread_window_capacity(d.Lp);
+	if ((d.Kp == 0 && d.Cp == 0) || d.Lp > M)
 		return ZEN_ERR_UNSUPPORTED;
 	d.copy_bord = copy_bord ? 1 : 0;
 	d.out_flags = (int)(flags & 7u);
@@ -246,34 +149,19 @@ size_t tile_scratch_floats(const Plan& pl)
 	return (ring + xr + tails + 3) & ~(size_t)3;
 }
 
-template <int NFFT>
-int launch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
-                int n_streams, long n_hops, int tile_hops, float* scratch, cudaStream_t s)
-{
-	constexpr int NT = nt_for<NFFT>();
-	auto kern = hpr_tile_kernel<NFFT, NT>;
-	size_t smem = HprSmem<NFFT>::bytes(pl.dev.Lp);
-	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int n_tiles = (int)((n_hops + tile_hops - 1) / tile_hops);
-	dim3 grid(n_tiles, n_streams);
-	kern<<<grid, NT, smem, s>>>(pl.dev, in, in_stride, oh, op, orr, out_stride, n_hops, tile_hops, scratch,
-	                            tile_scratch_floats(pl));
-	ZEN_CUDA_CHECK(cudaGetLastError());
-	return ZEN_OK;
-}
-
 int dispatch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
                   int n_streams, long n_hops, int tile_hops, float* scratch, cudaStream_t s)
 {
+	TileArgs a{pl.dev, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, tile_scratch_floats(pl), s};
 	switch (pl.nfft) {
-	case 128: return launch_tile<128>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 256: return launch_tile<256>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 512: return launch_tile<512>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 1024: return launch_tile<1024>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 2048: return launch_tile<2048>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 4096: return launch_tile<4096>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 8192: return launch_tile<8192>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
-	case 16384: return launch_tile<16384>(pl, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, s);
+	case 128: return launch_tile_impl<128>(a);
+	case 256: return launch_tile_impl<256>(a);
+	case 512: return launch_tile_impl<512>(a);
+	case 1024: return launch_tile_impl<1024>(a);
+	case 2048: return launch_tile_impl<2048>(a);
+	case 4096: return launch_tile_impl<4096>(a);
+	case 8192: return launch_tile_impl<8192>(a);
+	case 16384: return launch_tile_impl<16384>(a);
 	}
 	return ZEN_ERR_UNSUPPORTED;
 }
@@ -300,27 +188,37 @@ struct zen_hpr {
 
 namespace {
 
-template <int NFFT>
-int launch_hop(zen_hpr* h, const float* in_hop, float* eh, float* ep, float* er)
+int dispatch_hop(zen_hpr* h, const float* in_hop, float* eh, float* ep, float* er)
 {
-	constexpr int NT = nt_for<NFFT>();
-	auto kern = hpr_hop_kernel<NFFT, NT>;
-	size_t smem = HprSmem<NFFT>::bytes(h->plan.dev.Lp);
-	static thread_local const void* configured = nullptr;
-	if (configured != (const void*)kern) {
-		ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		configured = (const void*)kern;
+	HopArgs a;
+	a.dev = h->plan.dev;
+	a.st.mag_ring = h->d_mag_ring;
+	a.st.x_ring = h->d_x_ring;
+	a.st.xdepth = h->plan.dev.W;
+	a.st.tail[0] = a.st.tail[1] = a.st.tail[2] = nullptr;
+	a.iter = h->iter;
+	a.input = h->d_input;
+	a.in_hop = in_hop;
+	for (int o = 0; o < 3; ++o)
+		a.ola[o] = h->d_ola[o];
+	a.ext[0] = eh;
+	a.ext[1] = ep;
+	a.ext[2] = er;
+	a.stream = h->stream;
+	int rc = ZEN_ERR_UNSUPPORTED;
+	switch (h->plan.nfft) {
+	case 128: rc = launch_hop_impl<128>(a); break;
+	case 256: rc = launch_hop_impl<256>(a); break;
+	case 512: rc = launch_hop_impl<512>(a); break;
+	case 1024: rc = launch_hop_impl<1024>(a); break;
+	case 2048: rc = launch_hop_impl<2048>(a); break;
+	case 4096: rc = launch_hop_impl<4096>(a); break;
+	case 8192: rc = launch_hop_impl<8192>(a); break;
+	case 16384: rc = launch_hop_impl<16384>(a); break;
 	}
-	HprState st;
-	st.mag_ring = h->d_mag_ring;
-	st.x_ring = h->d_x_ring;
-	st.xdepth = h->plan.dev.W;
-	st.tail[0] = st.tail[1] = st.tail[2] = nullptr;
-	kern<<<1, NT, smem, h->stream>>>(h->plan.dev, st, h->iter, h->d_input, in_hop, h->d_ola[0], h->d_ola[1], h->d_ola[2],
-	                                 eh, ep, er);
-	ZEN_CUDA_CHECK(cudaGetLastError());
-	h->iter++;
-	return ZEN_OK;
+	if (rc == ZEN_OK)
+		h->iter++;
+	return rc;
 }
 
 int rebuild_plan(zen_hpr* h)
@@ -434,17 +332,7 @@ int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* eh, float* 
 		int rc = rebuild_plan(h);
 		if (rc != ZEN_OK) return rc;
 	}
-	switch (h->plan.nfft) {
-	case 128: return launch_hop<128>(h, d_in_hop, eh, ep, er);
-	case 256: return launch_hop<256>(h, d_in_hop, eh, ep, er);
-	case 512: return launch_hop<512>(h, d_in_hop, eh, ep, er);
-	case 1024: return launch_hop<1024>(h, d_in_hop, eh, ep, er);
-	case 2048: return launch_hop<2048>(h, d_in_hop, eh, ep, er);
-	case 4096: return launch_hop<4096>(h, d_in_hop, eh, ep, er);
-	case 8192: return launch_hop<8192>(h, d_in_hop, eh, ep, er);
-	case 16384: return launch_hop<16384>(h, d_in_hop, eh, ep, er);
-	}
-	return ZEN_ERR_UNSUPPORTED;
+	return dispatch_hop(h, d_in_hop, eh, ep, er);
 }
 
 int zen_hpr_process_next_hop(zen_hpr* h, const float* d_in_hop)
@@ -487,6 +375,59 @@ float* zen_hpr_state_ptr(zen_hpr* h, int which)
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------- fakert region ---
+// The loop zen/fakert.h:217-251 times, hop by hop: host copy into the mapped
+// input buffer -> process_next_hop -> copy_percussive -> host copy out.
+// fused != 0 uses the single-launch zen_hpr_process_hop_io instead of the
+// process_next_hop + copy_percussive pair.
+
+#include <chrono>
+
+extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const float* h_audio, long n_hops,
+                              int warmup_iters, int fused, float* h_perc_out, double* h_us_per_hop)
+{
+	if (!h_audio || n_hops < 1 || !h_perc_out)
+		return ZEN_ERR_ARG;
+	zen_hpr* h = nullptr;
+	int rc = zen_hpr_create(&h, fs, hop, beta, ZEN_OUTPUT_PERCUSSIVE, ZEN_TIME_CAUSAL, !(options & ZEN_OPT_NOCOPYBORD));
+	if (rc != ZEN_OK)
+		return rc;
+	if (options & ZEN_OPT_SSE) zen_hpr_use_sse_filter(h);
+	if (options & ZEN_OPT_SOFT_MASK) zen_hpr_use_soft_mask(h);
+	zen_io io;
+	rc = zen_io_alloc(&io, hop);
+	if (rc != ZEN_OK) {
+		zen_hpr_destroy(h);
+		return rc;
+	}
+	// HPRRealtime<GPU>::warmup (hps.cu:392-409): iota data, then reset_buffers
+	for (int i = 0; i < warmup_iters && rc == ZEN_OK; ++i) {
+		for (int j = 0; j < hop; ++j)
+			io.host_in[j] = (float)((long)i * hop + j);
+		rc = fused ? zen_hpr_process_hop_io(h, io.device_in, nullptr, io.device_out, nullptr) : zen_hpr_process_next_hop(h, io.device_in);
+		if (rc == ZEN_OK) rc = zen_hpr_synchronize(h);
+	}
+	if (rc == ZEN_OK) rc = zen_hpr_reset_buffers(h);
+	for (long i = 0; i < n_hops && rc == ZEN_OK; ++i) {
+		auto t1 = std::chrono::high_resolution_clock::now();
+		std::memcpy(io.host_in, h_audio + (size_t)i * hop, sizeof(float) * hop);
+		if (fused) {
+			rc = zen_hpr_process_hop_io(h, io.device_in, nullptr, io.device_out, nullptr);
+			if (rc == ZEN_OK) rc = zen_hpr_synchronize(h);
+		}
+		else {
+			rc = zen_hpr_process_next_hop(h, io.device_in);
+			if (rc == ZEN_OK) rc = zen_hpr_copy_percussive(h, io.device_out);
+		}
+		std::memcpy(h_perc_out + (size_t)i * hop, io.host_out, sizeof(float) * hop);
+		auto t2 = std::chrono::high_resolution_clock::now();
+		if (h_us_per_hop) h_us_per_hop[i] = std::chrono::duration<double, std::micro>(t2 - t1).count();
+	}
+	zen_io_free(&io);
+	zen_hpr_destroy(h);
+	return rc;
+}
 
 // ------------------------------------------------ debug-view materialise ---
 // The reference recomputes the whole stft_width x nfft matrices every hop and

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <type_traits>
 
 namespace zen_b200 {
 
@@ -176,6 +177,129 @@ static inline int sliding_K_for(int L)
 		if (L + pad <= 32 * K)
 			return K;
 	}
+	return 0;
+}
+
+// ---- windows up to 63 taps: one sorted window PER THREAD, in registers ----
+// Each thread owns a run of consecutive outputs.  Its window lives in C
+// registers (C compile-time, L <= C-1 run-time), padded below with -inf so the
+// median is always S[C/2] and above with +inf.  The first window is sorted
+// with Batcher's odd-even merge network; every further output removes the
+// outgoing value and inserts the incoming one with 4 ALU ops per register and
+// no data-dependent indexing:
+//     T[p]  = S[p] < o ? S[p] : S[p+1]            (drop one copy of o)
+//     S'[p] = max(T[p-1], min(T[p], v))           (insert v)
+// All C updates of a slide are independent (ILP), nothing is shuffled and the
+// only memory traffic is two shared-memory loads and one store per output.
+template <int I, int End, int Step, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+	if constexpr (I < End) {
+		f(std::integral_constant<int, I>{});
+		static_for<I + Step, End, Step>(f);
+	}
+}
+
+template <int I, int J, int C>
+__device__ __forceinline__ void ce_static(float (&v)[C])
+{
+	if constexpr (J < C) {  // ranks >= C are virtual +inf: the exchange would be a no-op
+		float a = v[I], b = v[J];
+		v[I] = fminf(a, b);
+		v[J] = fmaxf(a, b);
+	}
+}
+
+// Batcher odd-even merge of the subsequence LO, LO+R, LO+2R, ... (N elements span)
+template <int LO, int N, int R, int C>
+__device__ __forceinline__ void oe_merge(float (&v)[C])
+{
+	constexpr int step = R * 2;
+	if constexpr (step < N) {
+		oe_merge<LO, N, step, C>(v);
+		oe_merge<LO + R, N, step, C>(v);
+		static_for<LO + R, LO + N - R, step>([&](auto i) { ce_static<decltype(i)::value, decltype(i)::value + R, C>(v); });
+	}
+	else {
+		ce_static<LO, LO + R, C>(v);
+	}
+}
+
+template <int LO, int N, int C>
+__device__ __forceinline__ void oe_sort(float (&v)[C])
+{
+	if constexpr (N > 1 && LO < C) {
+		oe_sort<LO, N / 2, C>(v);
+		oe_sort<LO + N / 2, N / 2, C>(v);
+		oe_merge<LO, N, 1, C>(v);
+	}
+}
+
+constexpr int next_pow2(int n)
+{
+	int p = 1;
+	while (p < n) p <<= 1;
+	return p;
+}
+
+template <int C>
+__device__ __forceinline__ void thread_window_slide(float (&S)[C], float o, float v)
+{
+	float prevT = -CUDART_INF_F;
+#pragma unroll
+	for (int p = 0; p < C; ++p) {
+		float nxt = (p + 1 < C) ? S[p + 1] : CUDART_INF_F;
+		float t = (S[p] < o) ? S[p] : nxt;
+		S[p] = fmaxf(prevT, fminf(t, v));
+		prevT = t;
+	}
+}
+
+// out[s] = median(E[s .. s+L)) for s in [s0, s1); E, out in shared memory; L odd, L <= C-1
+template <int C>
+__device__ __forceinline__ void thread_sliding_median(const float* __restrict__ E, float* __restrict__ out, int s0, int s1, int L)
+{
+	if (s0 >= s1)
+		return;
+	const int pad_lo = C / 2 - (L >> 1);
+	float S[C];
+#pragma unroll
+	for (int p = 0; p < C; ++p) {
+		int idx = p - pad_lo;
+		S[p] = idx < 0 ? -CUDART_INF_F : (idx < L ? E[s0 + idx] : CUDART_INF_F);
+	}
+	oe_sort<0, next_pow2(C), C>(S);
+	out[s0] = S[C / 2];
+	const float* po = E + s0;
+	const float* pv = E + s0 + L;
+	float* pw = out + s0 + 1;
+	for (int n = s1 - s0 - 1; n > 0; --n) {
+		float o = *po++;
+		float v = *pv++;
+		thread_window_slide<C>(S, o, v);
+		*pw++ = S[C / 2];
+	}
+}
+
+__device__ __forceinline__ void thread_sliding_median_dyn(int C, const float* E, float* out, int s0, int s1, int L)
+{
+	switch (C) {
+	case 8: thread_sliding_median<8>(E, out, s0, s1, L); break;
+	case 16: thread_sliding_median<16>(E, out, s0, s1, L); break;
+	case 24: thread_sliding_median<24>(E, out, s0, s1, L); break;
+	case 32: thread_sliding_median<32>(E, out, s0, s1, L); break;
+	default: thread_sliding_median<48>(E, out, s0, s1, L); break;
+	}
+}
+
+// smallest register capacity for an L-tap window (L <= C-1); 0 if L > 47 (the
+// warp-resident window takes over: 64+ registers per thread would cost occupancy)
+static inline int thread_window_capacity(int L)
+{
+	const int caps[5] = {8, 16, 24, 32, 48};
+	for (int i = 0; i < 5; ++i)
+		if (L <= caps[i] - 1)
+			return caps[i];
 	return 0;
 }
 

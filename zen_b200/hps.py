@@ -70,6 +70,29 @@ class IOGPU:
             pass
 
 
+class PinnedArray:
+    """float32 [rows, cols] array in page-locked host memory (zen_host_alloc)."""
+
+    def __init__(self, rows, cols):
+        self.nbytes = rows * cols * 4
+        self.ptr = _lib.lib().zen_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("zen_host_alloc(%d bytes) failed" % self.nbytes)
+        self.array = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ctypes.c_float)), (rows, cols))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            _lib.lib().zen_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 class MedianFilterGPU:
     """libzen/mfilt.h:33-268.  filter(src, dst) on time x freq float32 CUDA tensors."""
 
