@@ -59,13 +59,14 @@ struct HprSmem {
 	float2* xbuf;  // M + 1
 	float* erow;   // M + 1 + Lp + 3   (extended magnitude row, later the H row)
 	float* prow;   // M + 1
+	int* taps;     // ZEN_MAX_TAPS: ring-row offset of every time tap for this hop (-1: frame before the stream start)
 	static __host__ __device__ size_t bytes(int Lp)
 	{
 		size_t z = sizeof(float2) * (size_t)fpad_size(M);
 		size_t x = sizeof(float2) * (size_t)(M + 2);
 		size_t e = sizeof(float) * (size_t)((M + 1 + Lp + 3 + 3) & ~3);
 		size_t p = sizeof(float) * (size_t)((M + 1 + 3) & ~3);
-		return z + x + e + p;
+		return z + x + e + p + sizeof(int) * ZEN_MAX_TAPS;
 	}
 	__device__ void carve(unsigned char* base, int Lp)
 	{
@@ -73,6 +74,7 @@ struct HprSmem {
 		xbuf = zbuf + fpad_size(M);
 		erow = reinterpret_cast<float*>(xbuf + (M + 2));
 		prow = erow + ((M + 1 + Lp + 3 + 3) & ~3);
+		taps = reinterpret_cast<int*>(prow + ((M + 1 + 3) & ~3));
 	}
 };
 
@@ -135,7 +137,7 @@ __device__ __forceinline__ float median_fixed(Get get)
 // One hop.  `full` == false: analysis only (fills the rings; halo iterations of a tile).
 // All NT threads of the CTA must call it with identical arguments.
 template <int NFFT, int NT>
-__device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, long i,
+__device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
                                               const float* __restrict__ prev, const float* __restrict__ cur,
                                               bool full, bool fresh_tail, const HprEmit& em)
 {
@@ -144,6 +146,12 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 	const int tid = threadIdx.x;
 	const int W = P.W;
 	const int eoff = (P.copy_bord || P.sse) ? P.midp : 0;
+
+	// ring rows of the time-axis taps for this hop (read in step F, after several barriers)
+	for (int t = tid; t < P.n_taps; t += NT) {
+		int j = i - P.tap_age[t];
+		sm.taps[t] = j >= 0 ? (j % W) * (M + 1) : -1;
+	}
 
 	// ---- A. window the 2-hop frame, pack even/odd samples as one complex value (hps.cu:452-462)
 	for (int n = tid; n < M; n += NT) {
@@ -216,7 +224,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		return;
 
 	// ---- D. the consumed frame: row stft_width - lag (hps.cu:501-504, 517-519)
-	const long jc = i - P.lag + 1;
+	const int jc = i - P.lag + 1;
 	if (P.lag > 1) {
 		const float* mrow = st.mag_ring + (size_t)((jc >= 0 ? jc : 0) % W) * (M + 1);
 		const float2* xrow = st.x_ring + (size_t)((jc >= 0 ? jc : 0) % st.xdepth) * (M + 1);
@@ -272,8 +280,8 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 	{
 		const int nt = P.n_taps;
 		auto tap = [&](int t, int k) -> float {
-			long j = i - P.tap_age[t];
-			return j >= 0 ? st.mag_ring[(size_t)(j % W) * (M + 1) + k] : 0.0f;
+			int off = sm.taps[t];
+			return off >= 0 ? st.mag_ring[off + k] : 0.0f;
 		};
 		for (int k = tid; k <= M; k += NT) {
 			float H;

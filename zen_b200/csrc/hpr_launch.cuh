@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_tile_kernel(cons
 		em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
 		em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
 		em.b[0] = em.b[1] = em.b[2] = nullptr;
-		hpr_iteration<NFFT, NT>(P, sm, st, i, prev, cur, i >= i_full, i == i_full, em);
+		hpr_iteration<NFFT, NT>(P, sm, st, (int)i, prev, cur, i >= i_full, i == i_full, em);
 	}
 }
 
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_hop_kernel(const
 		em.a[o] = (P.out_flags & (1 << o)) ? ola[o] : nullptr;
 		em.b[o] = (P.out_flags & (1 << o)) ? ext[o] : nullptr;
 	}
-	hpr_iteration<NFFT, NT>(P, sm, st, i, input, input + HOP, true, false, em);
+	hpr_iteration<NFFT, NT>(P, sm, st, (int)i, input, input + HOP, true, false, em);
 	// outputs that the masks never reach still advance like the reference's
 	// rotate-and-zero (hps.cu:435-449): residual with soft mask / SSE
 	if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse)) {
