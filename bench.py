@@ -206,7 +206,7 @@ def workload_config(args, n_streams, seconds):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from zen_b200 import _lib, hps
+    from zen_b200 import _lib, hps, shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; zen_b200 has no CPU fallback")
@@ -219,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
     n_streams, seconds = args.streams, args.seconds
     n_hops = fakert_hops(seconds * FS, HOP)
     n = n_hops * HOP
-    x = synth_batch_device(torch, n_streams, n, dev, seed0=1000 + 100000 * rank)
+    x = synth_batch_device(torch, n_streams, n, dev, seed0=shard.stream_seed(1000, rank, n_streams, 0))
     out_p = torch.empty_like(x)
     b = hps.HPRBatch(float(FS), HOP, BETA, hps.OUTPUT_PERCUSSIVE)
     small = n_streams * n * 4 < (512 << 20)
@@ -254,13 +254,11 @@ def run_ours(args, rank, world, local_rank):
     kern_ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1]) if flush is None else sum(kern_ms)
     launches = args.steps * b.last_launches
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = shard.max_over_ranks(dist if world > 1 else None, total_ms, dev)
     audio_per_step = n_streams * n / FS
-    value = world * audio_per_step * args.steps / (total_ms_max * 1e-3)
+    value = shard.aggregate_throughput(audio_per_step * args.steps, world, total_ms_max * 1e-3)
 
     # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
     e2e = None
@@ -279,10 +277,8 @@ def run_ours(args, rank, world, local_rank):
             b.process_host(h_in.array, [None, h_out.array, None])
         dt = time.perf_counter() - t0
         launches_e2e = e2e_steps * b.last_launches
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * audio_per_step * e2e_steps / float(te.item()), "unit": "audio-s/s",
+        dt_max = shard.max_over_ranks(dist if world > 1 else None, dt, dev)
+        e2e = {"value": shard.aggregate_throughput(audio_per_step * e2e_steps, world, dt_max), "unit": "audio-s/s",
                "h2d_bytes_per_step": int(n_streams) * n * 4, "d2h_bytes_per_step": int(n_streams) * n * 4,
                "steps": e2e_steps, "kernel_launches_per_step": launches_e2e // e2e_steps,
                "api": "zen_hpr_batch_process_host (pinned host buffers in and out)"}
@@ -382,9 +378,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from zen_b200 import shard
+    rank, world, local_rank = shard.rank_world()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

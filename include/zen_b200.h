@@ -116,6 +116,10 @@ int zen_hpr_copy_residual(zen_hpr* h, float* d_out_hop);
  * skipped.  This is the latency path (zen fakert's timed region). */
 int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* d_out_h, float* d_out_p, float* d_out_r);
 int zen_hpr_synchronize(zen_hpr* h);
+/* Make caller-owned device buffers (nwin floats each, 8-byte aligned) the object's
+ * streaming state, so that e.g. thrust::device_vector members named like the
+ * reference's (hps.h:182-197) ARE the state; zeroes them (reset_buffers). */
+int zen_hpr_bind_state(zen_hpr* h, float* d_input, float* d_harmonic_out, float* d_percussive_out, float* d_residual_out);
 /* Device pointers to the streaming state that the reference exposes as public
  * members of HPR<GPU> (hps.h:182-197): which = 0 input[nwin], 1 harmonic_out[nwin],
  * 2 percussive_out[nwin], 3 residual_out[nwin], 4 window[nwin]. */

@@ -177,6 +177,7 @@ struct zen_hpr {
 	int hop, causality, copy_bord;
 	bool sse = false, soft = false;
 	bool plan_dirty = false;
+	bool state_external = false;  // input / *_out owned by the caller (zen_hpr_bind_state)
 	long iter = 0;
 	cudaStream_t stream = nullptr;
 	// state
@@ -278,9 +279,11 @@ void zen_hpr_destroy(zen_hpr* h)
 		return;
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	free_plan(h->plan);
-	cudaFree(h->d_input);
-	for (int o = 0; o < 3; ++o)
-		cudaFree(h->d_ola[o]);
+	if (!h->state_external) {
+		cudaFree(h->d_input);
+		for (int o = 0; o < 3; ++o)
+			cudaFree(h->d_ola[o]);
+	}
 	cudaFree(h->d_mag_ring);
 	cudaFree(h->d_x_ring);
 	if (h->stream) cudaStreamDestroy(h->stream);
@@ -359,6 +362,26 @@ int zen_hpr_synchronize(zen_hpr* h)
 	if (!h) return ZEN_ERR_ARG;
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	return ZEN_OK;
+}
+
+int zen_hpr_bind_state(zen_hpr* h, float* d_input, float* d_harmonic_out, float* d_percussive_out, float* d_residual_out)
+{
+	if (!h || !d_input || !d_harmonic_out || !d_percussive_out || !d_residual_out)
+		return ZEN_ERR_ARG;
+	if (((uintptr_t)d_input | (uintptr_t)d_harmonic_out | (uintptr_t)d_percussive_out | (uintptr_t)d_residual_out) & 7)
+		return ZEN_ERR_ARG;
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+	if (!h->state_external) {
+		cudaFree(h->d_input);
+		for (int o = 0; o < 3; ++o)
+			cudaFree(h->d_ola[o]);
+	}
+	h->state_external = true;
+	h->d_input = d_input;
+	h->d_ola[0] = d_harmonic_out;
+	h->d_ola[1] = d_percussive_out;
+	h->d_ola[2] = d_residual_out;
+	return zen_hpr_reset_buffers(h);
 }
 
 float* zen_hpr_state_ptr(zen_hpr* h, int which)
