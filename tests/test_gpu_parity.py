@@ -385,3 +385,31 @@ def test_batch_host_path(torch, zen):
     assert np.array_equal(dev, host_out)
     assert b.last_launches >= 1
     b.close()
+
+
+@pytest.mark.parametrize("fs,hop,flags,causal,cb", [(44100.0, 1024, 7, True, True), (44100.0, 1024, 7, True, False),
+                                                     (48000.0, 256, 7, False, True), (48000.0, 256, 3, False, False),
+                                                     (44100.0, 4096, 7, True, True), (44100.0, 2048, 6, True, False),
+                                                     (44100.0, 512, 2, True, True)])
+def test_decision_path_equals_median_path(torch, zen, fs, hop, flags, causal, cb):
+    """hard masks decided by counting taps against the exact threshold == selecting the median and comparing:
+    the separated audio must be identical bit for bit"""
+    n_hops, n_streams = 60, 2
+    audio = np.stack([synth_audio(n_hops * hop, seed=700 + s, fs=int(fs)) for s in range(n_streams)])
+    x = torch.from_numpy(audio).cuda()
+    res = []
+    for no_decide in (False, True):
+        if no_decide:
+            os.environ["ZEN_B200_NO_DECIDE"] = "1"
+        else:
+            os.environ.pop("ZEN_B200_NO_DECIDE", None)
+        b = zen.HPRBatch(fs, hop, 2.5, flags, causal=causal, nocopybord=not cb)
+        outs = b.process(x)
+        torch.cuda.synchronize()
+        res.append([o.cpu().numpy() if o is not None else None for o in outs])
+        b.close()
+    os.environ.pop("ZEN_B200_NO_DECIDE", None)
+    for a, b_ in zip(*res):
+        if a is not None:
+            assert np.array_equal(a, b_)
+            assert np.abs(a).max() > 0

@@ -28,6 +28,7 @@ struct HprDev {
 	int Cp;              // register capacity of the per-thread sliding window (0: use the warp-resident one)
 	int copy_bord;       // frequency windows centred+circular (1) or forward-looking (0)
 	int out_flags, soft, sse;
+	int decide;          // hard mask: decide M = [median >= threshold] by counting taps instead of selecting the median
 	float power;         // (float)(int)beta, soft-mask exponent (hps.h:116-129)
 	float beta, beta_h;  // beta, beta - eps (hps.cu:505, 540)
 	float cola;
@@ -121,6 +122,128 @@ __device__ __forceinline__ void hpr_masks(const HprDev& P, const float* prow, co
 	else {
 		if (want_p) mp = two ? 0.5f * (mask_hard(Pf, H, P.beta) + mask_hard(Pb, H, P.beta)) : mask_hard(Pf, H, P.beta);
 		if (want_h) mh = two ? 0.5f * (mask_hard(H, Pf, P.beta_h) + mask_hard(H, Pb, P.beta_h)) : mask_hard(H, Pf, P.beta_h);
+	}
+}
+
+// ---- hard-mask decisions without computing the median ------------------------
+// The hard masks only need to know on which side of a threshold the frequency
+// median P[k] lies:  Mp = [P/(H+eps) >= beta],  Mh = [H/(P+eps) >= beta-eps]
+// (hps.h:100-113, hps.cu:501-505, 535-540).  Both tests are monotone in P, and
+// for a monotone predicate f, f(median(x)) == median(f(x)): the mask is 1 iff at
+// least mid+1 of the L window taps pass the test.  We therefore find, once per
+// bin, the exact float threshold of the test (the smallest x with
+// RN(x/d) >= beta, resp. the largest s with RN(h/s) >= beta_h) and then only
+// COUNT taps against it: one compare (ALU pipe) and one add (FMA pipe) per tap
+// instead of keeping a sorted window.  The decisions are bit-identical to
+// selecting the median and applying the reference's functor.
+__device__ __forceinline__ float f_next_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }    // x >= 0, finite
+__device__ __forceinline__ float f_next_down(float x) { return __uint_as_float(__float_as_uint(x) - 1u); }  // x > 0
+
+// smallest float x >= 0 with RN(x / d) >= beta   (d > 0);  +inf if none
+__device__ __forceinline__ float thr_ratio_ge(float d, float beta)
+{
+	if (!(beta > 0.0f))
+		return beta == beta ? 0.0f : CUDART_INF_F;  // every x >= 0 passes; NaN beta: nothing passes
+	float c = beta * d;
+	if (!(c < CUDART_INF_F))
+		return CUDART_INF_F;
+	while (!((c / d) >= beta)) {
+		c = f_next_up(c);
+		if (!(c < CUDART_INF_F))
+			return CUDART_INF_F;
+	}
+	while (c > 0.0f) {
+		float q = f_next_down(c);
+		if ((q / d) >= beta)
+			c = q;
+		else
+			break;
+	}
+	return c;
+}
+
+// largest float s > 0 with RN(h / s) >= beta_h   (h >= 0);  -1 if none, +inf if every s passes
+__device__ __forceinline__ float thr_ratio_le(float h, float beta_h)
+{
+	if (!(beta_h > 0.0f))
+		return beta_h == beta_h ? CUDART_INF_F : -1.0f;
+	if (!(h > 0.0f))
+		return -1.0f;
+	float c = h / beta_h;
+	if (!(c > 0.0f))
+		return -1.0f;
+	if (!(c < CUDART_INF_F))
+		c = 3.402823466e+38f;
+	while (!((h / c) >= beta_h)) {
+		c = f_next_down(c);
+		if (!(c > 0.0f))
+			return -1.0f;
+	}
+	while (c < 3.402823466e+38f) {
+		float q = f_next_up(c);
+		if ((h / q) >= beta_h)
+			c = q;
+		else
+			break;
+	}
+	return c;
+}
+
+constexpr int ZEN_DECIDE_U = 9;  // consecutive bins per thread: odd, so the lanes' tap loads hit distinct banks
+
+// Decisions for bins k in [k0, k0+U): taps of bin k are E[k + woff .. k + woff + L).
+// Returns bit u of *dp = [P >= tau_k], bit u of *dh = [P + eps <= sig_k]  for k = k0 + u.
+__device__ __forceinline__ void decide_group(const float* __restrict__ E, const float* __restrict__ hrow, int k0, int kmax, int woff,
+                                             int L, float beta, float beta_h, bool want_p, bool want_h, unsigned& dp, unsigned& dh)
+{
+	constexpr int U = ZEN_DECIDE_U;
+	float tau[U], sig[U], cp[U], ch[U];
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		const int k = min(k0 + u, kmax);
+		const float H = hrow[k];
+		tau[u] = want_p ? thr_ratio_ge(H + ZEN_EPS, beta) : CUDART_INF_F;
+		sig[u] = want_h ? thr_ratio_le(H, beta_h) : -1.0f;
+		cp[u] = 0.0f;
+		ch[u] = 0.0f;
+	}
+	const float* base = E + k0 + woff;
+	// head: tap j belongs to bins u <= j only
+#pragma unroll
+	for (int j = 0; j < U - 1; ++j) {
+		const float x = base[j], sx = x + ZEN_EPS;
+#pragma unroll
+		for (int u = 0; u <= j; ++u) {
+			cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
+			ch[u] += (sx <= sig[u]) ? 1.0f : 0.0f;
+		}
+	}
+	// body: every bin of the group sees the tap (needs L >= U - 1, guaranteed by the caller)
+	for (int j = U - 1; j < L; ++j) {
+		const float x = base[j], sx = x + ZEN_EPS;
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
+			ch[u] += (sx <= sig[u]) ? 1.0f : 0.0f;
+		}
+	}
+	// tail: tap L + j belongs to bins u > j only
+#pragma unroll
+	for (int j = 0; j < U - 1; ++j) {
+		const float x = base[L + j], sx = x + ZEN_EPS;
+#pragma unroll
+		for (int u = j + 1; u < U; ++u) {
+			cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
+			ch[u] += (sx <= sig[u]) ? 1.0f : 0.0f;
+		}
+	}
+	const float need = (float)(L / 2 + 1);
+	dp = 0u;
+	dh = 0u;
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		dp |= (cp[u] >= need ? 1u : 0u) << u;
+		dh |= (ch[u] >= need ? 1u : 0u) << u;
 	}
 }
 
@@ -248,36 +371,8 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 	}
 	__syncthreads();
 
-	// ---- E. frequency axis: prow[s] = median / mean of erow[s .. s+Lp)
-	if (!P.sse) {
-		if (P.Cp > 0) {
-			const int R = (M + 1 + NT - 1) / NT;
-			const int s0 = tid * R;
-			const int s1 = min(M + 1, s0 + R);
-			thread_sliding_median_dyn(P.Cp, sm.erow, sm.prow, s0, s1, P.Lp);
-		}
-		else {
-			constexpr int NW = NT / 32;
-			const int wid = tid >> 5, lane = tid & 31;
-			const int R = (M + 1 + NW - 1) / NW;
-			const int s0 = wid * R;
-			const int s1 = min(M + 1, s0 + R);
-			warp_sliding_median_dyn<float>(P.Kp, sm.erow, sm.prow, s0, s1, P.Lp, lane);
-		}
-	}
-	else {
-		for (int k = tid; k <= M; k += NT) {
-			float acc = 0.0f;
-			for (int t = 0; t < P.Lp; ++t)
-				acc += sm.erow[k + t];
-			float mean = acc * P.inv_lp;
-			sm.prow[k] = (1.0f / mean) * P.lp1;  // hps.cu:599-601
-		}
-	}
-	__syncthreads();
-
-	// ---- F. time axis: H row (into erow, whose magnitudes are no longer needed)
-	{
+	// time axis: H row (hps.cu:495 / 595, only the consumed row)
+	auto compute_h_row = [&](float* dst) {
 		const int nt = P.n_taps;
 		auto tap = [&](int t, int k) -> float {
 			int off = sm.taps[t];
@@ -305,10 +400,89 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 				default: H = median_generic([&](int t) { return tap(t, k); }, nt); break;
 				}
 			}
-			sm.erow[k] = H;
+			dst[k] = H;
 		}
+	};
+
+	const bool decide = P.decide && !P.sse && !P.soft && P.Lp >= ZEN_DECIDE_U - 1;
+	if (decide) {
+		// ---- E'/F'. hard mask by counting (see decide_group).  The H row goes into zbuf, which is
+		// free between the split pass and the inverse-FFT build; codes go into prow:
+		// bit0/bit1 = percussive decision at bins k / nfft-k, bit2/bit3 = harmonic.
+		float* hrow = reinterpret_cast<float*>(sm.zbuf);
+		compute_h_row(hrow);
+		__syncthreads();
+		unsigned* codes = reinterpret_cast<unsigned*>(sm.prow);
+		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
+		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
+		constexpr int U = ZEN_DECIDE_U;
+		constexpr int NG = (M + 1 + U - 1) / U;
+		for (int g = tid; g < NG; g += NT) {
+			const int k0 = g * U;
+			unsigned fp, fh;
+			decide_group(sm.erow, hrow, k0, M, 0, P.Lp, P.beta, P.beta_h, want_p, want_h, fp, fh);
+			unsigned bp = fp, bh = fh;
+			if (!P.copy_bord) {
+				// value at bin nfft-k: window k-L+1 .. k for k > L, never written (P = 0) for 1 <= k <= L
+				bp = 0u;
+				bh = 0u;
+				if (k0 + U - 1 > P.Lp)
+					decide_group(sm.erow, hrow, k0, M, -(P.Lp - 1), P.Lp, P.beta, P.beta_h, want_p, want_h, bp, bh);
+			}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int k = k0 + u;
+				if (k <= M) {
+					unsigned p0 = (fp >> u) & 1u, h0 = (fh >> u) & 1u, p1 = (bp >> u) & 1u, h1 = (bh >> u) & 1u;
+					if (!P.copy_bord) {
+						if (k == 0 || k == M) {
+							p1 = p0;
+							h1 = h0;
+						}
+						else if (k <= P.Lp) {
+							const float H = hrow[k];
+							p1 = (want_p && (0.0f / (H + ZEN_EPS)) >= P.beta) ? 1u : 0u;
+							h1 = (want_h && (H / (0.0f + ZEN_EPS)) >= P.beta_h) ? 1u : 0u;
+						}
+					}
+					codes[k] = p0 | (p1 << 1) | (h0 << 2) | (h1 << 3);
+				}
+			}
+		}
+		__syncthreads();
 	}
-	__syncthreads();
+	else {
+		// ---- E. frequency axis: prow[s] = median / mean of erow[s .. s+Lp)
+		if (!P.sse) {
+			if (P.Cp > 0) {
+				const int R = (M + 1 + NT - 1) / NT;
+				const int s0 = tid * R;
+				const int s1 = min(M + 1, s0 + R);
+				thread_sliding_median_dyn(P.Cp, sm.erow, sm.prow, s0, s1, P.Lp);
+			}
+			else {
+				constexpr int NW = NT / 32;
+				const int wid = tid >> 5, lane = tid & 31;
+				const int R = (M + 1 + NW - 1) / NW;
+				const int s0 = wid * R;
+				const int s1 = min(M + 1, s0 + R);
+				warp_sliding_median_dyn<float>(P.Kp, sm.erow, sm.prow, s0, s1, P.Lp, lane);
+			}
+		}
+		else {
+			for (int k = tid; k <= M; k += NT) {
+				float acc = 0.0f;
+				for (int t = 0; t < P.Lp; ++t)
+					acc += sm.erow[k + t];
+				float mean = acc * P.inv_lp;
+				sm.prow[k] = (1.0f / mean) * P.lp1;  // hps.cu:599-601
+			}
+		}
+		__syncthreads();
+		// ---- F. time axis: H row (into erow, whose magnitudes are no longer needed)
+		compute_h_row(sm.erow);
+		__syncthreads();
+	}
 
 	// ---- G. per output: mask, inverse real FFT, overlap-add (hps.cu:498-579, 607-651)
 	// order P, H, R as in the reference; output index 0 = H, 1 = P, 2 = R
@@ -323,8 +497,18 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		for (int k = tid; k <= M / 2; k += NT) {
 			const int kb = M - k;
 			float mpa, mha, mpb, mhb;
-			hpr_masks<NFFT>(P, sm.prow, sm.erow, k, mpa, mha);
-			hpr_masks<NFFT>(P, sm.prow, sm.erow, kb, mpb, mhb);
+			if (decide) {
+				const unsigned ca = reinterpret_cast<const unsigned*>(sm.prow)[k];
+				const unsigned cb = reinterpret_cast<const unsigned*>(sm.prow)[kb];
+				mpa = 0.5f * (float)((ca & 1u) + ((ca >> 1) & 1u));
+				mha = 0.5f * (float)(((ca >> 2) & 1u) + ((ca >> 3) & 1u));
+				mpb = 0.5f * (float)((cb & 1u) + ((cb >> 1) & 1u));
+				mhb = 0.5f * (float)(((cb >> 2) & 1u) + ((cb >> 3) & 1u));
+			}
+			else {
+				hpr_masks<NFFT>(P, sm.prow, sm.erow, k, mpa, mha);
+				hpr_masks<NFFT>(P, sm.prow, sm.erow, kb, mpb, mhb);
+			}
 			float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 			float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
 			float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];

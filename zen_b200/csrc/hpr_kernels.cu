@@ -74,6 +74,7 @@ int build_plan(Plan& pl, float fs, int hop, float beta, unsigned flags, int caus
 	d.copy_bord = copy_bord ? 1 : 0;
 	d.out_flags = (int)(flags & 7u);
 	d.soft = soft ? 1 : 0;
+	d.decide = std::getenv("ZEN_B200_NO_DECIDE") ? 0 : 1;  // debugging aid: force the median-selection path
 	d.sse = sse ? 1 : 0;
 	d.power = (float)(int)beta;
 	d.beta = beta;
