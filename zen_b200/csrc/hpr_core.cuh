@@ -189,62 +189,75 @@ __device__ __forceinline__ float thr_ratio_le(float h, float beta_h)
 	return c;
 }
 
-constexpr int ZEN_DECIDE_U = 9;  // consecutive bins per thread: odd, so the lanes' tap loads hit distinct banks
+constexpr int ZEN_DECIDE_U = 9;  // consecutive bins per thread in the batched kernels: odd, so the lanes' tap loads hit distinct banks
 
 // Decisions for bins k in [k0, k0+U): taps of bin k are E[k + woff .. k + woff + L).
 // Returns bit u of *dp = [P >= tau_k], bit u of *dh = [P + eps <= sig_k]  for k = k0 + u.
-__device__ __forceinline__ void decide_group(const float* __restrict__ E, const float* __restrict__ hrow, int k0, int kmax, int woff,
-                                             int L, float beta, float beta_h, bool want_p, bool want_h, unsigned& dp, unsigned& dh)
+template <int U, bool WP, bool WH>
+__device__ __forceinline__ void decide_group_t(const float* __restrict__ E, const float* __restrict__ hrow, int k0, int kmax, int woff,
+                                               int L, float beta, float beta_h, unsigned& dp, unsigned& dh)
 {
-	constexpr int U = ZEN_DECIDE_U;
 	float tau[U], sig[U], cp[U], ch[U];
 #pragma unroll
 	for (int u = 0; u < U; ++u) {
 		const int k = min(k0 + u, kmax);
 		const float H = hrow[k];
-		tau[u] = want_p ? thr_ratio_ge(H + ZEN_EPS, beta) : CUDART_INF_F;
-		sig[u] = want_h ? thr_ratio_le(H, beta_h) : -1.0f;
+		tau[u] = WP ? thr_ratio_ge(H + ZEN_EPS, beta) : CUDART_INF_F;
+		sig[u] = WH ? thr_ratio_le(H, beta_h) : -1.0f;
 		cp[u] = 0.0f;
 		ch[u] = 0.0f;
 	}
 	const float* base = E + k0 + woff;
+	auto tapf = [&](float x, int u) {
+		if (WP) cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
+		if (WH) ch[u] += ((x + ZEN_EPS) <= sig[u]) ? 1.0f : 0.0f;
+	};
 	// head: tap j belongs to bins u <= j only
 #pragma unroll
 	for (int j = 0; j < U - 1; ++j) {
-		const float x = base[j], sx = x + ZEN_EPS;
+		const float x = base[j];
 #pragma unroll
-		for (int u = 0; u <= j; ++u) {
-			cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
-			ch[u] += (sx <= sig[u]) ? 1.0f : 0.0f;
-		}
+		for (int u = 0; u <= j; ++u)
+			tapf(x, u);
 	}
 	// body: every bin of the group sees the tap (needs L >= U - 1, guaranteed by the caller)
+#pragma unroll 4
 	for (int j = U - 1; j < L; ++j) {
-		const float x = base[j], sx = x + ZEN_EPS;
+		const float x = base[j];
 #pragma unroll
-		for (int u = 0; u < U; ++u) {
-			cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
-			ch[u] += (sx <= sig[u]) ? 1.0f : 0.0f;
-		}
+		for (int u = 0; u < U; ++u)
+			tapf(x, u);
 	}
 	// tail: tap L + j belongs to bins u > j only
 #pragma unroll
 	for (int j = 0; j < U - 1; ++j) {
-		const float x = base[L + j], sx = x + ZEN_EPS;
+		const float x = base[L + j];
 #pragma unroll
-		for (int u = j + 1; u < U; ++u) {
-			cp[u] += (x >= tau[u]) ? 1.0f : 0.0f;
-			ch[u] += (sx <= sig[u]) ? 1.0f : 0.0f;
-		}
+		for (int u = j + 1; u < U; ++u)
+			tapf(x, u);
 	}
 	const float need = (float)(L / 2 + 1);
 	dp = 0u;
 	dh = 0u;
 #pragma unroll
 	for (int u = 0; u < U; ++u) {
-		dp |= (cp[u] >= need ? 1u : 0u) << u;
-		dh |= (ch[u] >= need ? 1u : 0u) << u;
+		if (WP) dp |= (cp[u] >= need ? 1u : 0u) << u;
+		if (WH) dh |= (ch[u] >= need ? 1u : 0u) << u;
 	}
+}
+
+template <int U>
+__device__ __forceinline__ void decide_group(const float* __restrict__ E, const float* __restrict__ hrow, int k0, int kmax, int woff,
+                                             int L, float beta, float beta_h, bool want_p, bool want_h, unsigned& dp, unsigned& dh)
+{
+	dp = 0u;
+	dh = 0u;
+	if (want_p && want_h)
+		decide_group_t<U, true, true>(E, hrow, k0, kmax, woff, L, beta, beta_h, dp, dh);
+	else if (want_p)
+		decide_group_t<U, true, false>(E, hrow, k0, kmax, woff, L, beta, beta_h, dp, dh);
+	else if (want_h)
+		decide_group_t<U, false, true>(E, hrow, k0, kmax, woff, L, beta, beta_h, dp, dh);
 }
 
 template <int L, typename Get>
@@ -259,10 +272,12 @@ __device__ __forceinline__ float median_fixed(Get get)
 
 // One hop.  `full` == false: analysis only (fills the rings; halo iterations of a tile).
 // All NT threads of the CTA must call it with identical arguments.
-template <int NFFT, int NT>
+// cur_stash (optional): the incoming hop is also copied there while it is read (the persistent
+// real-time kernel keeps it in shared memory as the next hop's `prev`).
+template <int NFFT, int NT, int U = ZEN_DECIDE_U>
 __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
                                               const float* __restrict__ prev, const float* __restrict__ cur,
-                                              bool full, bool fresh_tail, const HprEmit& em)
+                                              bool full, bool fresh_tail, const HprEmit& em, float* cur_stash = nullptr)
 {
 	constexpr int M = NFFT / 2;   // complex FFT length; also nwin
 	constexpr int HOP = M / 2;
@@ -283,8 +298,10 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			float2 x;
 			if (n < HOP / 2)
 				x = prev ? reinterpret_cast<const float2*>(prev)[n] : make_float2(0.0f, 0.0f);
-			else
+			else {
 				x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
+				if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
+			}
 			float2 w = __ldg(reinterpret_cast<const float2*>(P.window) + n);
 			z = make_float2(x.x * w.x, x.y * w.y);
 		}
@@ -404,7 +421,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		}
 	};
 
-	const bool decide = P.decide && !P.sse && !P.soft && P.Lp >= ZEN_DECIDE_U - 1;
+	const bool decide = P.decide && !P.sse && !P.soft && P.Lp >= U - 1;
 	if (decide) {
 		// ---- E'/F'. hard mask by counting (see decide_group).  The H row goes into zbuf, which is
 		// free between the split pass and the inverse-FFT build; codes go into prow:
@@ -415,19 +432,18 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		unsigned* codes = reinterpret_cast<unsigned*>(sm.prow);
 		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
 		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
-		constexpr int U = ZEN_DECIDE_U;
 		constexpr int NG = (M + 1 + U - 1) / U;
 		for (int g = tid; g < NG; g += NT) {
 			const int k0 = g * U;
 			unsigned fp, fh;
-			decide_group(sm.erow, hrow, k0, M, 0, P.Lp, P.beta, P.beta_h, want_p, want_h, fp, fh);
+			decide_group<U>(sm.erow, hrow, k0, M, 0, P.Lp, P.beta, P.beta_h, want_p, want_h, fp, fh);
 			unsigned bp = fp, bh = fh;
 			if (!P.copy_bord) {
 				// value at bin nfft-k: window k-L+1 .. k for k > L, never written (P = 0) for 1 <= k <= L
 				bp = 0u;
 				bh = 0u;
 				if (k0 + U - 1 > P.Lp)
-					decide_group(sm.erow, hrow, k0, M, -(P.Lp - 1), P.Lp, P.beta, P.beta_h, want_p, want_h, bp, bh);
+					decide_group<U>(sm.erow, hrow, k0, M, -(P.Lp - 1), P.Lp, P.beta, P.beta_h, want_p, want_h, bp, bh);
 			}
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
