@@ -116,6 +116,19 @@ int zen_hpr_copy_residual(zen_hpr* h, float* d_out_hop);
  * skipped.  This is the latency path (zen fakert's timed region). */
 int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* d_out_h, float* d_out_p, float* d_out_r);
 int zen_hpr_synchronize(zen_hpr* h);
+/* Resident real-time session for a causal stream: a persistent kernel keeps the
+ * stream's state in shared memory and serves zen_hpr_process_next_hop /
+ * zen_hpr_process_hop_io / zen_hpr_copy_* through a doorbell in mapped memory,
+ * so a hop costs neither a kernel launch nor a stream synchronisation.  Calls
+ * stay synchronous: on return the outputs are readable by the host.  The kernel
+ * leaves by itself after ZEN_B200_RT_IDLE_MS (default 250) without a hop and is
+ * brought back transparently by the next call; every other entry point pauses it
+ * first.  While it is resident, device-wide synchronisation (cudaDeviceSynchronize)
+ * waits for that idle time-out. */
+int zen_hpr_realtime_begin(zen_hpr* h);
+int zen_hpr_realtime_end(zen_hpr* h);
+/* diagnostics: device globaltimer (ns) at the phase boundaries of the last hop the resident kernel served */
+int zen_hpr_realtime_stamps(zen_hpr* h, unsigned long long* out16);
 /* Make caller-owned device buffers (nwin floats each, 8-byte aligned) the object's
  * streaming state, so that e.g. thrust::device_vector members named like the
  * reference's (hps.h:182-197) ARE the state; zeroes them (reset_buffers). */
@@ -136,7 +149,8 @@ int zen_hpr_materialize(zen_hpr* h, float* d_sliding_stft, float* d_s_mag, float
  * HPRRealtime<GPU>(fs, hop, beta, OUTPUT_PERCUSSIVE) + IOGPU(hop); warmup_iters
  * hops of iota data then reset (hps.cu:392-409); then per hop the region the
  * reference times: host copy-in -> process_next_hop -> copy_percussive -> host
- * copy-out.  fused != 0 replaces the two calls by zen_hpr_process_hop_io.
+ * copy-out.  fused == 1 replaces the two calls by zen_hpr_process_hop_io;
+ * fused == 2 additionally serves it from the resident kernel (zen_hpr_realtime_begin).
  * h_us_per_hop (optional) receives the wall time of each hop in microseconds. */
 int zen_fakert_run(float fs, int hop, float beta, int options, const float* h_audio, long n_hops,
                    int warmup_iters, int fused, float* h_perc_out, double* h_us_per_hop);

@@ -413,3 +413,49 @@ def test_decision_path_equals_median_path(torch, zen, fs, hop, flags, causal, cb
         if a is not None:
             assert np.array_equal(a, b_)
             assert np.abs(a).max() > 0
+
+
+@pytest.mark.parametrize("fs,hop,flags,cb,sse,soft", [(44100.0, 1024, 2, True, False, False), (44100.0, 1024, 7, False, False, False),
+                                                      (48000.0, 256, 7, True, False, False), (44100.0, 512, 3, True, True, False),
+                                                      (44100.0, 512, 7, True, False, True), (44100.0, 4096, 7, True, False, False)])
+def test_resident_realtime_kernel_equals_per_hop_launches(torch, zen, fs, hop, flags, cb, sse, soft):
+    """zen_hpr_realtime_begin: the persistent kernel (state in shared memory, doorbell in mapped memory) must
+    reproduce the per-launch path bit for bit, survive an idle time-out, and hand its state back on pause"""
+    import time
+    n_hops = 40
+    audio = synth_audio(n_hops * hop, seed=77, fs=int(fs))
+
+    def make():
+        h = zen.HPR(fs, hop, 2.5, flags, 0, cb)
+        if sse:
+            h.use_sse_filter()
+        if soft:
+            h.use_soft_mask()
+        return h
+    ref_obj = make()
+    ref = ref_obj.run(audio)
+    h = make()
+    io = zen.IOGPU(hop)
+    outs = [zen.IOGPU(hop) for _ in range(3)]
+    got = [np.zeros(n_hops * hop, np.float32) for _ in range(3)]
+    h.realtime_begin()
+    for i in range(n_hops):
+        if i == 10:
+            time.sleep(0.6)                  # longer than the idle time-out: the kernel leaves and is brought back
+        if i == 20:
+            mid_state = h.percussive_out     # pauses the resident kernel, reads the state from global memory
+            assert np.array_equal(mid_state[:hop], got[1][(i - 1) * hop:i * hop])
+        if i == 30:
+            h.realtime_end()                 # continue with per-hop launches on the same object
+        io.host_in[:] = audio[i * hop:(i + 1) * hop]
+        h.process_hop_io(io.device_in, outs[0].device_out, outs[1].device_out, outs[2].device_out)
+        h.synchronize()
+        for o in range(3):
+            if flags & (1 << o):
+                got[o][i * hop:(i + 1) * hop] = outs[o].host_out
+    for o in range(3):
+        if flags & (1 << o):
+            assert np.array_equal(got[o], ref[o]), o
+    assert np.array_equal(h.percussive_out, ref_obj.percussive_out)
+    h.close()
+    ref_obj.close()

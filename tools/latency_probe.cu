@@ -64,9 +64,9 @@ int main()
 		std::vector<float> audio(n_h * hop), perc(n_h * hop);
 		for (size_t i = 0; i < audio.size(); ++i) audio[i] = 0.3f * sinf(0.01f * i) + ((i % 7000) < 30 ? 0.7f : 0.0f);
 		std::vector<double> us(n_h);
-		for (int fused = 0; fused < 2; ++fused) {
+		for (int fused = 0; fused < 3; ++fused) {
 			zen_fakert_run(44100.0f, hop, 2.5f, 0, audio.data(), n_h, 300, fused, perc.data(), us.data());
-			std::printf("fakert region hop %4d %s p50 %.2f us\n", hop, fused ? "fused    " : "two-call ", p50(us));
+			std::printf("fakert region hop %4d %s p50 %.2f us\n", hop, fused == 2 ? "resident " : (fused ? "fused    " : "two-call "), p50(us));
 		}
 	}
 	return 0;

@@ -42,7 +42,7 @@ EXPORTS = [
     "zen_hpr_process_hop_io", "zen_hpr_synchronize", "zen_hpr_state_ptr", "zen_hpr_materialize",
     "zen_hpr_batch_create", "zen_hpr_batch_destroy", "zen_hpr_batch_process", "zen_hpr_batch_process_host",
     "zen_hpr_batch_last_launches", "zen_hpr_batch_last_kernel_ms", "zen_offline_process",
-    "zen_offline_process_device", "zen_copy_to_host", "zen_copy_to_device", "zen_fakert_run", "zen_host_alloc", "zen_host_free", "zen_hpr_bind_state",
+    "zen_offline_process_device", "zen_copy_to_host", "zen_copy_to_device", "zen_fakert_run", "zen_host_alloc", "zen_host_free", "zen_hpr_bind_state", "zen_hpr_realtime_begin", "zen_hpr_realtime_end", "zen_hpr_realtime_stamps",
 ]
 
 _lib = None
@@ -91,6 +91,9 @@ def lib():
     L.zen_offline_process.argtypes = [cf, ci, ci, cf, cf, ci, vp, cl, vp, vp, vp]
     L.zen_offline_process_device.argtypes = [cf, ci, ci, cf, cf, ci, vp, cl, vp, vp, vp, vp]
     L.zen_fakert_run.argtypes = [cf, ci, cf, ci, vp, cl, ci, ci, vp, vp]
+    L.zen_hpr_realtime_begin.argtypes = [vp]
+    L.zen_hpr_realtime_end.argtypes = [vp]
+    L.zen_hpr_realtime_stamps.argtypes = [vp, vp]
     L.zen_hpr_bind_state.argtypes = [vp, vp, vp, vp, vp]
     L.zen_host_alloc.argtypes = [ctypes.c_size_t]
     L.zen_host_alloc.restype = vp

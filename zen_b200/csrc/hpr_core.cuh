@@ -21,6 +21,13 @@ namespace zen_b200 {
 
 constexpr int ZEN_MAX_TAPS = 128;
 
+// rounding rule of `x / y >= c` for a float constant c (see thr_ratio_ge)
+struct RatioRule {
+	double m;      // rounding boundary just below the constant
+	int even;      // constant has an even mantissa: a tie rounds up to it
+	int trivial;   // 1: every non-negative value passes (constant <= 0); -1: nothing passes (NaN)
+};
+
 struct HprDev {
 	int hop, W, lag;
 	int n_taps;          // time-axis taps (0: the reference never writes the consumed row -> H = 0)
@@ -31,6 +38,7 @@ struct HprDev {
 	int decide;          // hard mask: decide M = [median >= threshold] by counting taps instead of selecting the median
 	float power;         // (float)(int)beta, soft-mask exponent (hps.h:116-129)
 	float beta, beta_h;  // beta, beta - eps (hps.cu:505, 540)
+	RatioRule rule_p, rule_h;  // exact rounding rules of the two hard-mask tests
 	float cola;
 	float lh1, lp1;      // l_harm + 1, l_perc + 1 (hps.cu:599-604)
 	float inv_lp;        // 1 / Lp for the box mean
@@ -139,54 +147,46 @@ __device__ __forceinline__ void hpr_masks(const HprDev& P, const float* prow, co
 __device__ __forceinline__ float f_next_up(float x) { return __uint_as_float(__float_as_uint(x) + 1u); }    // x >= 0, finite
 __device__ __forceinline__ float f_next_down(float x) { return __uint_as_float(__float_as_uint(x) - 1u); }  // x > 0
 
+// Exact thresholds without trial divisions.  For IEEE round-to-nearest-even division,
+//     RN(x / d) >= beta   <=>   x / d > m   or   (x / d == m and beta's mantissa is even)
+// where m = (pred(beta) + beta) / 2 is the rounding boundary below beta (25 significant bits, exact in
+// double).  x / d >< m is decided exactly as x >< d * m, because the product of a float (24 bits) and m
+// (25 bits) is exact in double.  HprDev carries m and the parity for beta and for beta - eps.
 // smallest float x >= 0 with RN(x / d) >= beta   (d > 0);  +inf if none
-__device__ __forceinline__ float thr_ratio_ge(float d, float beta)
+__device__ __forceinline__ float thr_ratio_ge(float d, const RatioRule& r)
 {
-	if (!(beta > 0.0f))
-		return beta == beta ? 0.0f : CUDART_INF_F;  // every x >= 0 passes; NaN beta: nothing passes
-	float c = beta * d;
-	if (!(c < CUDART_INF_F))
-		return CUDART_INF_F;
-	while (!((c / d) >= beta)) {
-		c = f_next_up(c);
-		if (!(c < CUDART_INF_F))
-			return CUDART_INF_F;
-	}
-	while (c > 0.0f) {
-		float q = f_next_down(c);
-		if ((q / d) >= beta)
-			c = q;
-		else
-			break;
-	}
-	return c;
+	if (r.trivial != 0)
+		return r.trivial > 0 ? 0.0f : CUDART_INF_F;
+	const double t = (double)d * r.m;               // exact
+	float x0 = __double2float_ru(t);                 // smallest float >= t
+	if ((double)x0 == t && !r.even)                  // exactly on the boundary and the tie rounds down
+		x0 = f_next_up(x0);
+	return x0;
 }
 
 // largest float s > 0 with RN(h / s) >= beta_h   (h >= 0);  -1 if none, +inf if every s passes
-__device__ __forceinline__ float thr_ratio_le(float h, float beta_h)
+__device__ __forceinline__ float thr_ratio_le(float h, const RatioRule& r)
 {
-	if (!(beta_h > 0.0f))
-		return beta_h == beta_h ? CUDART_INF_F : -1.0f;
+	if (r.trivial != 0)
+		return r.trivial > 0 ? CUDART_INF_F : -1.0f;
 	if (!(h > 0.0f))
 		return -1.0f;
-	float c = h / beta_h;
-	if (!(c > 0.0f))
-		return -1.0f;
-	if (!(c < CUDART_INF_F))
-		c = 3.402823466e+38f;
-	while (!((h / c) >= beta_h)) {
-		c = f_next_down(c);
-		if (!(c > 0.0f))
-			return -1.0f;
+	const double hd = (double)h;
+	auto pass = [&](float s) -> bool {               // h / s >= boundary, decided on exact products
+		const double p = (double)s * r.m;
+		return p < hd || (p == hd && r.even);
+	};
+	float s0 = __double2float_rd(hd / r.m);          // within one ulp of the answer
+	if (!(s0 < 3.402823466e+38f))
+		s0 = 3.402823466e+38f;
+	if (s0 > 0.0f && pass(s0)) {
+		const float up = f_next_up(s0);
+		return (up <= 3.402823466e+38f && pass(up)) ? up : s0;
 	}
-	while (c < 3.402823466e+38f) {
-		float q = f_next_up(c);
-		if ((h / q) >= beta_h)
-			c = q;
-		else
-			break;
-	}
-	return c;
+	if (!(s0 > 0.0f))
+		return (pass(1.401298464e-45f)) ? 1.401298464e-45f : -1.0f;
+	const float dn = f_next_down(s0);
+	return (dn > 0.0f && pass(dn)) ? dn : -1.0f;
 }
 
 constexpr int ZEN_DECIDE_U = 9;  // consecutive bins per thread in the batched kernels: odd, so the lanes' tap loads hit distinct banks
@@ -195,15 +195,15 @@ constexpr int ZEN_DECIDE_U = 9;  // consecutive bins per thread in the batched k
 // Returns bit u of *dp = [P >= tau_k], bit u of *dh = [P + eps <= sig_k]  for k = k0 + u.
 template <int U, bool WP, bool WH>
 __device__ __forceinline__ void decide_group_t(const float* __restrict__ E, const float* __restrict__ hrow, int k0, int kmax, int woff,
-                                               int L, float beta, float beta_h, unsigned& dp, unsigned& dh)
+                                               int L, const RatioRule& rp, const RatioRule& rh, unsigned& dp, unsigned& dh)
 {
 	float tau[U], sig[U], cp[U], ch[U];
 #pragma unroll
 	for (int u = 0; u < U; ++u) {
 		const int k = min(k0 + u, kmax);
 		const float H = hrow[k];
-		tau[u] = WP ? thr_ratio_ge(H + ZEN_EPS, beta) : CUDART_INF_F;
-		sig[u] = WH ? thr_ratio_le(H, beta_h) : -1.0f;
+		tau[u] = WP ? thr_ratio_ge(H + ZEN_EPS, rp) : CUDART_INF_F;
+		sig[u] = WH ? thr_ratio_le(H, rh) : -1.0f;
 		cp[u] = 0.0f;
 		ch[u] = 0.0f;
 	}
@@ -248,16 +248,17 @@ __device__ __forceinline__ void decide_group_t(const float* __restrict__ E, cons
 
 template <int U>
 __device__ __forceinline__ void decide_group(const float* __restrict__ E, const float* __restrict__ hrow, int k0, int kmax, int woff,
-                                             int L, float beta, float beta_h, bool want_p, bool want_h, unsigned& dp, unsigned& dh)
+                                             int L, const RatioRule& rp, const RatioRule& rh, bool want_p, bool want_h, unsigned& dp,
+                                             unsigned& dh)
 {
 	dp = 0u;
 	dh = 0u;
 	if (want_p && want_h)
-		decide_group_t<U, true, true>(E, hrow, k0, kmax, woff, L, beta, beta_h, dp, dh);
+		decide_group_t<U, true, true>(E, hrow, k0, kmax, woff, L, rp, rh, dp, dh);
 	else if (want_p)
-		decide_group_t<U, true, false>(E, hrow, k0, kmax, woff, L, beta, beta_h, dp, dh);
+		decide_group_t<U, true, false>(E, hrow, k0, kmax, woff, L, rp, rh, dp, dh);
 	else if (want_h)
-		decide_group_t<U, false, true>(E, hrow, k0, kmax, woff, L, beta, beta_h, dp, dh);
+		decide_group_t<U, false, true>(E, hrow, k0, kmax, woff, L, rp, rh, dp, dh);
 }
 
 template <int L, typename Get>
@@ -277,8 +278,17 @@ __device__ __forceinline__ float median_fixed(Get get)
 template <int NFFT, int NT, int U = ZEN_DECIDE_U>
 __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
                                               const float* __restrict__ prev, const float* __restrict__ cur,
-                                              bool full, bool fresh_tail, const HprEmit& em, float* cur_stash = nullptr)
+                                              bool full, bool fresh_tail, const HprEmit& em, float* cur_stash = nullptr,
+                                              unsigned long long* stamps = nullptr)
 {
+	auto stamp = [&](int idx) {
+		if (stamps && threadIdx.x == 0) {
+			unsigned long long t;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+			stamps[idx] = t;
+		}
+	};
+	stamp(0);
 	constexpr int M = NFFT / 2;   // complex FFT length; also nwin
 	constexpr int HOP = M / 2;
 	const int tid = threadIdx.x;
@@ -308,9 +318,11 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		sm.zbuf[fpad(n)] = z;
 	}
 	__syncthreads();
+	stamp(1);
 
 	// ---- B. forward FFT (hps.cu:465)
 	fft_smem<M, NT, -1>(sm.zbuf, P.tw, tid);
+	stamp(2);
 
 	// ---- C. split into the real-input spectrum X[0..M], magnitudes into the ring (hps.cu:469-472, 492-493)
 	{
@@ -360,6 +372,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		}
 	}
 	__syncthreads();
+	stamp(3);
 	if (!full)
 		return;
 
@@ -429,6 +442,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		float* hrow = reinterpret_cast<float*>(sm.zbuf);
 		compute_h_row(hrow);
 		__syncthreads();
+		stamp(4);
 		unsigned* codes = reinterpret_cast<unsigned*>(sm.prow);
 		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
 		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
@@ -436,14 +450,14 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		for (int g = tid; g < NG; g += NT) {
 			const int k0 = g * U;
 			unsigned fp, fh;
-			decide_group<U>(sm.erow, hrow, k0, M, 0, P.Lp, P.beta, P.beta_h, want_p, want_h, fp, fh);
+			decide_group<U>(sm.erow, hrow, k0, M, 0, P.Lp, P.rule_p, P.rule_h, want_p, want_h, fp, fh);
 			unsigned bp = fp, bh = fh;
 			if (!P.copy_bord) {
 				// value at bin nfft-k: window k-L+1 .. k for k > L, never written (P = 0) for 1 <= k <= L
 				bp = 0u;
 				bh = 0u;
 				if (k0 + U - 1 > P.Lp)
-					decide_group<U>(sm.erow, hrow, k0, M, -(P.Lp - 1), P.Lp, P.beta, P.beta_h, want_p, want_h, bp, bh);
+					decide_group<U>(sm.erow, hrow, k0, M, -(P.Lp - 1), P.Lp, P.rule_p, P.rule_h, want_p, want_h, bp, bh);
 			}
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
@@ -466,6 +480,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			}
 		}
 		__syncthreads();
+		stamp(5);
 	}
 	else {
 		// ---- E. frequency axis: prow[s] = median / mean of erow[s .. s+Lp)
@@ -545,7 +560,9 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			}
 		}
 		__syncthreads();
+		stamp(6);
 		fft_smem<M, NT, +1>(sm.zbuf, P.tw, tid);
+		stamp(7);
 		// overlap-add: out = tail + Re(y[0:hop]) * COLA ; tail' = Re(y[hop:nwin]) * COLA   (hps.h:68-80)
 		float* tail = st.tail[o];
 		for (int n = tid; n < HOP / 2; n += NT) {
@@ -561,6 +578,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			reinterpret_cast<float2*>(tail)[n - HOP / 2] = make_float2(v.x * P.cola, v.y * P.cola);
 		}
 		__syncthreads();
+		stamp(8);
 	}
 }
 

@@ -5,7 +5,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <vector>
+
+#include <xmmintrin.h>
 
 #include "hpr_launch.cuh"
 
@@ -46,6 +49,35 @@ struct Plan {
 	size_t smem_bytes = 0;
 };
 
+// rounding boundary of RN(x / y) >= c: the midpoint between c and its predecessor (hpr_core.cuh: thr_ratio_ge)
+RatioRule make_ratio_rule(float c)
+{
+	RatioRule r;
+	r.m = 0.0;
+	r.even = 0;
+	r.trivial = 0;
+	if (c != c) {
+		r.trivial = -1;
+		return r;
+	}
+	if (!(c > 0.0f)) {
+		r.trivial = 1;
+		return r;
+	}
+	if (std::isinf(c)) {
+		r.trivial = -1;
+		return r;
+	}
+	uint32_t bits;
+	std::memcpy(&bits, &c, sizeof(bits));
+	uint32_t pb = bits - 1u;
+	float pred;
+	std::memcpy(&pred, &pb, sizeof(pred));
+	r.m = 0.5 * ((double)pred + (double)c);
+	r.even = (bits & 1u) == 0u;
+	return r;
+}
+
 int build_plan(Plan& pl, float fs, int hop, float beta, unsigned flags, int causality, int copy_bord, bool sse, bool soft)
 {
 	if (hop < 32 || hop > 4096 || !is_pow2(hop))
@@ -79,6 +111,8 @@ int build_plan(Plan& pl, float fs, int hop, float beta, unsigned flags, int caus
 	d.power = (float)(int)beta;
 	d.beta = beta;
 	d.beta_h = beta - ZEN_EPS;
+	d.rule_p = make_ratio_rule(d.beta);
+	d.rule_h = make_ratio_rule(d.beta_h);
 	d.cola = g.cola_factor;
 	d.lh1 = (float)g.l_harm + 1.0f;
 	d.lp1 = (float)g.l_perc + 1.0f;
@@ -186,6 +220,15 @@ struct zen_hpr {
 	float* d_ola[3] = {nullptr, nullptr, nullptr};  // nwin each (harmonic_out, percussive_out, residual_out)
 	float* d_mag_ring = nullptr;
 	float2* d_x_ring = nullptr;
+	// persistent real-time session (zen_hpr_realtime_begin)
+	bool rt_mode = false;      // hops are served by the resident kernel
+	bool rt_running = false;   // a resident kernel has been launched and not yet collected
+	RtCtrl* rt_ctrl = nullptr;
+	RtCtrl* rt_ctrl_dev = nullptr;
+	cudaStream_t rt_stream = nullptr;
+	int* d_iter = nullptr;
+	unsigned rt_seq = 0;
+	unsigned long long rt_idle_ns = 250ull * 1000 * 1000;
 };
 
 namespace {
@@ -223,6 +266,140 @@ int dispatch_hop(zen_hpr* h, const float* in_hop, float* eh, float* ep, float* e
 	return rc;
 }
 
+int rebuild_plan_fwd(zen_hpr* h);
+
+// ---- persistent real-time session -------------------------------------------
+
+int rt_launch(zen_hpr* h)
+{
+	if (!h->rt_ctrl) {
+		ZEN_CUDA_CHECK(cudaHostAlloc((void**)&h->rt_ctrl, sizeof(RtCtrl), cudaHostAllocMapped | cudaHostAllocPortable));
+		std::memset((void*)h->rt_ctrl, 0, sizeof(RtCtrl));
+		ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->rt_ctrl_dev, (void*)h->rt_ctrl, 0));
+		ZEN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->rt_stream, cudaStreamNonBlocking));
+		ZEN_CUDA_CHECK(cudaMalloc(&h->d_iter, sizeof(int)));
+		if (const char* e = std::getenv("ZEN_B200_RT_IDLE_MS")) {
+			long ms = std::atol(e);
+			if (ms > 0) h->rt_idle_ns = (unsigned long long)ms * 1000ull * 1000ull;
+		}
+	}
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+	int it = (int)h->iter;
+	ZEN_CUDA_CHECK(cudaMemcpy(h->d_iter, &it, sizeof(int), cudaMemcpyHostToDevice));
+	RtArgs a;
+	a.dev = h->plan.dev;
+	a.ctrl = h->rt_ctrl_dev;
+	a.mag_ring = h->d_mag_ring;
+	a.input = h->d_input;
+	for (int o = 0; o < 3; ++o)
+		a.ola[o] = h->d_ola[o];
+	a.iter = h->d_iter;
+	a.seq0 = h->rt_seq;
+	a.idle_ns = h->rt_idle_ns;
+	a.stream = h->rt_stream;
+	h->rt_ctrl->seq_out = h->rt_seq;
+	h->rt_ctrl->exit_reason = 0;
+	h->rt_ctrl->alive = 1;
+	_mm_sfence();
+	int rc = ZEN_ERR_UNSUPPORTED;
+	const size_t limit = 227 * 1024;
+#define ZEN_RT_CASE(N)                                                            \
+	case N:                                                                       \
+		a.state_in_smem = rt_smem_bytes<N>(a.dev, 1) <= limit ? 1 : 0;            \
+		rc = launch_rt_impl<N>(a);                                                \
+		break;
+	switch (h->plan.nfft) {
+		ZEN_RT_CASE(128)
+		ZEN_RT_CASE(256)
+		ZEN_RT_CASE(512)
+		ZEN_RT_CASE(1024)
+		ZEN_RT_CASE(2048)
+		ZEN_RT_CASE(4096)
+		ZEN_RT_CASE(8192)
+		ZEN_RT_CASE(16384)
+	}
+#undef ZEN_RT_CASE
+	if (rc == ZEN_OK)
+		h->rt_running = true;
+	else
+		h->rt_ctrl->alive = 0;
+	return rc;
+}
+
+// the resident kernel has left (stop or idle time-out): fetch the frame counter
+int rt_collect(zen_hpr* h)
+{
+	if (!h->rt_running)
+		return ZEN_OK;
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->rt_stream));
+	int it = 0;
+	ZEN_CUDA_CHECK(cudaMemcpy(&it, h->d_iter, sizeof(int), cudaMemcpyDeviceToHost));
+	h->iter = it;
+	h->rt_running = false;
+	return ZEN_OK;
+}
+
+int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, float* o2, int which)
+{
+	if (h->plan_dirty) {
+		int rc = rt_collect(h);  // cannot be running with a dirty plan, but be safe
+		if (rc == ZEN_OK) rc = rebuild_plan_fwd(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	if (!h->rt_running) {
+		int rc = rt_launch(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	RtCtrl* c = h->rt_ctrl;
+	const unsigned target = h->rt_seq + 1;
+	c->op = op;
+	c->in = in;
+	c->out[0] = o0;
+	c->out[1] = o1;
+	c->out[2] = o2;
+	c->which = which;
+	_mm_sfence();  // the caller's samples sit in write-combined memory (IOGPU::host_in): drain them first
+	c->seq_in = target;
+	const auto t0 = std::chrono::steady_clock::now();
+	unsigned spins = 0;
+	while (c->seq_out != target) {
+		if ((++spins & 1023u) == 0) {
+			if (!c->alive) {
+				if (c->seq_out == target)
+					break;
+				// the kernel timed out between our check and the doorbell: bring it back, it will see the doorbell
+				int rc = rt_collect(h);
+				if (rc == ZEN_OK && op != RT_OP_STOP) rc = rt_launch(h);
+				if (rc != ZEN_OK) return rc;
+				if (op == RT_OP_STOP) break;
+			}
+			if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+				std::fprintf(stderr, "zen_b200: the resident real-time kernel did not answer within 5 s\n");
+				return ZEN_ERR_CUDA;
+			}
+		}
+	}
+	h->rt_seq = target;
+	return ZEN_OK;
+}
+
+// leave the resident kernel (state goes back to global memory); rt_mode is kept
+int rt_pause(zen_hpr* h)
+{
+	if (!h->rt_running)
+		return ZEN_OK;
+	if (h->rt_ctrl->alive) {
+		int rc = rt_call(h, RT_OP_STOP, nullptr, nullptr, nullptr, nullptr, 0);
+		if (rc != ZEN_OK) return rc;
+		const auto t0 = std::chrono::steady_clock::now();
+		while (h->rt_ctrl->alive) {
+			if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5))
+				return ZEN_ERR_CUDA;
+		}
+	}
+	return rt_collect(h);
+}
+
 int rebuild_plan(zen_hpr* h)
 {
 	free_plan(h->plan);
@@ -230,6 +407,8 @@ int rebuild_plan(zen_hpr* h)
 	h->plan_dirty = false;
 	return rc;
 }
+
+int rebuild_plan_fwd(zen_hpr* h) { return rebuild_plan(h); }
 
 }  // namespace
 
@@ -278,6 +457,10 @@ void zen_hpr_destroy(zen_hpr* h)
 {
 	if (!h)
 		return;
+	rt_pause(h);
+	if (h->rt_ctrl) cudaFreeHost((void*)h->rt_ctrl);
+	if (h->rt_stream) cudaStreamDestroy(h->rt_stream);
+	cudaFree(h->d_iter);
 	if (h->stream) cudaStreamSynchronize(h->stream);
 	free_plan(h->plan);
 	if (!h->state_external) {
@@ -294,6 +477,7 @@ void zen_hpr_destroy(zen_hpr* h)
 int zen_hpr_use_sse_filter(zen_hpr* h)
 {
 	if (!h) return ZEN_ERR_ARG;
+	if (rt_pause(h) != ZEN_OK) return ZEN_ERR_CUDA;
 	h->sse = true;
 	h->plan_dirty = true;
 	return ZEN_OK;
@@ -302,6 +486,7 @@ int zen_hpr_use_sse_filter(zen_hpr* h)
 int zen_hpr_use_soft_mask(zen_hpr* h)
 {
 	if (!h) return ZEN_ERR_ARG;
+	if (rt_pause(h) != ZEN_OK) return ZEN_ERR_CUDA;
 	h->soft = true;
 	h->plan_dirty = true;
 	return ZEN_OK;
@@ -310,6 +495,7 @@ int zen_hpr_use_soft_mask(zen_hpr* h)
 int zen_hpr_reset_buffers(zen_hpr* h)
 {
 	if (!h) return ZEN_ERR_ARG;
+	if (rt_pause(h) != ZEN_OK) return ZEN_ERR_CUDA;
 	const zen_geometry& g = h->plan.geom;
 	const int M = g.nfft / 2;
 	ZEN_CUDA_CHECK(cudaMemsetAsync(h->d_input, 0, sizeof(float) * g.nwin, h->stream));
@@ -332,6 +518,8 @@ int zen_hpr_get_geometry(const zen_hpr* h, zen_geometry* out)
 int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* eh, float* ep, float* er)
 {
 	if (!h || !d_in_hop) return ZEN_ERR_ARG;
+	if (h->rt_mode)
+		return rt_call(h, RT_OP_PROCESS, d_in_hop, eh, ep, er, 0);
 	if (h->plan_dirty) {
 		int rc = rebuild_plan(h);
 		if (rc != ZEN_OK) return rc;
@@ -347,6 +535,8 @@ int zen_hpr_process_next_hop(zen_hpr* h, const float* d_in_hop)
 static int copy_out(zen_hpr* h, int o, float* d_out)
 {
 	if (!h || !d_out) return ZEN_ERR_ARG;
+	if (h->rt_mode)
+		return rt_call(h, RT_OP_COPY, nullptr, d_out, nullptr, nullptr, o);
 	int hop = h->hop;
 	copy_hop_kernel<<<(hop + 255) / 256, 256, 0, h->stream>>>(h->d_ola[o], d_out, hop);
 	ZEN_CUDA_CHECK(cudaGetLastError());
@@ -365,12 +555,42 @@ int zen_hpr_synchronize(zen_hpr* h)
 	return ZEN_OK;
 }
 
+int zen_hpr_realtime_begin(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	if (h->plan.dev.lag != 1) return ZEN_ERR_UNSUPPORTED;  // the resident kernel serves causal streams (HPRRealtime)
+	if (h->plan_dirty) {
+		int rc = rebuild_plan(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	h->rt_mode = true;
+	return h->rt_running ? ZEN_OK : rt_launch(h);
+}
+
+// diagnostics: device globaltimer stamps (ns) of the last hop served by the resident kernel
+int zen_hpr_realtime_stamps(zen_hpr* h, unsigned long long* out16)
+{
+	if (!h || !out16 || !h->rt_ctrl) return ZEN_ERR_ARG;
+	for (int i = 0; i < 16; ++i)
+		out16[i] = h->rt_ctrl->stamps[i];
+	return ZEN_OK;
+}
+
+int zen_hpr_realtime_end(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	int rc = rt_pause(h);
+	h->rt_mode = false;
+	return rc;
+}
+
 int zen_hpr_bind_state(zen_hpr* h, float* d_input, float* d_harmonic_out, float* d_percussive_out, float* d_residual_out)
 {
 	if (!h || !d_input || !d_harmonic_out || !d_percussive_out || !d_residual_out)
 		return ZEN_ERR_ARG;
 	if (((uintptr_t)d_input | (uintptr_t)d_harmonic_out | (uintptr_t)d_percussive_out | (uintptr_t)d_residual_out) & 7)
 		return ZEN_ERR_ARG;
+	if (rt_pause(h) != ZEN_OK) return ZEN_ERR_CUDA;
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	if (!h->state_external) {
 		cudaFree(h->d_input);
@@ -388,6 +608,7 @@ int zen_hpr_bind_state(zen_hpr* h, float* d_input, float* d_harmonic_out, float*
 float* zen_hpr_state_ptr(zen_hpr* h, int which)
 {
 	if (!h) return nullptr;
+	if (rt_pause(h) != ZEN_OK) return nullptr;  // the overlap-add tails live in the resident kernel's shared memory
 	switch (which) {
 	case 0: return h->d_input;
 	case 1: return h->d_ola[0];
@@ -424,6 +645,14 @@ extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const 
 	if (rc != ZEN_OK) {
 		zen_hpr_destroy(h);
 		return rc;
+	}
+	if (fused == 2) {
+		rc = zen_hpr_realtime_begin(h);  // resident kernel: no launch, no stream synchronisation per hop
+		if (rc != ZEN_OK) {
+			zen_io_free(&io);
+			zen_hpr_destroy(h);
+			return rc;
+		}
 	}
 	// HPRRealtime<GPU>::warmup (hps.cu:392-409): iota data, then reset_buffers
 	for (int i = 0; i < warmup_iters && rc == ZEN_OK; ++i) {
@@ -531,6 +760,8 @@ extern "C" int zen_hpr_materialize(zen_hpr* h, float* d_stft, float* d_s_mag, fl
 {
 	if (!h)
 		return ZEN_ERR_ARG;
+	if (rt_pause(h) != ZEN_OK)
+		return ZEN_ERR_CUDA;
 	if (h->plan_dirty) {
 		int rc = rebuild_plan(h);
 		if (rc != ZEN_OK) return rc;

@@ -42,8 +42,48 @@ struct HopArgs {
 	cudaStream_t stream;
 };
 
+// Control block of the persistent real-time kernel, in mapped pinned host memory.
+// Host -> device: fill the arguments, then publish seq_in (the doorbell).
+// Device -> host: seq_out = the sequence number just completed.
+struct RtCtrl {
+	volatile unsigned seq_in;
+	volatile unsigned op;          // RT_OP_*
+	const float* in;               // device-visible pointer to the incoming hop
+	float* out[3];                 // device-visible destinations of the emitted hop (H, P, R) or null
+	int which;                     // RT_OP_COPY: which output
+	unsigned pad0[16];
+	volatile unsigned seq_out;     // own cache line
+	volatile unsigned alive;       // 1 while the kernel is resident
+	volatile unsigned exit_reason; // 1 stop requested, 2 idle time-out
+	unsigned pad1[13];
+	unsigned long long stamps[16]; // globaltimer at the phase boundaries of the last hop (diagnostics)
+};
+enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3 };
+
+struct RtArgs {
+	HprDev dev;
+	RtCtrl* ctrl;          // device alias of the control block
+	float* mag_ring;       // global state, loaded at start and written back at exit
+	float* input;          // nwin
+	float* ola[3];         // nwin each
+	int* iter;             // frame counter, read at start, written back at exit
+	unsigned seq0;         // last sequence number already served
+	unsigned long long idle_ns;
+	int state_in_smem;     // ring + tails resident in shared memory
+	cudaStream_t stream;
+};
+
+template <int NFFT>
+constexpr int nt_rt_for()
+{
+	return (NFFT / 8) < 128 ? 128 : ((NFFT / 8) > 512 ? 512 : (NFFT / 8));
+}
+constexpr int ZEN_RT_U = 5;
+
 template <int NFFT> int launch_tile_impl(const TileArgs& a);
 template <int NFFT> int launch_hop_impl(const HopArgs& a);
+template <int NFFT> int launch_rt_impl(const RtArgs& a);
+template <int NFFT> size_t rt_smem_bytes(const HprDev& d, int state_in_smem);
 
 }  // namespace zen_b200
 
@@ -143,6 +183,160 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_hop_kernel(const
 }
 
 
+
+// Persistent real-time kernel: one resident CTA serves one stream hop after hop.
+// The host writes the hop into mapped memory and rings a doorbell; the CTA polls
+// it, runs the fused step with ring / overlap-add tails / previous hop held in
+// SHARED memory, writes the outputs straight to mapped host memory and publishes
+// the completion flag.  No launch and no stream synchronisation per hop (those
+// alone cost ~9 us on this box).  The kernel leaves on RT_OP_STOP or after
+// idle_ns without a doorbell, writing its state back to global memory so the
+// per-launch kernels (or a later session) continue seamlessly.
+__device__ __forceinline__ unsigned long long rt_globaltimer()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+template <int NFFT, int NT>
+__global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ HprDev P, RtCtrl* ctrl, float* g_ring, float* g_input,
+                                                       float* g_ola_h, float* g_ola_p, float* g_ola_r, int* g_iter, unsigned seq0,
+                                                       unsigned long long idle_ns, int state_in_smem)
+{
+	constexpr int M = NFFT / 2, HOP = M / 2;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	HprSmem<NFFT> sm;
+	sm.carve(smem_raw, P.Lp);
+	float* extra = reinterpret_cast<float*>(smem_raw + ((HprSmem<NFFT>::bytes(P.Lp) + 15) & ~(size_t)15));
+	// double buffer: previous hop / incoming hop (in global memory, i.e. the `input` vector itself, when smem is short)
+	float* hopbuf[2] = {state_in_smem ? extra : g_input, state_in_smem ? extra + HOP : g_input + HOP};
+	if (state_in_smem) extra += 2 * HOP;
+	const int tid = threadIdx.x;
+	const int ring_n = P.W * (M + 1);
+	float* g_ola[3] = {g_ola_h, g_ola_p, g_ola_r};
+	HprState st;
+	st.x_ring = nullptr;
+	st.xdepth = 0;
+	if (state_in_smem) {
+		st.mag_ring = extra;
+		extra += (ring_n + 3) & ~3;
+		for (int o = 0; o < 3; ++o)
+			st.tail[o] = extra + o * HOP;
+		for (int n = tid; n < ring_n; n += NT)
+			st.mag_ring[n] = g_ring[n];
+		for (int o = 0; o < 3; ++o)
+			for (int n = tid; n < HOP; n += NT)
+				st.tail[o][n] = g_ola[o][HOP + n];
+	}
+	else {
+		st.mag_ring = g_ring;
+		for (int o = 0; o < 3; ++o)
+			st.tail[o] = g_ola[o] + HOP;
+	}
+	if (state_in_smem) {
+		for (int n = tid; n < HOP; n += NT) {
+			hopbuf[0][n] = g_input[n];          // older hop (only kept so `input` can be written back)
+			hopbuf[1][n] = g_input[HOP + n];    // the previous hop
+		}
+	}
+	int prev_idx = 1;
+	int iter = *g_iter;
+	unsigned seq = seq0;
+	__shared__ unsigned s_op, s_seq;
+	__shared__ const float* s_in;
+	__shared__ float* s_out[3];
+	__shared__ int s_which;
+	__syncthreads();
+
+	for (;;) {
+		if (tid == 0) {
+			const unsigned long long t0 = rt_globaltimer();
+			unsigned now = seq;
+			unsigned spins = 0;
+			for (;;) {
+				now = ctrl->seq_in;
+				if (now != seq)
+					break;
+				if ((++spins & 63u) == 0 && rt_globaltimer() - t0 > idle_ns)
+					break;
+			}
+			if (now == seq) {
+				s_op = 0xffffffffu;  // idle time-out
+			}
+			else {
+				__threadfence_system();  // order the argument reads after the doorbell read
+				s_op = ctrl->op;
+				s_in = ctrl->in;
+				s_out[0] = ctrl->out[0];
+				s_out[1] = ctrl->out[1];
+				s_out[2] = ctrl->out[2];
+				s_which = ctrl->which;
+			}
+			s_seq = now;
+		}
+		__syncthreads();
+		const unsigned op = s_op;
+		if (op == 0xffffffffu || op == RT_OP_STOP) {
+			if (tid == 0) ctrl->exit_reason = (op == RT_OP_STOP) ? 1u : 2u;
+			if (op == RT_OP_STOP) seq = s_seq;
+			break;
+		}
+		if (op == RT_OP_PROCESS) {
+			HprEmit em;
+			for (int o = 0; o < 3; ++o) {
+				const bool on = (P.out_flags & (1 << o)) != 0;
+				em.a[o] = on ? g_ola[o] : nullptr;   // keep the public *_out vectors current (hps.h:195-197)
+				em.b[o] = on ? s_out[o] : nullptr;
+			}
+			float* stash = hopbuf[prev_idx ^ 1];
+			if (tid == 0) ctrl->stamps[9] = rt_globaltimer();
+			hpr_iteration<NFFT, NT, ZEN_RT_U>(P, sm, st, iter, hopbuf[prev_idx], s_in, true, false, em, stash, ctrl->stamps);
+			if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && s_out[2])
+				for (int n = tid; n < HOP; n += NT)
+					s_out[2][n] = 0.0f;
+			prev_idx ^= 1;
+			++iter;
+		}
+		else if (op == RT_OP_COPY) {
+			const float* src = g_ola[s_which];
+			float* dst = s_out[0];
+			for (int n = tid; n < HOP; n += NT)
+				dst[n] = src[n];
+		}
+		__syncthreads();
+		seq = s_seq;
+		if (tid == 0) {
+			__threadfence_system();
+			ctrl->seq_out = seq;
+		}
+	}
+
+	// write the state back
+	if (state_in_smem) {
+		for (int n = tid; n < ring_n; n += NT)
+			g_ring[n] = st.mag_ring[n];
+		for (int o = 0; o < 3; ++o)
+			for (int n = tid; n < HOP; n += NT)
+				g_ola[o][HOP + n] = st.tail[o][n];
+	}
+	if (state_in_smem || prev_idx == 0) {
+		// `input` must read [older hop | newest hop]; when it served as the double buffer itself, swap the halves if needed
+		for (int n = tid; n < HOP; n += NT) {
+			float older = hopbuf[prev_idx ^ 1][n], newest = hopbuf[prev_idx][n];
+			g_input[n] = older;
+			g_input[HOP + n] = newest;
+		}
+	}
+	if (tid == 0) *g_iter = iter;
+	__syncthreads();
+	if (tid == 0) {
+		__threadfence_system();
+		ctrl->seq_out = seq;
+		ctrl->alive = 0u;
+	}
+}
+
 namespace zen_b200 {
 
 template <int NFFT>
@@ -176,8 +370,33 @@ int launch_hop_impl(const HopArgs& a)
 	return ZEN_OK;
 }
 
+template <int NFFT>
+size_t rt_smem_bytes(const HprDev& d, int state_in_smem)
+{
+	constexpr int M = NFFT / 2, HOP = M / 2;
+	size_t b = (HprSmem<NFFT>::bytes(d.Lp) + 15) & ~(size_t)15;
+	if (state_in_smem)
+		b += sizeof(float) * (2 * (size_t)HOP + (((size_t)d.W * (M + 1) + 3) & ~(size_t)3) + 3 * (size_t)HOP);
+	return b;
+}
+
+template <int NFFT>
+int launch_rt_impl(const RtArgs& a)
+{
+	constexpr int NT = nt_rt_for<NFFT>();
+	auto kern = hpr_rt_kernel<NFFT, NT>;
+	size_t smem = rt_smem_bytes<NFFT>(a.dev, a.state_in_smem);
+	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	kern<<<1, NT, smem, a.stream>>>(a.dev, a.ctrl, a.mag_ring, a.input, a.ola[0], a.ola[1], a.ola[2], a.iter, a.seq0, a.idle_ns,
+	                                a.state_in_smem);
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	return ZEN_OK;
+}
+
 template int launch_tile_impl<ZEN_HPR_INSTANTIATE>(const TileArgs&);
 template int launch_hop_impl<ZEN_HPR_INSTANTIATE>(const HopArgs&);
+template int launch_rt_impl<ZEN_HPR_INSTANTIATE>(const RtArgs&);
+template size_t rt_smem_bytes<ZEN_HPR_INSTANTIATE>(const HprDev&, int);
 
 }  // namespace zen_b200
 #endif

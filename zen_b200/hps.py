@@ -185,6 +185,13 @@ class HPR:
     def synchronize(self):
         check(_lib.lib().zen_hpr_synchronize(self._h), "synchronize")
 
+    def realtime_begin(self):
+        """serve the following hops from the resident (persistent) kernel"""
+        check(_lib.lib().zen_hpr_realtime_begin(self._h), "realtime_begin")
+
+    def realtime_end(self):
+        check(_lib.lib().zen_hpr_realtime_end(self._h), "realtime_end")
+
     def _state(self, which, n):
         self.synchronize()
         out = np.empty(n, dtype=np.float32)
