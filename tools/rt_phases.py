@@ -19,9 +19,9 @@ for i in range(400):
     _lib.lib().zen_hpr_realtime_stamps(h._h, st)
     if i >= 100:
         s = list(st)
-        acc.append([(t1 - t0) * 1e6] + [(s[k + 1] - s[k]) / 1e3 for k in range(8)] + [(s[0] - s[9]) / 1e3, (s[8] - s[9]) / 1e3])
+        acc.append([(t1 - t0) * 1e6] + [(s[k + 1] - s[k]) / 1e3 for k in range(8)] + [(s[0] - s[9]) / 1e3, (s[8] - s[9]) / 1e3, (s[11] - s[10]) / max(1.0, float(s[8] - s[9]))])
 a = np.median(np.array(acc), axis=0)
-names = ["host call us", "A load+window", "B fft fwd", "C split+mag", "F' H row", "E' decide", "G build", "G ifft", "G ola+emit", "pre", "kernel total"]
+names = ["host call us", "A load+window", "B fft fwd", "C split+mag", "F' H row", "E' decide", "G build", "G ifft", "G ola+emit", "pre", "kernel total", "SM clock GHz"]
 for n, v in zip(names, a):
     print("%-14s %7.2f us" % (n, v))
 h.close()

@@ -1,6 +1,7 @@
 // FFTC2CWrapperGPU::forward / backward (libzen/fftw.h:35-43) without cuFFT:
 // one CTA runs the shared-memory Stockham FFT of fft_smem.cuh on the whole
 // transform.  Unnormalised in both directions, like cufftExecC2C.
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(NT) fft_c2c_kernel(float2* __restrict__ data, 
 		data[i] = buf[fpad(i)];
 }
 
-// twiddle tables exp(-2 pi i t / N), one per size and device, built on first use
+// per-stage twiddle tables (fft_fill_twiddles), one per size and device, built on first use
 struct TwiddleCache {
 	std::mutex mu;
 	float2* tab[8][20] = {};
@@ -36,14 +37,13 @@ struct TwiddleCache {
 			return nullptr;
 		std::lock_guard<std::mutex> lk(mu);
 		if (!tab[dev][order]) {
-			std::vector<float2> h(n);
-			const double two_pi = 6.283185307179586476925286766559;
-			for (int t = 0; t < n; ++t)
-				h[t] = make_float2((float)std::cos(two_pi * t / n), (float)-std::sin(two_pi * t / n));
+			const int cnt = std::max(1, fft_twiddle_count_rt(n));
+			std::vector<float2> h(cnt);
+			fft_fill_twiddles(n, h.data());
 			float2* d = nullptr;
-			if (cudaMalloc(&d, sizeof(float2) * n) != cudaSuccess)
+			if (cudaMalloc(&d, sizeof(float2) * cnt) != cudaSuccess)
 				return nullptr;
-			if (cudaMemcpy(d, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+			if (cudaMemcpy(d, h.data(), sizeof(float2) * cnt, cudaMemcpyHostToDevice) != cudaSuccess) {
 				cudaFree(d);
 				return nullptr;
 			}

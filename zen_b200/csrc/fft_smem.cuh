@@ -5,6 +5,7 @@
 // Layout: complex values as float2 in shared memory, index padded by one slot
 // every 16 (fpad) so the stride-R stores of the early stages spread over banks.
 #pragma once
+#include <cmath>
 #include <cuda_runtime.h>
 
 namespace zen_b200 {
@@ -78,8 +79,57 @@ __device__ __forceinline__ void dftR(float2* v)
 		dft2<S>(v);
 }
 
+// Per-stage twiddle tables.  Stage (NS, R) needs w^(r*k) for r = 1..R-1, k = 0..NS-1 with
+// w = exp(-2*pi*i / (NS*R)).  They are stored stage after stage as tab[(r-1)*NS + k], so the 32 lanes
+// of a warp (consecutive butterflies j, k = j mod NS) read consecutive addresses instead of gathering
+// from one big exp(-2*pi*i*t/M) table.  Stage NS = 1 needs none.
+template <int M, int NS = 1>
+constexpr int fft_twiddle_count()
+{
+	if constexpr (NS >= M) {
+		return 0;
+	}
+	else {
+		constexpr int rem = M / NS;
+		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		return (NS > 1 ? (R - 1) * NS : 0) + fft_twiddle_count<M, NS * R>();
+	}
+}
+
+// host: fill the table in the order the stages consume it (double precision -> float)
+template <typename F2>
+inline void fft_fill_twiddles(int M, F2* out)
+{
+	const double two_pi = 6.283185307179586476925286766559;
+	int NS = 1, pos = 0;
+	while (NS < M) {
+		int rem = M / NS;
+		int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		if (NS > 1)
+			for (int r = 1; r < R; ++r)
+				for (int k = 0; k < NS; ++k) {
+					double a = -two_pi * (double)r * (double)k / ((double)NS * (double)R);
+					out[pos].x = (float)std::cos(a);
+					out[pos].y = (float)std::sin(a);
+					++pos;
+				}
+		NS *= R;
+	}
+}
+inline int fft_twiddle_count_rt(int M)
+{
+	int NS = 1, n = 0;
+	while (NS < M) {
+		int rem = M / NS;
+		int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		if (NS > 1) n += (R - 1) * NS;
+		NS *= R;
+	}
+	return n;
+}
+
 // One Stockham decimation-in-time stage of radix R on an M-point transform
-// whose already-combined sub-transforms have length NS.  tw[t] = exp(-2*pi*i*t/M).
+// whose already-combined sub-transforms have length NS.  tw points at this stage's table.
 template <int M, int NT, int S, int R, int NS>
 __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ tw, int tid)
 {
@@ -91,16 +141,21 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 		int j = tid + b * NT;
 		if ((NB % NT == 0) || j < NB) {
 			int k = j & (NS - 1);
+			float2 w[R];
+			if constexpr (NS > 1) {
+#pragma unroll
+				for (int r = 1; r < R; ++r)
+					w[r] = __ldg(&tw[(r - 1) * NS + k]);
+			}
 #pragma unroll
 			for (int r = 0; r < R; ++r)
 				v[b][r] = buf[fpad(j + r * NB)];
 			if constexpr (NS > 1) {
 #pragma unroll
 				for (int r = 1; r < R; ++r) {
-					float2 w = __ldg(&tw[(r * k) * (M / (NS * R))]);
 					if (S > 0)
-						w.y = -w.y;
-					v[b][r] = cmul(v[b][r], w);
+						w[r].y = -w[r].y;
+					v[b][r] = cmul(v[b][r], w[r]);
 				}
 			}
 			dftR<S, R>(v[b]);
@@ -122,7 +177,8 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 }
 
 // M-point complex FFT in shared memory, all NT threads of the CTA participate.
-// The caller must have synchronised after filling buf.  Ends synchronised.
+// tw: the per-stage tables of fft_fill_twiddles(M).  The caller must have
+// synchronised after filling buf.  Ends synchronised.
 template <int M, int NT, int S, int NS = 1>
 __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
 {
@@ -130,7 +186,7 @@ __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__
 		constexpr int rem = M / NS;
 		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
 		fft_stage<M, NT, S, R, NS>(buf, tw, tid);
-		fft_smem<M, NT, S, NS * R>(buf, tw, tid);
+		fft_smem<M, NT, S, NS * R>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
 	}
 }
 

@@ -43,7 +43,7 @@ struct HprDev {
 	float lh1, lp1;      // l_harm + 1, l_perc + 1 (hps.cu:599-604)
 	float inv_lp;        // 1 / Lp for the box mean
 	const float* window;   // nwin
-	const float2* tw;      // exp(-2 pi i t / M), t < M        (M = nfft/2)
+	const float2* tw;      // per-stage twiddle tables of the M-point FFT (fft_fill_twiddles), M = nfft/2
 	const float2* twr;     // exp(-2 pi i k / nfft), k <= M/2
 	short tap_age[ZEN_MAX_TAPS];
 };

@@ -146,17 +146,17 @@ int build_plan(Plan& pl, float fs, int hop, float beta, unsigned flags, int caus
 	// tables
 	std::vector<float> win(g.nwin);
 	zen_window(ZEN_WIN_SQRT_VON_HANN, g.nwin, win.data());
-	std::vector<float2> tw(M), twr(M / 2 + 1);
+	const int ntw = std::max(1, fft_twiddle_count_rt(M));
+	std::vector<float2> tw(ntw), twr(M / 2 + 1);
 	const double two_pi = 6.283185307179586476925286766559;
-	for (int t = 0; t < M; ++t)
-		tw[t] = make_float2((float)std::cos(two_pi * t / M), (float)-std::sin(two_pi * t / M));
+	fft_fill_twiddles(M, tw.data());
 	for (int k = 0; k <= M / 2; ++k)
 		twr[k] = make_float2((float)std::cos(two_pi * k / g.nfft), (float)-std::sin(two_pi * k / g.nfft));
 	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_window, sizeof(float) * g.nwin));
-	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_tw, sizeof(float2) * M));
+	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_tw, sizeof(float2) * ntw));
 	ZEN_CUDA_CHECK(cudaMalloc(&pl.d_twr, sizeof(float2) * (M / 2 + 1)));
 	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_window, win.data(), sizeof(float) * g.nwin, cudaMemcpyHostToDevice));
-	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_tw, tw.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_tw, tw.data(), sizeof(float2) * ntw, cudaMemcpyHostToDevice));
 	ZEN_CUDA_CHECK(cudaMemcpy(pl.d_twr, twr.data(), sizeof(float2) * (M / 2 + 1), cudaMemcpyHostToDevice));
 	d.window = pl.d_window;
 	d.tw = pl.d_tw;

@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	int iter = *g_iter;
 	unsigned seq = seq0;
 	__shared__ unsigned s_op, s_seq;
+	__shared__ unsigned long long s_stamps[16];
 	__shared__ const float* s_in;
 	__shared__ float* s_out[3];
 	__shared__ int s_which;
@@ -290,13 +291,17 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				em.b[o] = on ? s_out[o] : nullptr;
 			}
 			float* stash = hopbuf[prev_idx ^ 1];
-			if (tid == 0) ctrl->stamps[9] = rt_globaltimer();
-			hpr_iteration<NFFT, NT, ZEN_RT_U>(P, sm, st, iter, hopbuf[prev_idx], s_in, true, false, em, stash, ctrl->stamps);
+			if (tid == 0) {
+				s_stamps[9] = rt_globaltimer();
+				s_stamps[10] = (unsigned long long)clock64();
+			}
+			hpr_iteration<NFFT, NT, ZEN_RT_U>(P, sm, st, iter, hopbuf[prev_idx], s_in, true, false, em, stash, s_stamps);
 			if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && s_out[2])
 				for (int n = tid; n < HOP; n += NT)
 					s_out[2][n] = 0.0f;
 			prev_idx ^= 1;
 			++iter;
+			if (tid == 0) s_stamps[11] = (unsigned long long)clock64();
 		}
 		else if (op == RT_OP_COPY) {
 			const float* src = g_ola[s_which];
@@ -310,6 +315,8 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			__threadfence_system();
 			ctrl->seq_out = seq;
 		}
+		if (tid < 16 && op == RT_OP_PROCESS)
+			ctrl->stamps[tid] = s_stamps[tid];  // diagnostics, after the completion flag
 	}
 
 	// write the state back
