@@ -228,6 +228,7 @@ struct zen_hpr {
 	cudaStream_t rt_stream = nullptr;
 	int* d_iter = nullptr;
 	unsigned rt_seq = 0;
+	bool rt_args_valid = false;  // the resident kernel holds the pointers of the previous call
 	unsigned long long rt_idle_ns = 250ull * 1000 * 1000;
 };
 
@@ -297,6 +298,7 @@ int rt_launch(zen_hpr* h)
 	a.seq0 = h->rt_seq;
 	a.idle_ns = h->rt_idle_ns;
 	a.stream = h->rt_stream;
+	h->rt_args_valid = false;
 	h->rt_ctrl->seq_out = h->rt_seq;
 	h->rt_ctrl->exit_reason = 0;
 	h->rt_ctrl->alive = 1;
@@ -352,12 +354,17 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 	}
 	RtCtrl* c = h->rt_ctrl;
 	const unsigned target = h->rt_seq + 1;
-	c->op = op;
-	c->in = in;
-	c->out[0] = o0;
-	c->out[1] = o1;
-	c->out[2] = o2;
-	c->which = which;
+	// the pointers usually repeat hop after hop (IOGPU buffers): the kernel re-reads them only when told to
+	const bool same = h->rt_args_valid && c->in == in && c->out[0] == o0 && c->out[1] == o1 && c->out[2] == o2 && c->which == which;
+	if (!same) {
+		c->in = in;
+		c->out[0] = o0;
+		c->out[1] = o1;
+		c->out[2] = o2;
+		c->which = which;
+		h->rt_args_valid = true;
+	}
+	c->op = op | (same ? 0u : (unsigned)RT_OP_NEW_ARGS);
 	_mm_sfence();  // the caller's samples sit in write-combined memory (IOGPU::host_in): drain them first
 	c->seq_in = target;
 	const auto t0 = std::chrono::steady_clock::now();
@@ -369,7 +376,12 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 					break;
 				// the kernel timed out between our check and the doorbell: bring it back, it will see the doorbell
 				int rc = rt_collect(h);
-				if (rc == ZEN_OK && op != RT_OP_STOP) rc = rt_launch(h);
+				if (rc == ZEN_OK && op != RT_OP_STOP) {
+					c->op = op | (unsigned)RT_OP_NEW_ARGS;  // the new kernel has no cached pointers
+					_mm_sfence();
+					rc = rt_launch(h);
+					h->rt_args_valid = true;
+				}
 				if (rc != ZEN_OK) return rc;
 				if (op == RT_OP_STOP) break;
 			}

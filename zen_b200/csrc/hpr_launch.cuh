@@ -58,7 +58,7 @@ struct RtCtrl {
 	unsigned pad1[13];
 	unsigned long long stamps[16]; // globaltimer at the phase boundaries of the last hop (diagnostics)
 };
-enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3 };
+enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3, RT_OP_NEW_ARGS = 0x100 };
 
 struct RtArgs {
 	HprDev dev;
@@ -253,10 +253,11 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	for (;;) {
 		if (tid == 0) {
 			const unsigned long long t0 = rt_globaltimer();
-			unsigned now = seq;
+			unsigned now = seq, opw = 0;
 			unsigned spins = 0;
 			for (;;) {
-				now = ctrl->seq_in;
+				// doorbell and op code share one 8-byte word: one PCIe read per poll
+				asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(now), "=r"(opw) : "l"(&ctrl->seq_in) : "memory");
 				if (now != seq)
 					break;
 				if ((++spins & 63u) == 0 && rt_globaltimer() - t0 > idle_ns)
@@ -266,13 +267,16 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				s_op = 0xffffffffu;  // idle time-out
 			}
 			else {
-				__threadfence_system();  // order the argument reads after the doorbell read
-				s_op = ctrl->op;
-				s_in = ctrl->in;
-				s_out[0] = ctrl->out[0];
-				s_out[1] = ctrl->out[1];
-				s_out[2] = ctrl->out[2];
-				s_which = ctrl->which;
+				if (opw & RT_OP_NEW_ARGS) {
+					// pointers changed since the last hop: fetch them (one more round trip), else reuse the cached ones
+					__threadfence_system();
+					s_in = ctrl->in;
+					s_out[0] = ctrl->out[0];
+					s_out[1] = ctrl->out[1];
+					s_out[2] = ctrl->out[2];
+					s_which = ctrl->which;
+				}
+				s_op = opw & 0xffu;
 			}
 			s_seq = now;
 		}
