@@ -401,13 +401,42 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 	}
 	__syncthreads();
 
-	// time axis: H row (hps.cu:495 / 595, only the consumed row)
+	// time axis: H row (hps.cu:495 / 595, only the consumed row).  For the short windows the bins-per-thread
+	// loop is fully unrolled so that all ring loads of a thread are in flight together.
 	auto compute_h_row = [&](float* dst) {
 		const int nt = P.n_taps;
+		constexpr int ITER = (M + 1 + NT - 1) / NT;
 		auto tap = [&](int t, int k) -> float {
 			int off = sm.taps[t];
 			return off >= 0 ? st.mag_ring[off + k] : 0.0f;
 		};
+		auto fixed = [&](auto LC) {
+			constexpr int L = decltype(LC)::value;
+			int offs[L];
+#pragma unroll
+			for (int t = 0; t < L; ++t)
+				offs[t] = sm.taps[t];
+#pragma unroll
+			for (int it = 0; it < ITER; ++it) {
+				const int k = tid + it * NT;
+				if (k <= M) {
+					float v[L];
+#pragma unroll
+					for (int t = 0; t < L; ++t)
+						v[t] = offs[t] >= 0 ? st.mag_ring[offs[t] + k] : 0.0f;
+					dst[k] = median_regs<L>(v);
+				}
+			}
+		};
+		if (!P.sse && (nt == 1 || nt == 3 || nt == 5 || nt == 7)) {
+			switch (nt) {
+			case 1: fixed(std::integral_constant<int, 1>{}); break;
+			case 3: fixed(std::integral_constant<int, 3>{}); break;
+			case 5: fixed(std::integral_constant<int, 5>{}); break;
+			default: fixed(std::integral_constant<int, 7>{}); break;
+			}
+			return;
+		}
 		for (int k = tid; k <= M; k += NT) {
 			float H;
 			if (P.sse) {
@@ -420,10 +449,6 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			else {
 				switch (nt) {
 				case 0: H = 0.0f; break;
-				case 1: H = tap(0, k); break;
-				case 3: H = median_fixed<3>([&](int t) { return tap(t, k); }); break;
-				case 5: H = median_fixed<5>([&](int t) { return tap(t, k); }); break;
-				case 7: H = median_fixed<7>([&](int t) { return tap(t, k); }); break;
 				case 9: H = median_fixed<9>([&](int t) { return tap(t, k); }); break;
 				case 11: H = median_fixed<11>([&](int t) { return tap(t, k); }); break;
 				case 13: H = median_fixed<13>([&](int t) { return tap(t, k); }); break;

@@ -184,10 +184,26 @@ size_t tile_scratch_floats(const Plan& pl)
 	return (ring + xr + tails + 3) & ~(size_t)3;
 }
 
-int dispatch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
-                  int n_streams, long n_hops, int tile_hops, float* scratch, cudaStream_t s)
+int resident_ctas_for(const Plan& pl)
 {
-	TileArgs a{pl.dev, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, tile_scratch_floats(pl), s};
+	switch (pl.nfft) {
+	case 128: return tile_resident_ctas<128>(pl.dev);
+	case 256: return tile_resident_ctas<256>(pl.dev);
+	case 512: return tile_resident_ctas<512>(pl.dev);
+	case 1024: return tile_resident_ctas<1024>(pl.dev);
+	case 2048: return tile_resident_ctas<2048>(pl.dev);
+	case 4096: return tile_resident_ctas<4096>(pl.dev);
+	case 8192: return tile_resident_ctas<8192>(pl.dev);
+	case 16384: return tile_resident_ctas<16384>(pl.dev);
+	}
+	return 0;
+}
+
+int dispatch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
+                  int n_streams, long n_hops, int tile_hops, float* scratch, int* work_counter, int resident, cudaStream_t s)
+{
+	TileArgs a{pl.dev, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, tile_scratch_floats(pl),
+	           work_counter, resident, s};
 	switch (pl.nfft) {
 	case 128: return launch_tile_impl<128>(a);
 	case 256: return launch_tile_impl<256>(a);
@@ -843,7 +859,9 @@ struct zen_hpr_batch {
 	int max_streams;
 	long max_hops;
 	int tile_hops;
-	float* d_scratch = nullptr;
+	float* d_scratch = nullptr;   // [2 pipeline slots][resident CTAs] scratch states
+	int* d_counters = nullptr;    // work-queue heads, one per pipeline slot
+	int resident = 0;             // resident CTAs of the tile kernel on this device
 	size_t scratch_ctas = 0;
 	long last_launches = 0;
 	float last_kernel_ms = 0.0f;
@@ -857,38 +875,33 @@ struct zen_hpr_batch {
 
 namespace {
 
-// tile length: enough CTAs to fill the GPU a few times over, but long enough
-// that the W-hop halo stays a small fraction of the work
-int choose_tile_hops(const Plan& pl, int n_streams, long n_hops)
+// Tile length.  Work items (stream, tile) are pulled from a queue by the resident CTAs, so what matters
+// is (a) enough items per resident CTA that the tail, when the queue runs dry, is short, and (b) tiles long
+// enough that the W-hop halo each tile re-analyses stays a small fraction of its work.
+int choose_tile_hops(const Plan& pl, int n_streams, long n_hops, int resident)
 {
-	int sms = 148;
-	int dev = 0;
-	if (cudaGetDevice(&dev) == cudaSuccess) {
-		int v = 0;
-		if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-			sms = v;
-	}
-	const long target_ctas = 8L * sms;
-	long min_tile = 8L * pl.dev.W;  // halo <= 12.5 % of the tile
-	if (min_tile < 16) min_tile = 16;
-	long tiles_wanted = (target_ctas + n_streams - 1) / n_streams;
+	if (resident < 1) resident = 148;
+	const long items_wanted = 32L * resident;
+	long tiles_wanted = (items_wanted + n_streams - 1) / n_streams;
 	if (tiles_wanted < 1) tiles_wanted = 1;
 	long tile = (n_hops + tiles_wanted - 1) / tiles_wanted;
+	long min_tile = 16L * pl.dev.W;  // halo <= 6 % of the tile
+	if (min_tile < 32) min_tile = 32;
 	if (tile < min_tile) tile = min_tile;
 	if (tile > n_hops) tile = n_hops;
 	if (tile < 1) tile = 1;
 	return (int)tile;
 }
 
-int ensure_scratch(zen_hpr_batch* b, size_t ctas)
+int ensure_scratch(zen_hpr_batch* b)
 {
-	if (ctas <= b->scratch_ctas)
+	if (b->d_scratch)
 		return ZEN_OK;
-	cudaFree(b->d_scratch);
-	b->d_scratch = nullptr;
-	b->scratch_ctas = 0;
-	ZEN_CUDA_CHECK(cudaMalloc(&b->d_scratch, sizeof(float) * tile_scratch_floats(b->plan) * ctas));
-	b->scratch_ctas = ctas;
+	b->resident = resident_ctas_for(b->plan);
+	if (b->resident < 1)
+		return ZEN_ERR_CUDA;
+	ZEN_CUDA_CHECK(cudaMalloc(&b->d_scratch, sizeof(float) * tile_scratch_floats(b->plan) * 2 * (size_t)b->resident));
+	ZEN_CUDA_CHECK(cudaMalloc(&b->d_counters, sizeof(int) * 2));
 	return ZEN_OK;
 }
 
@@ -928,6 +941,7 @@ void zen_hpr_batch_destroy(zen_hpr_batch* b)
 		return;
 	free_plan(b->plan);
 	cudaFree(b->d_scratch);
+	cudaFree(b->d_counters);
 	for (int s = 0; s < 2; ++s) {
 		cudaFree(b->d_stage_in[s]);
 		for (int o = 0; o < 3; ++o)
@@ -947,16 +961,15 @@ int zen_hpr_batch_process(zen_hpr_batch* b, const float* d_in, long in_stride, i
 	if ((in_stride & 1) || (out_stride & 1) || ((uintptr_t)d_in & 7))
 		return ZEN_ERR_ARG;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	int tile = choose_tile_hops(b->plan, n_streams, n_hops);
-	b->tile_hops = tile;
-	long n_tiles = (n_hops + tile - 1) / tile;
-	int rc = ensure_scratch(b, (size_t)n_tiles * n_streams);
+	int rc = ensure_scratch(b);
 	if (rc != ZEN_OK)
 		return rc;
+	int tile = choose_tile_hops(b->plan, n_streams, n_hops, b->resident);
+	b->tile_hops = tile;
 	const unsigned f = b->plan.dev.out_flags;
 	cudaEventRecord(b->ev0, s);
 	rc = dispatch_tile(b->plan, d_in, in_stride, (f & 1) ? d_out_h : nullptr, (f & 2) ? d_out_p : nullptr,
-	                   (f & 4) ? d_out_r : nullptr, out_stride, n_streams, n_hops, tile, b->d_scratch, s);
+	                   (f & 4) ? d_out_r : nullptr, out_stride, n_streams, n_hops, tile, b->d_scratch, b->d_counters, b->resident, s);
 	cudaEventRecord(b->ev1, s);
 	b->last_launches = 1;
 	return rc;
@@ -1000,14 +1013,13 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 		}
 		b->stage_streams = chunk;
 	}
-	int tile = choose_tile_hops(b->plan, chunk, n_hops);
-	b->tile_hops = tile;
-	long n_tiles = (n_hops + tile - 1) / tile;
-	// both pipeline slots run concurrently: separate scratch halves
-	int rc = ensure_scratch(b, 2 * (size_t)n_tiles * chunk);
+	int rc = ensure_scratch(b);
 	if (rc != ZEN_OK)
 		return rc;
-	const size_t scratch_half = tile_scratch_floats(b->plan) * (size_t)n_tiles * chunk;
+	int tile = choose_tile_hops(b->plan, chunk, n_hops, b->resident);
+	b->tile_hops = tile;
+	// both pipeline slots can run concurrently: separate scratch halves and work counters
+	const size_t scratch_half = tile_scratch_floats(b->plan) * (size_t)b->resident;
 	long launches = 0;
 	int slot = 0;
 	for (int s0 = 0; s0 < n_streams; s0 += chunk, slot ^= 1) {
@@ -1017,7 +1029,8 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 		                                 (size_t)in_stride * sizeof(float), row * sizeof(float), ns,
 		                                 cudaMemcpyHostToDevice, st));
 		rc = dispatch_tile(b->plan, b->d_stage_in[slot], (long)row, b->d_stage_out[slot][0], b->d_stage_out[slot][1],
-		                   b->d_stage_out[slot][2], (long)row, ns, n_hops, tile, b->d_scratch + slot * scratch_half, st);
+		                   b->d_stage_out[slot][2], (long)row, ns, n_hops, tile, b->d_scratch + slot * scratch_half,
+		                   b->d_counters + slot, b->resident, st);
 		if (rc != ZEN_OK)
 			return rc;
 		++launches;

@@ -1,6 +1,8 @@
 // Kernels of the fused HPR step and their launchers, instantiated once per FFT
 // size in hpr_inst_<NFFT>.cu so the sizes compile in parallel.
 #pragma once
+#include <algorithm>
+
 #include "hpr_core.cuh"
 
 namespace zen_b200 {
@@ -26,8 +28,10 @@ struct TileArgs {
 	int n_streams;
 	long n_hops;
 	int tile_hops;
-	float* scratch;
+	float* scratch;          // resident_ctas * scratch_per_cta floats
 	size_t scratch_per_cta;
+	int* work_counter;       // device int, zeroed by the launcher
+	int resident_ctas;       // grid size (<= SMs * occupancy)
 	cudaStream_t stream;
 };
 
@@ -81,6 +85,7 @@ constexpr int nt_rt_for()
 constexpr int ZEN_RT_U = 5;
 
 template <int NFFT> int launch_tile_impl(const TileArgs& a);
+template <int NFFT> int tile_resident_ctas(const HprDev& d);
 template <int NFFT> int launch_hop_impl(const HopArgs& a);
 template <int NFFT> int launch_rt_impl(const RtArgs& a);
 template <int NFFT> size_t rt_smem_bytes(const HprDev& d, int state_in_smem);
@@ -99,19 +104,19 @@ using namespace zen_b200;
 // given that halo, so tiles need no communication.
 template <int NFFT, int NT>
 __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_tile_kernel(const __grid_constant__ HprDev P,
-                                                      const float* __restrict__ in, long in_stride,
-                                                      float* out_h, float* out_p, float* out_r, long out_stride,
-                                                      long n_hops, int tile_hops,
-                                                      float* scratch, size_t scratch_per_cta)
+                                                                            const float* __restrict__ in, long in_stride,
+                                                                            float* out_h, float* out_p, float* out_r, long out_stride,
+                                                                            long n_hops, int tile_hops, int n_tiles, int total_items,
+                                                                            int* work_counter, float* scratch, size_t scratch_per_cta)
 {
 	constexpr int M = NFFT / 2, HOP = M / 2;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	HprSmem<NFFT> sm;
 	sm.carve(smem_raw, P.Lp);
+	__shared__ int s_item;
 
-	const int tile = blockIdx.x, stream = blockIdx.y;
-	const size_t cta = (size_t)stream * gridDim.x + tile;
-	float* sc = scratch + cta * scratch_per_cta;
+	// scratch belongs to the RESIDENT CTA, not to the work item: a few tens of MB that stay in L2
+	float* sc = scratch + (size_t)blockIdx.x * scratch_per_cta;
 	HprState st;
 	st.mag_ring = sc;
 	sc += (size_t)P.W * (M + 1) + ((P.W * (M + 1)) & 1);
@@ -121,21 +126,32 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_tile_kernel(cons
 	for (int o = 0; o < 3; ++o)
 		st.tail[o] = sc + (size_t)o * HOP;
 
-	const float* sin = in + (size_t)stream * in_stride;
-	const long e0 = (long)tile * tile_hops;
-	const long e1 = min(n_hops, e0 + (long)tile_hops);
-	const long i_begin = max(0L, e0 - P.W);
-	const long i_full = max(0L, e0 - 1);
-	for (long i = i_begin; i < e1; ++i) {
-		const float* cur = sin + (size_t)i * HOP;
-		const float* prev = i > 0 ? cur - HOP : nullptr;
-		HprEmit em;
-		const bool emit = i >= e0;
-		em.a[0] = (emit && out_h) ? out_h + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
-		em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
-		em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
-		em.b[0] = em.b[1] = em.b[2] = nullptr;
-		hpr_iteration<NFFT, NT>(P, sm, st, (int)i, prev, cur, i >= i_full, i == i_full, em);
+	// work items (stream, tile) are handed out dynamically, so no CTA idles while others finish a long tail
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_item = atomicAdd(work_counter, 1);
+		__syncthreads();
+		const int item = s_item;
+		if (item >= total_items)
+			break;
+		const int stream = item / n_tiles, tile = item - stream * n_tiles;
+		const float* sin = in + (size_t)stream * in_stride;
+		const long e0 = (long)tile * tile_hops;
+		const long e1 = min(n_hops, e0 + (long)tile_hops);
+		const long i_begin = max(0L, e0 - P.W);
+		const long i_full = max(0L, e0 - 1);
+		for (long i = i_begin; i < e1; ++i) {
+			const float* cur = sin + (size_t)i * HOP;
+			const float* prev = i > 0 ? cur - HOP : nullptr;
+			HprEmit em;
+			const bool emit = i >= e0;
+			em.a[0] = (emit && out_h) ? out_h + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+			em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+			em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+			em.b[0] = em.b[1] = em.b[2] = nullptr;
+			hpr_iteration<NFFT, NT>(P, sm, st, (int)i, prev, cur, i >= i_full, i == i_full, em);
+		}
 	}
 }
 
@@ -357,12 +373,32 @@ int launch_tile_impl(const TileArgs& a)
 	auto kern = hpr_tile_kernel<NFFT, NT>;
 	size_t smem = HprSmem<NFFT>::bytes(a.dev.Lp);
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int n_tiles = (int)((a.n_hops + a.tile_hops - 1) / a.tile_hops);
-	dim3 grid(n_tiles, a.n_streams);
+	const int n_tiles = (int)((a.n_hops + a.tile_hops - 1) / a.tile_hops);
+	const long total = (long)n_tiles * a.n_streams;
+	if (total > 0x7fffffffL)
+		return ZEN_ERR_UNSUPPORTED;
+	ZEN_CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), a.stream));
+	const int grid = (int)std::min<long>(total, a.resident_ctas);
 	kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
-	                                   a.scratch, a.scratch_per_cta);
+	                                   n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta);
 	ZEN_CUDA_CHECK(cudaGetLastError());
 	return ZEN_OK;
+}
+
+// resident CTAs per SM of the tile kernel (occupancy query), times the SM count
+template <int NFFT>
+int tile_resident_ctas(const HprDev& d)
+{
+	constexpr int NT = nt_for<NFFT>();
+	auto kern = hpr_tile_kernel<NFFT, NT>;
+	size_t smem = HprSmem<NFFT>::bytes(d.Lp);
+	if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+		return 0;
+	int per_sm = 0, dev = 0, sms = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess
+	    || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+		return 0;
+	return per_sm * sms;
 }
 
 template <int NFFT>
@@ -405,6 +441,7 @@ int launch_rt_impl(const RtArgs& a)
 }
 
 template int launch_tile_impl<ZEN_HPR_INSTANTIATE>(const TileArgs&);
+template int tile_resident_ctas<ZEN_HPR_INSTANTIATE>(const HprDev&);
 template int launch_hop_impl<ZEN_HPR_INSTANTIATE>(const HopArgs&);
 template int launch_rt_impl<ZEN_HPR_INSTANTIATE>(const RtArgs&);
 template size_t rt_smem_bytes<ZEN_HPR_INSTANTIATE>(const HprDev&, int);
