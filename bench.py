@@ -197,7 +197,8 @@ def workload_config(args, n_streams, seconds):
     return {"workload": "BASELINE.json configs[4]: %d independent synthetic %d s mono 44.1 kHz streams per GPU, real-time HPR "
                         "(causal, copy-border, percussive out, hard mask), hop %d, beta %.1f" % (n_streams, seconds, HOP, BETA),
             "streams_per_gpu": n_streams, "hops_per_stream": fakert_hops(seconds * FS, HOP), "hop": HOP, "nfft": 4 * HOP,
-            "fs": FS, "l2": "inputs exceed L2 (43 GB per GPU per step)" if n_streams * seconds >= 4096 else "small run: L2 flushed between steps",
+            "fs": FS, "l2": ("inputs exceed L2 (%.1f GB in + %.1f GB out per GPU per step)" % (2 * (n_streams * seconds * FS * 4 / 1e9,))
+                             if n_streams * seconds * FS * 4 >= (512 << 20) else "small run: L2 flushed between steps"),
             "parallelism": "streams sharded over GPUs, no collective"}
 
 
@@ -300,7 +301,9 @@ def run_ours(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # measured on the full 4096 x 2583-hop launch; scaled to this run's launch size
+            traffic = tj.get("dram_bytes_per_launch") * (n_streams * n_hops * BYTES_PER_HOP) / tj.get("algorithmic_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
 

@@ -854,12 +854,15 @@ extern "C" int zen_hpr_materialize(zen_hpr* h, float* d_stft, float* d_s_mag, fl
 
 // --------------------------------------------------------------- batched ---
 
+// host-buffer pipeline depth: H2D of chunk n+1, kernel of chunk n and D2H of chunk n-1 overlap
+constexpr int ZEN_PIPE_SLOTS = 3;
+
 struct zen_hpr_batch {
 	Plan plan;
 	int max_streams;
 	long max_hops;
 	int tile_hops;
-	float* d_scratch = nullptr;   // [2 pipeline slots][resident CTAs] scratch states
+	float* d_scratch = nullptr;   // [ZEN_PIPE_SLOTS pipeline slots][resident CTAs] scratch states
 	int* d_counters = nullptr;    // work-queue heads, one per pipeline slot
 	int resident = 0;             // resident CTAs of the tile kernel on this device
 	size_t scratch_ctas = 0;
@@ -867,9 +870,9 @@ struct zen_hpr_batch {
 	float last_kernel_ms = 0.0f;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	// host pipeline
-	cudaStream_t streams[2] = {nullptr, nullptr};
-	float* d_stage_in[2] = {nullptr, nullptr};
-	float* d_stage_out[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+	cudaStream_t streams[ZEN_PIPE_SLOTS] = {};
+	float* d_stage_in[ZEN_PIPE_SLOTS] = {};
+	float* d_stage_out[ZEN_PIPE_SLOTS][3] = {};
 	int stage_streams = 0;
 };
 
@@ -900,8 +903,8 @@ int ensure_scratch(zen_hpr_batch* b)
 	b->resident = resident_ctas_for(b->plan);
 	if (b->resident < 1)
 		return ZEN_ERR_CUDA;
-	ZEN_CUDA_CHECK(cudaMalloc(&b->d_scratch, sizeof(float) * tile_scratch_floats(b->plan) * 2 * (size_t)b->resident));
-	ZEN_CUDA_CHECK(cudaMalloc(&b->d_counters, sizeof(int) * 2));
+	ZEN_CUDA_CHECK(cudaMalloc(&b->d_scratch, sizeof(float) * tile_scratch_floats(b->plan) * ZEN_PIPE_SLOTS * (size_t)b->resident));
+	ZEN_CUDA_CHECK(cudaMalloc(&b->d_counters, sizeof(int) * ZEN_PIPE_SLOTS));
 	return ZEN_OK;
 }
 
@@ -942,7 +945,7 @@ void zen_hpr_batch_destroy(zen_hpr_batch* b)
 	free_plan(b->plan);
 	cudaFree(b->d_scratch);
 	cudaFree(b->d_counters);
-	for (int s = 0; s < 2; ++s) {
+	for (int s = 0; s < ZEN_PIPE_SLOTS; ++s) {
 		cudaFree(b->d_stage_in[s]);
 		for (int o = 0; o < 3; ++o)
 			cudaFree(b->d_stage_out[s][o]);
@@ -996,10 +999,10 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 	const size_t row = (size_t)n_hops * hop;
 	const unsigned f = b->plan.dev.out_flags;
 	float* h_out[3] = {(f & 1) ? h_out_h : nullptr, (f & 2) ? h_out_p : nullptr, (f & 4) ? h_out_r : nullptr};
-	// chunk so that one chunk's input is ~256 MB
-	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, ((size_t)256 << 20) / (row * sizeof(float)) + 1));
+	// chunk so that one chunk's input is ~128 MB
+	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, ((size_t)128 << 20) / (row * sizeof(float)) + 1));
 	if (chunk > b->stage_streams) {
-		for (int s = 0; s < 2; ++s) {
+		for (int s = 0; s < ZEN_PIPE_SLOTS; ++s) {
 			cudaFree(b->d_stage_in[s]);
 			b->d_stage_in[s] = nullptr;
 			for (int o = 0; o < 3; ++o) {
@@ -1018,11 +1021,11 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 		return rc;
 	int tile = choose_tile_hops(b->plan, chunk, n_hops, b->resident);
 	b->tile_hops = tile;
-	// both pipeline slots can run concurrently: separate scratch halves and work counters
+	// the pipeline slots can run concurrently: separate scratch areas and work counters
 	const size_t scratch_half = tile_scratch_floats(b->plan) * (size_t)b->resident;
 	long launches = 0;
 	int slot = 0;
-	for (int s0 = 0; s0 < n_streams; s0 += chunk, slot ^= 1) {
+	for (int s0 = 0; s0 < n_streams; s0 += chunk, slot = (slot + 1) % ZEN_PIPE_SLOTS) {
 		const int ns = std::min(chunk, n_streams - s0);
 		cudaStream_t st = b->streams[slot];
 		ZEN_CUDA_CHECK(cudaMemcpy2DAsync(b->d_stage_in[slot], row * sizeof(float), h_in + (size_t)s0 * in_stride,
@@ -1040,8 +1043,8 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 				                                 b->d_stage_out[slot][o], row * sizeof(float), row * sizeof(float), ns,
 				                                 cudaMemcpyDeviceToHost, st));
 	}
-	ZEN_CUDA_CHECK(cudaStreamSynchronize(b->streams[0]));
-	ZEN_CUDA_CHECK(cudaStreamSynchronize(b->streams[1]));
+	for (int s = 0; s < ZEN_PIPE_SLOTS; ++s)
+		ZEN_CUDA_CHECK(cudaStreamSynchronize(b->streams[s]));
 	b->last_launches = launches;
 	return ZEN_OK;
 }
