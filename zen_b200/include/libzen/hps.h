@@ -119,6 +119,11 @@ namespace hps {
 
 		void warmup(zen::io::IOGPU& io);
 
+		// zen_b200 extension: serve the following hops from a resident (persistent) kernel that keeps the stream
+		// state in shared memory and is driven through a doorbell in mapped memory: no launch per hop
+		void start_resident();
+		void stop_resident();
+
 		void use_sse_filter();
 		void use_soft_mask();
 
@@ -193,6 +198,18 @@ namespace hps {
 			p_impl->process_next_hop(io.device_in);
 		}
 		p_impl->reset_buffers();
+	}
+
+	template <zen::Backend B>
+	void HPRRealtime<B>::start_resident()
+	{
+		zen::b200_detail::check(zen_hpr_realtime_begin(p_impl->handle()), "start_resident");
+	}
+
+	template <zen::Backend B>
+	void HPRRealtime<B>::stop_resident()
+	{
+		zen::b200_detail::check(zen_hpr_realtime_end(p_impl->handle()), "stop_resident");
 	}
 
 	template <zen::Backend B>
