@@ -80,9 +80,15 @@ struct RtArgs {
 template <int NFFT>
 constexpr int nt_rt_for()
 {
-	return (NFFT / 8) < 128 ? 128 : ((NFFT / 8) > 512 ? 512 : (NFFT / 8));
+	// measured on a B200 (tools/rt_phases.py): 512 threads are the sweet spot at nfft 4096 (1024 threads spill in
+	// the FFT stages); the large transforms want 1024, the small ones nfft/4
+	return NFFT == 4096 ? 512 : ((NFFT / 4) < 128 ? 128 : ((NFFT / 4) > 1024 ? 1024 : (NFFT / 4)));
 }
-constexpr int ZEN_RT_U = 5;
+template <int NFFT>
+constexpr int rt_u_for()
+{
+	return NFFT == 4096 ? 5 : 3;
+}
 
 template <int NFFT> int launch_tile_impl(const TileArgs& a);
 template <int NFFT> int tile_resident_ctas(const HprDev& d);
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				s_stamps[9] = rt_globaltimer();
 				s_stamps[10] = (unsigned long long)clock64();
 			}
-			hpr_iteration<NFFT, NT, ZEN_RT_U>(P, sm, st, iter, hopbuf[prev_idx], s_in, true, false, em, stash, s_stamps);
+			hpr_iteration<NFFT, NT, rt_u_for<NFFT>()>(P, sm, st, iter, hopbuf[prev_idx], s_in, true, false, em, stash, s_stamps);
 			if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && s_out[2])
 				for (int n = tid; n < HOP; n += NT)
 					s_out[2][n] = 0.0f;
