@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libzen_b200.so")
+LIB_PATH = os.environ.get("ZEN_B200_LIB") or os.path.join(_HERE, "lib", "libzen_b200.so")  # override: A/B builds only
 
 ZEN_OK, ZEN_ERR_GEOMETRY, ZEN_ERR_CUDA, ZEN_ERR_UNSUPPORTED, ZEN_ERR_ARG = 0, -1, -2, -3, -4
 TIME_CAUSAL, TIME_ANTICAUSAL, FREQUENCY = 0, 1, 2

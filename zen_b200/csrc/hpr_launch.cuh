@@ -13,10 +13,13 @@ constexpr int nt_for()
 	return (NFFT / 16) < 64 ? 64 : ((NFFT / 16) > 512 ? 512 : (NFFT / 16));
 }
 // resident CTAs per SM the register allocation is tuned for
+#ifndef ZEN_TILE_THREADS_PER_SM
+#define ZEN_TILE_THREADS_PER_SM 1024
+#endif
 template <int NT>
 constexpr int min_blocks_for()
 {
-	return NT >= 512 ? 1 : 768 / NT;
+	return NT >= 512 ? 1 : ZEN_TILE_THREADS_PER_SM / NT;
 }
 
 struct TileArgs {
@@ -379,6 +382,7 @@ int launch_tile_impl(const TileArgs& a)
 	auto kern = hpr_tile_kernel<NFFT, NT>;
 	size_t smem = HprSmem<NFFT>::bytes(a.dev.Lp);
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	const int n_tiles = (int)((a.n_hops + a.tile_hops - 1) / a.tile_hops);
 	const long total = (long)n_tiles * a.n_streams;
 	if (total > 0x7fffffffL)
@@ -398,7 +402,8 @@ int tile_resident_ctas(const HprDev& d)
 	constexpr int NT = nt_for<NFFT>();
 	auto kern = hpr_tile_kernel<NFFT, NT>;
 	size_t smem = HprSmem<NFFT>::bytes(d.Lp);
-	if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+	if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
+	    || cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
 		return 0;
 	int per_sm = 0, dev = 0, sms = 0;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess
