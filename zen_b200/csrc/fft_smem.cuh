@@ -130,7 +130,11 @@ inline int fft_twiddle_count_rt(int M)
 
 // One Stockham decimation-in-time stage of radix R on an M-point transform
 // whose already-combined sub-transforms have length NS.  tw points at this stage's table.
-template <int M, int NT, int S, int R, int NS>
+// ZIN : the upper half of the input is known to be zero (zero-padded frame): those loads and the butterfly
+//       arithmetic that depends on them disappear (first stage only).
+// HOUT: only the lower half of the output is needed: the stores of the upper half and the arithmetic feeding
+//       them disappear (last stage only).
+template <int M, int NT, int S, int R, int NS, bool ZIN = false, bool HOUT = false>
 __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ tw, int tid)
 {
 	constexpr int NB = M / R;
@@ -148,8 +152,12 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 					w[r] = __ldg(&tw[(r - 1) * NS + k]);
 			}
 #pragma unroll
-			for (int r = 0; r < R; ++r)
-				v[b][r] = buf[fpad(j + r * NB)];
+			for (int r = 0; r < R; ++r) {
+				if (ZIN && r >= R / 2)
+					v[b][r] = make_float2(0.0f, 0.0f);
+				else
+					v[b][r] = buf[fpad(j + r * NB)];
+			}
 			if constexpr (NS > 1) {
 #pragma unroll
 				for (int r = 1; r < R; ++r) {
@@ -170,7 +178,8 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 			int j0 = (j - k) * R + k;
 #pragma unroll
 			for (int r = 0; r < R; ++r)
-				buf[fpad(j0 + r * NS)] = v[b][r];
+				if (!(HOUT && r >= R / 2))
+					buf[fpad(j0 + r * NS)] = v[b][r];
 		}
 	}
 	__syncthreads();
@@ -179,14 +188,14 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 // M-point complex FFT in shared memory, all NT threads of the CTA participate.
 // tw: the per-stage tables of fft_fill_twiddles(M).  The caller must have
 // synchronised after filling buf.  Ends synchronised.
-template <int M, int NT, int S, int NS = 1>
+template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false>
 __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
 {
 	if constexpr (NS < M) {
 		constexpr int rem = M / NS;
 		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
-		fft_stage<M, NT, S, R, NS>(buf, tw, tid);
-		fft_smem<M, NT, S, NS * R>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
+		fft_stage<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M)>(buf, tw, tid);
+		fft_smem<M, NT, S, NS * R, ZIN, HOUT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
 	}
 }
 

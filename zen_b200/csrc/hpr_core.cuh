@@ -302,26 +302,23 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 	}
 
 	// ---- A. window the 2-hop frame, pack even/odd samples as one complex value (hps.cu:452-462)
-	for (int n = tid; n < M; n += NT) {
-		float2 z = make_float2(0.0f, 0.0f);
-		if (n < HOP) {
-			float2 x;
-			if (n < HOP / 2)
-				x = prev ? reinterpret_cast<const float2*>(prev)[n] : make_float2(0.0f, 0.0f);
-			else {
-				x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
-				if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
-			}
-			float2 w = __ldg(reinterpret_cast<const float2*>(P.window) + n);
-			z = make_float2(x.x * w.x, x.y * w.y);
+	// (the zero padding n >= HOP is never stored: the first FFT stage knows it is zero)
+	for (int n = tid; n < HOP; n += NT) {
+		float2 x;
+		if (n < HOP / 2)
+			x = prev ? reinterpret_cast<const float2*>(prev)[n] : make_float2(0.0f, 0.0f);
+		else {
+			x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
+			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
 		}
-		sm.zbuf[fpad(n)] = z;
+		float2 w = __ldg(reinterpret_cast<const float2*>(P.window) + n);
+		sm.zbuf[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
 	}
 	__syncthreads();
 	stamp(1);
 
 	// ---- B. forward FFT (hps.cu:465)
-	fft_smem<M, NT, -1>(sm.zbuf, P.tw, tid);
+	fft_smem<M, NT, -1, 1, true, false>(sm.zbuf, P.tw, tid);
 	stamp(2);
 
 	// ---- C. split into the real-input spectrum X[0..M], magnitudes into the ring (hps.cu:469-472, 492-493)
@@ -586,7 +583,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		}
 		__syncthreads();
 		stamp(6);
-		fft_smem<M, NT, +1>(sm.zbuf, P.tw, tid);
+		fft_smem<M, NT, +1, 1, false, true>(sm.zbuf, P.tw, tid);
 		stamp(7);
 		// overlap-add: out = tail + Re(y[0:hop]) * COLA ; tail' = Re(y[hop:nwin]) * COLA   (hps.h:68-80)
 		float* tail = st.tail[o];
