@@ -171,6 +171,8 @@ HPR_CASES = [
     (44100.0, 4096, 2.5, 7, False, False, False, False, 10),
     (48000.0, 128, 2.0, 7, True, True, False, False, 120),
     (48000.0, 64, 2.0, 3, True, True, False, False, 150),
+    (48000.0, 32, 2.0, 7, True, True, False, False, 260),
+    (48000.0, 32, 2.0, 7, False, False, False, False, 260),
 ]
 
 

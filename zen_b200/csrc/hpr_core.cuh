@@ -279,7 +279,7 @@ template <int NFFT, int NT, int U = ZEN_DECIDE_U>
 __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
                                               const float* __restrict__ prev, const float* __restrict__ cur,
                                               bool full, bool fresh_tail, const HprEmit& em, float* cur_stash = nullptr,
-                                              unsigned long long* stamps = nullptr)
+                                              unsigned long long* stamps = nullptr, const float* next_hop = nullptr)
 {
 	auto stamp = [&](int idx) {
 		if (stamps && threadIdx.x == 0) {
@@ -300,6 +300,11 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		int j = i - P.tap_age[t];
 		sm.taps[t] = j >= 0 ? (j % W) * (M + 1) : -1;
 	}
+
+	// pull the NEXT hop towards L2 while this one is processed (the batched kernels read the input from HBM
+	// exactly once; without this the first loads of every hop wait a full DRAM round trip)
+	if (next_hop != nullptr && tid < (HOP * 4) / 128)
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(next_hop) + tid * 128));
 
 	// ---- A. window the 2-hop frame, pack even/odd samples as one complex value (hps.cu:452-462)
 	// (the zero padding n >= HOP is never stored: the first FFT stage knows it is zero)
@@ -431,6 +436,34 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			case 3: fixed(std::integral_constant<int, 3>{}); break;
 			case 5: fixed(std::integral_constant<int, 5>{}); break;
 			default: fixed(std::integral_constant<int, 7>{}); break;
+			}
+			return;
+		}
+		if (!P.sse && nt > 13 && nt <= 127) {
+			// long time windows (hops below 256): one warp per bin sorts the taps across its lanes
+			// (bitonic network, K ranks per lane) and reads the middle rank
+			constexpr int NW = NT / 32;
+			const int wid = tid >> 5, lane = tid & 31;
+			for (int k = wid; k <= M; k += NW) {
+				auto load = [&](int t) { return tap(t, k); };
+				float med;
+				if (nt <= 31) {
+					WarpSortedWindow<1> w;
+					w.init(load, nt, lane);
+					med = __shfl_sync(0xffffffffu, w.median_reg(), w.med_lane);
+				}
+				else if (nt <= 63) {
+					WarpSortedWindow<2> w;
+					w.init(load, nt, lane);
+					med = __shfl_sync(0xffffffffu, w.median_reg(), w.med_lane);
+				}
+				else {
+					WarpSortedWindow<4> w;
+					w.init(load, nt, lane);
+					med = __shfl_sync(0xffffffffu, w.median_reg(), w.med_lane);
+				}
+				if (lane == 0)
+					dst[k] = med;
 			}
 			return;
 		}

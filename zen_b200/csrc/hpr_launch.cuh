@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_tile_kernel(cons
 			em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
 			em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
 			em.b[0] = em.b[1] = em.b[2] = nullptr;
-			hpr_iteration<NFFT, NT>(P, sm, st, (int)i, prev, cur, i >= i_full, i == i_full, em);
+			hpr_iteration<NFFT, NT>(P, sm, st, (int)i, prev, cur, i >= i_full, i == i_full, em, nullptr, nullptr,
+			                        i + 1 < e1 ? cur + HOP : nullptr);
 		}
 	}
 }
