@@ -461,3 +461,22 @@ def test_resident_realtime_kernel_equals_per_hop_launches(torch, zen, fs, hop, f
     assert np.array_equal(h.percussive_out, ref_obj.percussive_out)
     h.close()
     ref_obj.close()
+
+
+def test_batch_many_streams_sampled(torch, zen):
+    """a batch large enough to keep every resident CTA busy for several work items (work queue, L2-resident scratch
+    reuse between items): sampled streams must equal the per-hop path bit for bit"""
+    fs, hop, n_hops, n_streams = 44100.0, 1024, 150, 700
+    base = np.stack([synth_audio(n_hops * hop, seed=900 + s) for s in range(8)])
+    audio = np.tile(base, (n_streams // 8 + 1, 1))[:n_streams].copy()
+    audio *= (1.0 - 0.3 * (np.arange(n_streams) % 7)[:, None] / 7.0).astype(np.float32)
+    b = zen.HPRBatch(fs, hop, 2.5, 7)
+    outs = b.process(torch.from_numpy(audio).cuda())
+    torch.cuda.synchronize()
+    for s in (0, 1, 349, 698, 699):
+        h = zen.HPR(fs, hop, 2.5, 7, 0, True)
+        ref = h.run(audio[s])
+        h.close()
+        for o in range(3):
+            assert np.array_equal(outs[o][s].cpu().numpy(), ref[o]), (s, o)
+    b.close()
