@@ -60,6 +60,7 @@ def test_argument_and_geometry_errors_without_compute():
     assert L.zen_box_filter(9, 9, 10, _lib.TIME_ANTICAUSAL, 1, 1, None) == _lib.ZEN_ERR_GEOMETRY
     assert L.zen_median_filter(9, 9, 3, 0, 0, None, None, None) == _lib.ZEN_ERR_ARG
     assert L.zen_fft_c2c(1000, 1, 0, None) == _lib.ZEN_ERR_UNSUPPORTED
+    assert L.zen_fft_c2c(1 << 17, 1, 0, None) == _lib.ZEN_ERR_UNSUPPORTED
     a = np.zeros(8, np.float32)
     assert L.zen_offline_process(44100.0, 4096, 300, 2.0, 2.0, 0, a.ctypes.data, 8, a.ctypes.data, a.ctypes.data,
                                  a.ctypes.data) == _lib.ZEN_ERR_GEOMETRY     # hps.cu:33-36

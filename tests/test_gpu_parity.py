@@ -138,7 +138,7 @@ def test_fft_vs_cufft_golden(torch, zen, n):
         assert np.abs(got - d["n%d_%s" % (n, key)]).max() <= 2e-4
 
 
-@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
 def test_fft_vs_float64(torch, zen, n):
     rng = np.random.default_rng(n)
     x = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)

@@ -30,6 +30,25 @@ __global__ void __launch_bounds__(NT) fft_c2c_kernel(float2* __restrict__ data, 
 struct TwiddleCache {
 	std::mutex mu;
 	float2* tab[8][20] = {};
+	float2* scr[8] = {};
+	size_t scr_n[8] = {};
+	// scratch of the four-step transform, grown on demand (one per device; calls on one device are serialised by the caller's stream)
+	float2* scratch(size_t n)
+	{
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 8)
+			return nullptr;
+		std::lock_guard<std::mutex> lk(mu);
+		if (scr_n[dev] < n) {
+			cudaFree(scr[dev]);
+			scr[dev] = nullptr;
+			scr_n[dev] = 0;
+			if (cudaMalloc(&scr[dev], sizeof(float2) * n) != cudaSuccess)
+				return nullptr;
+			scr_n[dev] = n;
+		}
+		return scr[dev];
+	}
 	float2* get(int n, int order)
 	{
 		int dev = 0;
@@ -73,14 +92,83 @@ int launch_fft(float2* d, const float2* tw, int inverse, cudaStream_t s)
 	return ZEN_OK;
 }
 
+
+// ---- N = 32768, 65536: four-step FFT through global memory --------------------------------------------
+// N = N1 * N2.  With n = n1*N2 + n2 and k = k1 + N1*k2:
+//   X[k1 + N1*k2] = sum_{n2} [ w_N^(n2*k1) * sum_{n1} x[n1*N2 + n2] * w_N1^(n1*k1) ] * w_N2^(n2*k2)
+// Kernel 1: one CTA per column n2 does the N1-point FFT over n1 (stride N2), multiplies by the twiddle
+// w_N^(n2*k1) and stores Y[k1][n2] into a scratch buffer.  Kernel 2: one CTA per row k1 does the N2-point FFT
+// over n2 and scatters X[k1 + N1*k2] back into the caller's array.
+template <int N1, int N2, int NT, int S>
+__global__ void __launch_bounds__(NT) fft_large_cols_kernel(const float2* __restrict__ x, float2* __restrict__ y, const float2* __restrict__ tw1)
+{
+	extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+	float2* buf = reinterpret_cast<float2*>(fft_smem_raw);
+	const int n2 = blockIdx.x;
+	for (int n1 = threadIdx.x; n1 < N1; n1 += NT)
+		buf[fpad(n1)] = x[(size_t)n1 * N2 + n2];
+	__syncthreads();
+	fft_smem<N1, NT, S>(buf, tw1, threadIdx.x);
+	constexpr int N = N1 * N2;
+	for (int k1 = threadIdx.x; k1 < N1; k1 += NT) {
+		float sn, cs;
+		sincospif(2.0f * (float)(((long)n2 * k1) % N) / (float)N, &sn, &cs);  // accurate to ~1 ulp on the reduced angle
+		float2 w = make_float2(cs, S > 0 ? sn : -sn);
+		y[(size_t)k1 * N2 + n2] = cmul(buf[fpad(k1)], w);
+	}
+}
+
+template <int N1, int N2, int NT, int S>
+__global__ void __launch_bounds__(NT) fft_large_rows_kernel(const float2* __restrict__ y, float2* __restrict__ x, const float2* __restrict__ tw2)
+{
+	extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+	float2* buf = reinterpret_cast<float2*>(fft_smem_raw);
+	const int k1 = blockIdx.x;
+	for (int n2 = threadIdx.x; n2 < N2; n2 += NT)
+		buf[fpad(n2)] = y[(size_t)k1 * N2 + n2];
+	__syncthreads();
+	fft_smem<N2, NT, S>(buf, tw2, threadIdx.x);
+	for (int k2 = threadIdx.x; k2 < N2; k2 += NT)
+		x[(size_t)k1 + (size_t)N1 * k2] = buf[fpad(k2)];
+}
+
+template <int N1, int N2>
+int launch_fft_large(float2* d, int inverse, cudaStream_t s)
+{
+	constexpr int NT = 128;
+	int o1 = 0, o2 = 0;
+	while ((1 << o1) < N1) ++o1;
+	while ((1 << o2) < N2) ++o2;
+	const float2* tw1 = g_tw.get(N1, o1);
+	const float2* tw2 = g_tw.get(N2, o2);
+	float2* scratch = g_tw.scratch((size_t)N1 * N2);
+	if (!tw1 || !tw2 || !scratch)
+		return ZEN_ERR_CUDA;
+	size_t sm1 = sizeof(float2) * (size_t)fpad_size(N1), sm2 = sizeof(float2) * (size_t)fpad_size(N2);
+	if (inverse) {
+		fft_large_cols_kernel<N1, N2, NT, +1><<<N2, NT, sm1, s>>>(d, scratch, tw1);
+		fft_large_rows_kernel<N1, N2, NT, +1><<<N1, NT, sm2, s>>>(scratch, d, tw2);
+	}
+	else {
+		fft_large_cols_kernel<N1, N2, NT, -1><<<N2, NT, sm1, s>>>(d, scratch, tw1);
+		fft_large_rows_kernel<N1, N2, NT, -1><<<N1, NT, sm2, s>>>(scratch, d, tw2);
+	}
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	return ZEN_OK;
+}
+
 }  // namespace
 
 extern "C" int zen_fft_c2c(int nfft, float* d_inout, int inverse, void* cuda_stream)
 {
 	if (!d_inout || nfft < 2)
 		return ZEN_ERR_ARG;
-	if (!is_pow2(nfft) || nfft > 16384)
+	if (!is_pow2(nfft) || nfft > 65536)
 		return ZEN_ERR_UNSUPPORTED;
+	if (nfft == 32768)
+		return launch_fft_large<128, 256>(reinterpret_cast<float2*>(d_inout), inverse, (cudaStream_t)cuda_stream);
+	if (nfft == 65536)
+		return launch_fft_large<256, 256>(reinterpret_cast<float2*>(d_inout), inverse, (cudaStream_t)cuda_stream);
 	int order = 0;
 	while ((1 << order) < nfft)
 		++order;
