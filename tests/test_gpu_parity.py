@@ -480,3 +480,47 @@ def test_batch_many_streams_sampled(torch, zen):
         for o in range(3):
             assert np.array_equal(outs[o][s].cpu().numpy(), ref[o]), (s, o)
     b.close()
+
+
+SWEEP = [
+    # fs, hop, beta, flags, causal, copy_bord, sse, soft, n_hops
+    (22050.0, 512, 2.0, 7, True, True, False, False, 50),
+    (96000.0, 1024, 3.0, 7, True, True, False, False, 40),
+    (44100.0, 1024, 1.0, 7, True, True, False, False, 40),     # beta - eps < 1 <= beta
+    (44100.0, 512, 0.5, 7, True, True, False, False, 50),      # beta < 1: both masks can be 1, residual mask -1
+    (44100.0, 1024, 2.5, 1, True, True, False, False, 40),     # harmonic only
+    (44100.0, 1024, 2.5, 4, True, True, False, False, 40),     # residual only: masks of disabled outputs are 0 -> Mr = 1
+    (44100.0, 1024, 2.5, 5, True, False, False, False, 40),    # H + R, no copy border
+    (44100.0, 256, 2.5, 6, False, True, False, False, 80),     # P + R, anticausal
+    (44100.0, 1024, 0.7, 3, True, True, False, True, 40),      # soft mask with (int)beta == 0: x^0 / (x^0 + y^0 + eps)
+    (44100.0, 2048, 2.5, 3, True, True, False, True, 12),      # soft mask, L = 93 (warp-resident sliding window)
+    (44100.0, 4096, 2.5, 2, False, True, False, True, 8),      # soft mask, L = 187
+    (44100.0, 2048, 2.5, 7, False, True, True, False, 12),     # SSE at a large hop
+    (8000.0, 256, 2.0, 7, True, True, False, False, 60),
+]
+
+
+@pytest.mark.parametrize("fs,hop,beta,flags,causal,cb,sse,soft,n_hops", SWEEP)
+def test_hpr_parameter_sweep_vs_oracle(torch, zen, oracle, fs, hop, beta, flags, causal, cb, sse, soft, n_hops):
+    """sample rates, beta below / at / above 1, every output-flag subset, long frequency windows"""
+    audio = synth_audio(n_hops * hop, seed=int(fs) % 97 + hop, fs=int(fs))
+    try:
+        o = oracle.OracleHPR(oracle.GEOM_GPU, fs, hop, beta, flags, oracle.CAUSAL if causal else oracle.ANTICAUSAL, cb)
+    except ValueError:
+        with pytest.raises(zen.ZgException):
+            zen.HPR(fs, hop, beta, flags, 0 if causal else 1, cb)
+        return
+    h = zen.HPR(fs, hop, beta, flags, 0 if causal else 1, cb)
+    assert (h.l_harm, h.l_perc, h.lag, h.stft_width) == (o.l_harm, o.l_perc, o.lag, o.stft_width)
+    if sse:
+        o.use_sse_filter()
+        h.use_sse_filter()
+    if soft:
+        o.use_soft_mask()
+        h.use_soft_mask()
+    r = flip_aware_compare(h, o, audio, hop, flags, hard_mask=not (sse or soft))
+    assert r["margin_ok"], r["worst_margin"]
+    assert np.count_nonzero(r["flips"]) <= max(2, n_hops // 8), r["flips"]
+    for name, e, snr in zip("HPR", r["err"], r["snr"]):
+        assert e <= TOL_ABS and snr >= TOL_SNR, (name, e, snr)
+    h.close()
