@@ -32,54 +32,83 @@ __device__ __forceinline__ int wrap_idx(int i, int dim)
 	return i < 0 ? i + dim : i;
 }
 
-// ---- short windows (L <= 15): sorting network in registers ----
-// Frequency axis: one output per thread, taps are L consecutive floats that
-// neighbouring threads share through L1.  Time axis: RT consecutive rows per
-// thread so L + RT - 1 loads serve RT outputs.
-template <int L>
-__global__ void __launch_bounds__(256) median_small_freq_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
-{
-	const int r = blockIdx.y;
-	const int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= g.n_out)
-		return;
-	const int c = g.first + q;
-	const float* row = src + (size_t)r * g.F;
-	float v[L];
-#pragma unroll
-	for (int t = 0; t < L; ++t) {
-		int i = c + g.tap_off + t;
-		if (g.wrap) i = wrap_idx(i, g.F);
-		v[t] = __ldg(row + i);
-	}
-	dst[(size_t)r * g.F + c] = median_regs<L>(v);
-}
+// ---- windows up to 47 taps: one sorted window per thread, sliding along the filtered axis ----
+// (thread_sliding_run in median_select.cuh: 4 ALU ops per register and output, C = capacity >= L + 1).
+// Time axis: a thread owns one column and a run of consecutive output rows (8..64, shorter when the matrix is
+// too small to fill the GPU otherwise); lanes are adjacent
+// columns, so every load is coalesced and the tap that leaves is re-read from L1/L2.
+// Frequency axis: a CTA stages one row segment in shared memory with coalesced loads; a thread owns RUN_F
+// consecutive columns (odd, so the lanes' strided shared-memory accesses hit distinct banks); results go
+// back through shared memory for a coalesced store.
+constexpr int RUN_F = 17;
+constexpr int SM_NT = 128;
 
-template <int L, int RT>
-__global__ void __launch_bounds__(256) median_small_time_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+template <int C>
+__global__ void __launch_bounds__(256) median_run_time_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g,
+                                                              int run_t)
 {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	const int q0 = blockIdx.y * RT;
+	const int q0 = blockIdx.y * run_t;
 	if (c >= g.F)
 		return;
-	float w[L + RT - 1];
-#pragma unroll
-	for (int t = 0; t < L + RT - 1; ++t) {
-		int i = g.first + q0 + g.tap_off + t;
+	const int n_out = min(run_t, g.n_out - q0);
+	const int base = g.first + q0 + g.tap_off;
+	auto get = [&](int j) -> float {
+		int i = base + j;
 		if (g.wrap) i = wrap_idx(i, g.T);
-		// rows past the last output of this block are loaded only if they exist
-		bool ok = g.wrap || (i >= 0 && i < g.T);
-		w[t] = ok ? __ldg(src + (size_t)i * g.F + c) : 0.0f;
+		return __ldg(src + (size_t)i * g.F + c);
+	};
+	auto put = [&](int q, float v) { dst[(size_t)(g.first + q0 + q) * g.F + c] = v; };
+	thread_sliding_run<C>(get, put, n_out, g.L);
+}
+
+template <int C>
+__global__ void __launch_bounds__(SM_NT) median_run_freq_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+{
+	extern __shared__ float run_smem[];
+	constexpr int CHUNK = SM_NT * RUN_F;
+	float* E = run_smem;                    // CHUNK + L - 1
+	float* O = run_smem + CHUNK + g.L + 3;  // CHUNK
+	const int r = blockIdx.y;
+	const int q0 = blockIdx.x * CHUNK;
+	const int nq = min(CHUNK, g.n_out - q0);
+	const float* row = src + (size_t)r * g.F;
+	for (int t = threadIdx.x; t < nq + g.L - 1; t += SM_NT) {
+		int i = g.first + q0 + g.tap_off + t;
+		if (g.wrap) i = wrap_idx(i, g.F);
+		E[t] = __ldg(row + i);
 	}
-#pragma unroll
-	for (int u = 0; u < RT; ++u) {
-		if (q0 + u < g.n_out) {
-			float v[L];
-#pragma unroll
-			for (int t = 0; t < L; ++t)
-				v[t] = w[u + t];
-			dst[(size_t)(g.first + q0 + u) * g.F + c] = median_regs<L>(v);
-		}
+	__syncthreads();
+	const int s0 = threadIdx.x * RUN_F;
+	const int n_out = min(RUN_F, nq - s0);
+	auto get = [&](int j) -> float { return E[s0 + j]; };
+	auto put = [&](int q, float v) { O[s0 + q] = v; };
+	thread_sliding_run<C>(get, put, n_out, g.L);
+	__syncthreads();
+	for (int t = threadIdx.x; t < nq; t += SM_NT)
+		dst[(size_t)r * g.F + g.first + q0 + t] = O[t];
+}
+
+__global__ void __launch_bounds__(256) copy_axis_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+{
+	// L == 1: the median of one tap is the tap
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	const int r = blockIdx.y;
+	if (c >= g.F)
+		return;
+	if (g.axis == 1) {
+		if (c < g.first || c >= g.first + g.n_out)
+			return;
+		int i = c + g.tap_off;
+		if (g.wrap) i = wrap_idx(i, g.F);
+		dst[(size_t)r * g.F + c] = __ldg(src + (size_t)r * g.F + i);
+	}
+	else {
+		if (r < g.first || r >= g.first + g.n_out)
+			return;
+		int i = r + g.tap_off;
+		if (g.wrap) i = wrap_idx(i, g.T);
+		dst[(size_t)r * g.F + c] = __ldg(src + (size_t)i * g.F + c);
 	}
 }
 
@@ -184,17 +213,23 @@ int make_geom(AxisGeom& g, int T, int F, int filter_len, int dir, int copy_bord)
 	return ZEN_OK;
 }
 
-template <int L>
-void launch_small(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
+template <int C>
+void launch_run(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
 {
 	if (g.axis == 1) {
-		dim3 grid((g.n_out + 255) / 256, g.T);
-		median_small_freq_kernel<L><<<grid, 256, 0, s>>>(src, dst, g);
+		constexpr int CHUNK = SM_NT * RUN_F;
+		dim3 grid((g.n_out + CHUNK - 1) / CHUNK, g.T);
+		size_t smem = sizeof(float) * (size_t)(2 * CHUNK + g.L + 8);
+		median_run_freq_kernel<C><<<grid, SM_NT, smem, s>>>(src, dst, g);
 	}
 	else {
-		constexpr int RT = 4;
-		dim3 grid((g.F + 255) / 256, (g.n_out + RT - 1) / RT);
-		median_small_time_kernel<L, RT><<<grid, 256, 0, s>>>(src, dst, g);
+		// run length: long enough to amortise the initial sort, short enough for >= ~4 CTAs per SM
+		const int col_blocks = (g.F + 255) / 256;
+		int run_t = 64;
+		while (run_t > 8 && (long)col_blocks * ((g.n_out + run_t - 1) / run_t) < 600)
+			run_t >>= 1;
+		dim3 grid(col_blocks, (g.n_out + run_t - 1) / run_t);
+		median_run_time_kernel<C><<<grid, 256, 0, s>>>(src, dst, g, run_t);
 	}
 }
 
@@ -214,16 +249,26 @@ int zen_median_filter(int time, int freq, int filter_len, int direction, int cop
 	if (g.n_out <= 0)
 		return ZEN_OK;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	switch (g.L) {
-	case 1: launch_small<1>(d_src, d_dst, g, s); break;
-	case 3: launch_small<3>(d_src, d_dst, g, s); break;
-	case 5: launch_small<5>(d_src, d_dst, g, s); break;
-	case 7: launch_small<7>(d_src, d_dst, g, s); break;
-	case 9: launch_small<9>(d_src, d_dst, g, s); break;
-	case 11: launch_small<11>(d_src, d_dst, g, s); break;
-	case 13: launch_small<13>(d_src, d_dst, g, s); break;
-	case 15: launch_small<15>(d_src, d_dst, g, s); break;
-	default: {
+	if (g.L == 1) {
+		dim3 grid((g.F + 255) / 256, g.T);
+		copy_axis_kernel<<<grid, 256, 0, s>>>(d_src, d_dst, g);
+	}
+	else if (g.L <= 47) {
+		switch (g.L) {
+		case 3: launch_run<4>(d_src, d_dst, g, s); break;
+		case 5: launch_run<6>(d_src, d_dst, g, s); break;
+		case 7: launch_run<8>(d_src, d_dst, g, s); break;
+		case 9: launch_run<10>(d_src, d_dst, g, s); break;
+		case 11: launch_run<12>(d_src, d_dst, g, s); break;
+		case 13: launch_run<14>(d_src, d_dst, g, s); break;
+		case 15: launch_run<16>(d_src, d_dst, g, s); break;
+		default:
+			if (g.L <= 23) launch_run<24>(d_src, d_dst, g, s);
+			else if (g.L <= 31) launch_run<32>(d_src, d_dst, g, s);
+			else launch_run<48>(d_src, d_dst, g, s);
+		}
+	}
+	else {
 		const int K = g.axis == 1 ? sliding_K_for(g.L) : 0;
 		if (K > 0) {
 			dim3 grid((g.n_out + SL_CHUNK - 1) / SL_CHUNK, g.T);
@@ -235,7 +280,6 @@ int zen_median_filter(int time, int freq, int filter_len, int direction, int cop
 			dim3 grid((n_other + 255) / 256, g.n_out);
 			median_generic_kernel<<<grid, 256, 0, s>>>(d_src, d_dst, g);
 		}
-	}
 	}
 	ZEN_CUDA_CHECK(cudaGetLastError());
 	return ZEN_OK;

@@ -281,6 +281,31 @@ __device__ __forceinline__ void thread_sliding_median(const float* __restrict__ 
 	}
 }
 
+// Same sliding window, taps fetched through `get(j)` (j-th sample of the run's extended line) and results
+// handed to `put(q, value)`: used by the standalone filter kernels, whose taps live in global or shared
+// memory with arbitrary strides.  Output q is the median of get(q) .. get(q+L-1).
+template <int C, typename Get, typename Put>
+__device__ __forceinline__ void thread_sliding_run(Get get, Put put, int n_out, int L)
+{
+	if (n_out <= 0)
+		return;
+	const int pad_lo = C / 2 - (L >> 1);
+	float S[C];
+#pragma unroll
+	for (int p = 0; p < C; ++p) {
+		int idx = p - pad_lo;
+		S[p] = idx < 0 ? -CUDART_INF_F : (idx < L ? get(idx) : CUDART_INF_F);
+	}
+	oe_sort<0, next_pow2(C), C>(S);
+	put(0, S[C / 2]);
+	for (int q = 1; q < n_out; ++q) {
+		float o = get(q - 1);
+		float v = get(q + L - 1);
+		thread_window_slide<C>(S, o, v);
+		put(q, S[C / 2]);
+	}
+}
+
 __device__ __forceinline__ void thread_sliding_median_dyn(int C, const float* E, float* out, int s0, int s1, int L)
 {
 	switch (C) {
