@@ -310,8 +310,10 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 	// (the zero padding n >= HOP is never stored: the first FFT stage knows it is zero)
 	for (int n = tid; n < HOP; n += NT) {
 		float2 x;
-		if (n < HOP / 2)
-			x = prev ? reinterpret_cast<const float2*>(prev)[n] : make_float2(0.0f, 0.0f);
+		if (n < HOP / 2)  // last use of that hop: streaming load, so it does not push the per-CTA scratch out of L2
+			x = !prev ? make_float2(0.0f, 0.0f)
+			          : (__isGlobal(prev) ? __ldcs(reinterpret_cast<const float2*>(prev) + n)  // (the resident kernel keeps it in smem)
+			                              : reinterpret_cast<const float2*>(prev)[n]);
 		else {
 			x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
 			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
@@ -624,8 +626,8 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			float2 v = sm.zbuf[fpad(n)];
 			float2 t = fresh_tail ? make_float2(0.0f, 0.0f) : reinterpret_cast<const float2*>(tail)[n];
 			float2 r = make_float2(fmaf(v.x, P.cola, t.x), fmaf(v.y, P.cola, t.y));
-			if (em.a[o]) reinterpret_cast<float2*>(em.a[o])[n] = r;
-			if (em.b[o]) reinterpret_cast<float2*>(em.b[o])[n] = r;
+			if (em.a[o]) __stcs(reinterpret_cast<float2*>(em.a[o]) + n, r);  // written once, never re-read by the kernel
+			if (em.b[o]) __stcs(reinterpret_cast<float2*>(em.b[o]) + n, r);
 		}
 		__syncthreads();
 		for (int n = HOP / 2 + tid; n < HOP; n += NT) {
