@@ -163,7 +163,8 @@ int zen_fakert_run(float fs, int hop, float beta, int options, const float* h_au
  * d_in: n_streams rows of n_hops*hop samples (row stride in_stride floats);
  * d_out_*: same layout (row stride out_stride), NULL for outputs not wanted.
  * causality ZEN_TIME_CAUSAL reproduces HPRRealtime, ZEN_TIME_ANTICAUSAL the
- * objects HPRIOffline drives.  options: ZEN_OPT_* bits. */
+ * objects HPRIOffline drives.  options: ZEN_OPT_* bits.  max_streams / max_hops_per_stream are sizing hints
+ * (1 is fine): scratch belongs to the resident CTAs and staging buffers grow on demand. */
 typedef struct zen_hpr_batch zen_hpr_batch;
 int zen_hpr_batch_create(zen_hpr_batch** out, float fs, int hop, float beta, unsigned output_flags,
                          int causality, int options, int max_streams, long max_hops_per_stream);

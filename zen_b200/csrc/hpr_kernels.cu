@@ -884,12 +884,12 @@ namespace {
 int choose_tile_hops(const Plan& pl, int n_streams, long n_hops, int resident)
 {
 	if (resident < 1) resident = 148;
-	const long items_wanted = 32L * resident;
+	const long items_wanted = 32L * resident;  // many small items: the tail when the queue runs dry stays short
 	long tiles_wanted = (items_wanted + n_streams - 1) / n_streams;
 	if (tiles_wanted < 1) tiles_wanted = 1;
 	long tile = (n_hops + tiles_wanted - 1) / tiles_wanted;
-	long min_tile = 16L * pl.dev.W;  // halo <= 6 % of the tile
-	if (min_tile < 32) min_tile = 32;
+	long min_tile = 4L * pl.dev.W;  // the halo (analysis only, roughly a third of a full hop) stays below ~10 % of the tile's work
+	if (min_tile < 16) min_tile = 16;
 	if (tile < min_tile) tile = min_tile;
 	if (tile > n_hops) tile = n_hops;
 	if (tile < 1) tile = 1;

@@ -16,10 +16,11 @@ constexpr int nt_for()
 #ifndef ZEN_TILE_THREADS_PER_SM
 #define ZEN_TILE_THREADS_PER_SM 1024
 #endif
-template <int NT>
+template <int NT, int NFFT = 0>
 constexpr int min_blocks_for()
 {
-	return NT >= 512 ? 1 : ZEN_TILE_THREADS_PER_SM / NT;
+	// 512-thread CTAs: two fit at nfft 8192 (101 KB of shared memory each), one at 16384 (200 KB)
+	return NT >= 512 ? (NFFT == 8192 ? 2 : 1) : ZEN_TILE_THREADS_PER_SM / NT;
 }
 
 struct TileArgs {
@@ -112,7 +113,7 @@ using namespace zen_b200;
 // half is the first overlap-add tail of the tile).  Frames are independent
 // given that halo, so tiles need no communication.
 template <int NFFT, int NT>
-__global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_tile_kernel(const __grid_constant__ HprDev P,
+__global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_kernel(const __grid_constant__ HprDev P,
                                                                             const float* __restrict__ in, long in_stride,
                                                                             float* out_h, float* out_p, float* out_r, long out_stride,
                                                                             long n_hops, int tile_hops, int n_tiles, int total_items,
