@@ -524,3 +524,35 @@ def test_hpr_parameter_sweep_vs_oracle(torch, zen, oracle, fs, hop, beta, flags,
     for name, e, snr in zip("HPR", r["err"], r["snr"]):
         assert e <= TOL_ABS and snr >= TOL_SNR, (name, e, snr)
     h.close()
+
+
+@pytest.mark.parametrize("kind", ["zeros", "dc", "impulse", "alternating", "tiny", "zeros_then_noise"])
+@pytest.mark.parametrize("sse,soft", [(False, False), (False, True), (True, False)])
+def test_hpr_edge_inputs(torch, zen, oracle, kind, sse, soft):
+    """silence (0/0 in the masks, 1/0 in the SSE reciprocal), DC, a single impulse, Nyquist, near-denormal levels"""
+    fs, hop, n_hops = 44100.0, 512, 40
+    n = n_hops * hop
+    rng = np.random.default_rng(3)
+    x = {"zeros": np.zeros(n), "dc": np.full(n, 0.5), "impulse": np.eye(1, n, 7 * hop + 13)[0],
+         "alternating": np.where(np.arange(n) % 2 == 0, 1.0, -1.0), "tiny": 1e-30 * rng.standard_normal(n),
+         "zeros_then_noise": np.concatenate([np.zeros(n // 2), 0.3 * rng.standard_normal(n - n // 2)])}[kind].astype(np.float32)
+    o = oracle.OracleHPR(oracle.GEOM_GPU, fs, hop, 2.5, 7, oracle.CAUSAL, True)
+    h = zen.HPR(fs, hop, 2.5, 7, 0, True)
+    if sse:
+        o.use_sse_filter()
+        h.use_sse_filter()
+    if soft:
+        o.use_soft_mask()
+        h.use_soft_mask()
+    with np.errstate(all="ignore"):
+        r = flip_aware_compare(h, o, x, hop, 7, hard_mask=not (sse or soft))
+    for name, g, ref in zip("HPR", r["got"], r["ref"]):
+        assert np.array_equal(np.isnan(g), np.isnan(ref)), (name, "NaN pattern")
+    if kind == "zeros":
+        for g in r["got"]:
+            assert np.all(np.nan_to_num(g) == 0)
+    assert r["margin_ok"], r["worst_margin"]
+    for name, e, snr, ref in zip("HPR", r["err"], r["snr"], r["ref"]):
+        if np.isfinite(e) and np.nanmax(np.abs(ref)) > 0:
+            assert e <= TOL_ABS and (snr >= TOL_SNR or not np.isfinite(snr)), (name, e, snr)
+    h.close()
