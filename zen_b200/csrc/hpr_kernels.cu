@@ -1000,7 +1000,12 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 	const unsigned f = b->plan.dev.out_flags;
 	float* h_out[3] = {(f & 1) ? h_out_h : nullptr, (f & 2) ? h_out_p : nullptr, (f & 4) ? h_out_r : nullptr};
 	// chunk so that one chunk's input is ~128 MB
-	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, ((size_t)128 << 20) / (row * sizeof(float)) + 1));
+	size_t chunk_mb = 128;
+	if (const char* e = std::getenv("ZEN_B200_CHUNK_MB")) {
+		long v = std::atol(e);
+		if (v > 0) chunk_mb = (size_t)v;
+	}
+	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, (chunk_mb << 20) / (row * sizeof(float)) + 1));
 	if (chunk > b->stage_streams) {
 		for (int s = 0; s < ZEN_PIPE_SLOTS; ++s) {
 			cudaFree(b->d_stage_in[s]);

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_kerne
 // the zen_hpr object between launches.  ola[o] is the reference's *_out vector:
 // [0:hop] the emitted hop, [hop:nwin] the overlap-add tail.
 template <int NFFT, int NT>
-__global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_hop_kernel(const __grid_constant__ HprDev P, HprState st, long i,
+__global__ void __launch_bounds__(NT, 1) hpr_hop_kernel(const __grid_constant__ HprDev P, HprState st, long i,
                                                      float* input /* nwin: previous hop | current hop */,
                                                      const float* __restrict__ in_hop,
                                                      float* ola_h, float* ola_p, float* ola_r,
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT>()) hpr_hop_kernel(const
 		em.a[o] = (P.out_flags & (1 << o)) ? ola[o] : nullptr;
 		em.b[o] = (P.out_flags & (1 << o)) ? ext[o] : nullptr;
 	}
-	hpr_iteration<NFFT, NT>(P, sm, st, (int)i, input, input + HOP, true, false, em);
+	hpr_iteration<NFFT, NT, rt_u_for<NFFT>()>(P, sm, st, (int)i, input, input + HOP, true, false, em);
 	// outputs that the masks never reach still advance like the reference's
 	// rotate-and-zero (hps.cu:435-449): residual with soft mask / SSE
 	if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse)) {
@@ -417,7 +417,7 @@ int tile_resident_ctas(const HprDev& d)
 template <int NFFT>
 int launch_hop_impl(const HopArgs& a)
 {
-	constexpr int NT = nt_for<NFFT>();
+	constexpr int NT = nt_rt_for<NFFT>();  // one CTA per hop: latency, not throughput, decides the thread count
 	auto kern = hpr_hop_kernel<NFFT, NT>;
 	size_t smem = HprSmem<NFFT>::bytes(a.dev.Lp);
 	static thread_local size_t configured = 0;
