@@ -462,6 +462,52 @@ def test_resident_realtime_kernel_equals_per_hop_launches(torch, zen, fs, hop, f
     h.close()
     ref_obj.close()
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("hop,flags,mode", [(1024, 7, "device"), (1024, 2, "pull"), (32, 7, "push"), (2048, 3, "device"),
+                                            (4096, 2, "mixed")])
+def test_resident_kernel_request_protocols(torch, zen, hop, flags, mode):
+    """the resident kernel takes the hop either pushed in tagged 16-byte groups (host-visible buffers, the IOGPU
+    case) or pulled by the kernel itself (device memory, or ZEN_B200_RT_PUSH=0), and emits either tagged groups or
+    plain stores + completion flag: every combination must give the per-launch result bit for bit, also when the
+    buffers change from one hop to the next"""
+    fs, n_hops = 44100.0, 24
+    audio = synth_audio(n_hops * hop, seed=78)
+    ref_obj = zen.HPR(fs, hop, 2.5, flags, 0, True)
+    ref = ref_obj.run(audio)
+    ref_obj.close()
+    if mode == "pull":
+        os.environ["ZEN_B200_RT_PUSH"] = "0"
+    try:
+        h = zen.HPR(fs, hop, 2.5, flags, 0, True)
+        h.realtime_begin()
+        ios = [zen.IOGPU(hop) for _ in range(2)]
+        houts = [[zen.IOGPU(hop) for _ in range(3)] for _ in range(2)]
+        d_in = torch.from_numpy(audio).cuda()
+        d_out = [torch.zeros(n_hops * hop, dtype=torch.float32, device="cuda") for _ in range(3)]
+        got = [np.zeros(n_hops * hop, np.float32) for _ in range(3)]
+        for i in range(n_hops):
+            sl = slice(i * hop, (i + 1) * hop)
+            dev_in = mode == "device" or (mode == "mixed" and i % 3 == 0)
+            dev_out = mode == "device" or (mode == "mixed" and i % 4 < 2)
+            io, ho = ios[i & 1], houts[(i >> 1) & 1]
+            io.host_in[:] = audio[sl]
+            src = d_in[sl].data_ptr() if dev_in else io.device_in
+            dst = [d_out[o][sl].data_ptr() if dev_out else ho[o].device_out for o in range(3)]
+            h.process_hop_io(src, *dst)
+            if dev_out:
+                torch.cuda.synchronize()
+            for o in range(3):
+                if flags & (1 << o):
+                    got[o][sl] = d_out[o][sl].cpu().numpy() if dev_out else ho[o].host_out
+        for o in range(3):
+            if flags & (1 << o):
+                assert np.array_equal(got[o], ref[o]), o
+        assert max(np.abs(got[o]).max() for o in range(3)) > 0
+        h.close()
+    finally:
+        os.environ.pop("ZEN_B200_RT_PUSH", None)
+
+
 
 def test_batch_many_streams_sampled(torch, zen):
     """a batch large enough to keep every resident CTA busy for several work items (work queue, L2-resident scratch

@@ -1,5 +1,6 @@
 """Phase breakdown (device globaltimer) of one hop served by the resident real-time kernel."""
-import ctypes, sys, time
+import ctypes, os, sys, time
+os.environ["ZEN_B200_RT_STAMPS"] = "1"
 sys.path.insert(0, ".")
 import numpy as np
 from zen_b200 import _lib, hps
@@ -19,7 +20,9 @@ for i in range(400):
     _lib.lib().zen_hpr_realtime_stamps(h._h, st)
     if i >= 100:
         s = list(st)
-        acc.append([(t1 - t0) * 1e6] + [(s[k + 1] - s[k]) / 1e3 for k in range(8)] + [(s[0] - s[9]) / 1e3, (s[8] - s[9]) / 1e3, (s[11] - s[10]) / max(1.0, float(s[8] - s[9]))])
+        ghz = (s[11] - s[10]) / max(1.0, float(s[12] - s[9]))  # SM cycles per globaltimer ns over the whole hop
+        cyc = 1e3 * ghz                                        # cycles per us
+        acc.append([(t1 - t0) * 1e6] + [(s[k + 1] - s[k]) / cyc for k in range(8)] + [(s[0] - s[10]) / cyc, (s[8] - s[10]) / cyc, ghz])
 a = np.median(np.array(acc), axis=0)
 names = ["host call us", "A load+window", "B fft fwd", "C split+mag", "F' H row", "E' decide", "G build", "G ifft", "G ola+emit", "pre", "kernel total", "SM clock GHz"]
 for n, v in zip(names, a):

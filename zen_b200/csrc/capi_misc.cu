@@ -70,7 +70,10 @@ int zen_io_alloc(zen_io* io, size_t size)
 	std::memset(io, 0, sizeof(*io));
 	io->size = size;
 	unsigned flags = cudaHostAllocMapped | cudaHostAllocPortable;
-	ZEN_CUDA_CHECK(cudaHostAlloc((void**)&io->host_in, size * sizeof(float), flags | cudaHostAllocWriteCombined));
+	// The reference allocates host_in write-combined (libzen/libzen/io.h:30-34).  Ours is ordinary cached pinned memory:
+	// the resident real-time kernel's host side re-reads the hop to push it in tagged groups (rt_publish), and reading
+	// write-combined memory back on the host is uncached.
+	ZEN_CUDA_CHECK(cudaHostAlloc((void**)&io->host_in, size * sizeof(float), flags));
 	ZEN_CUDA_CHECK(cudaHostAlloc((void**)&io->host_out, size * sizeof(float), flags));
 	ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&io->device_in, io->host_in, 0));
 	ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&io->device_out, io->host_out, 0));

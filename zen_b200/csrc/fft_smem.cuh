@@ -134,7 +134,9 @@ inline int fft_twiddle_count_rt(int M)
 //       arithmetic that depends on them disappear (first stage only).
 // HOUT: only the lower half of the output is needed: the stores of the upper half and the arithmetic feeding
 //       them disappear (last stage only).
-template <int M, int NT, int S, int R, int NS, bool ZIN = false, bool HOUT = false>
+// GT  : tw may point into shared memory (the resident real-time kernel keeps its tables there): plain generic
+//       loads instead of the read-only global path.
+template <int M, int NT, int S, int R, int NS, bool ZIN = false, bool HOUT = false, bool GT = false>
 __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ tw, int tid)
 {
 	constexpr int NB = M / R;
@@ -149,7 +151,7 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 			if constexpr (NS > 1) {
 #pragma unroll
 				for (int r = 1; r < R; ++r)
-					w[r] = __ldg(&tw[(r - 1) * NS + k]);
+					w[r] = GT ? tw[(r - 1) * NS + k] : __ldg(&tw[(r - 1) * NS + k]);
 			}
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
@@ -188,14 +190,14 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict_
 // M-point complex FFT in shared memory, all NT threads of the CTA participate.
 // tw: the per-stage tables of fft_fill_twiddles(M).  The caller must have
 // synchronised after filling buf.  Ends synchronised.
-template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false>
+template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
 __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
 {
 	if constexpr (NS < M) {
 		constexpr int rem = M / NS;
 		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
-		fft_stage<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M)>(buf, tw, tid);
-		fft_smem<M, NT, S, NS * R, ZIN, HOUT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
+		fft_stage<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M), GT>(buf, tw, tid);
+		fft_smem<M, NT, S, NS * R, ZIN, HOUT, GT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
 	}
 }
 

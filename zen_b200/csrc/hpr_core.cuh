@@ -61,6 +61,22 @@ struct HprEmit {
 	float* b[3];  // optional second destination
 };
 
+// Table overrides of the resident real-time kernel (copies in shared memory; generic loads).
+struct HprTables {
+	const float* window;
+	const float2* tw;
+	const float2* twr;
+};
+
+// Tagged emission of the resident real-time kernel: the emitted hop is also written to mapped host memory as
+// 16-byte groups {x[3g], x[3g+1], x[3g+2], tag}.  One group is one aligned 16-byte store, so the host sees a
+// group either old or complete and needs no completion flag behind a system-wide fence (rt_call, hpr_kernels.cu).
+struct HprPack {
+	float* buf;     // hop floats of shared memory
+	uint4* dst[3];  // per output (H, P, R) or null
+	unsigned tag;
+};
+
 template <int NFFT>
 struct HprSmem {
 	static constexpr int M = NFFT / 2;
@@ -271,22 +287,61 @@ __device__ __forceinline__ float median_fixed(Get get)
 	return median_regs<L>(v);
 }
 
+// overlap-add of one output and emission of the hop: out = tail + Re(y[0:hop]) * COLA ; tail' = Re(y[hop:nwin]) * COLA
+// (hps.h:68-80).  zb holds the inverse transform (packed: zb[n] = (y[2n], y[2n+1])).  Ends synchronised.
+template <int NFFT, int NT>
+__device__ __forceinline__ void hpr_ola_emit(const HprDev& P, const float2* zb, float* tail, bool fresh_tail, float* ea, float* eb,
+                                             float* pbuf, uint4* pdst, unsigned ptag)
+{
+	constexpr int M = NFFT / 2, HOP = M / 2;
+	const int tid = threadIdx.x;
+	for (int n = tid; n < HOP / 2; n += NT) {
+		float2 v = zb[fpad(n)];
+		float2 t = fresh_tail ? make_float2(0.0f, 0.0f) : reinterpret_cast<const float2*>(tail)[n];
+		float2 r = make_float2(fmaf(v.x, P.cola, t.x), fmaf(v.y, P.cola, t.y));
+		if (ea) __stcs(reinterpret_cast<float2*>(ea) + n, r);  // written once, never re-read by the kernel
+		if (eb) __stcs(reinterpret_cast<float2*>(eb) + n, r);
+		if (pdst) reinterpret_cast<float2*>(pbuf)[n] = r;
+	}
+	__syncthreads();
+	if (pdst) {
+		for (int g = tid; 3 * g < HOP; g += NT) {
+			uint4 v;
+			v.x = __float_as_uint(pbuf[3 * g]);
+			v.y = 3 * g + 1 < HOP ? __float_as_uint(pbuf[3 * g + 1]) : 0u;
+			v.z = 3 * g + 2 < HOP ? __float_as_uint(pbuf[3 * g + 2]) : 0u;
+			v.w = ptag;
+			asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pdst + g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+			             : "memory");
+		}
+	}
+	for (int n = HOP / 2 + tid; n < HOP; n += NT) {
+		float2 v = zb[fpad(n)];
+		reinterpret_cast<float2*>(tail)[n - HOP / 2] = make_float2(v.x * P.cola, v.y * P.cola);
+	}
+	__syncthreads();
+}
+
 // One hop.  `full` == false: analysis only (fills the rings; halo iterations of a tile).
 // All NT threads of the CTA must call it with identical arguments.
 // cur_stash (optional): the incoming hop is also copied there while it is read (the persistent
 // real-time kernel keeps it in shared memory as the next hop's `prev`).
-template <int NFFT, int NT, int U = ZEN_DECIDE_U>
+template <int NFFT, int NT, int U = ZEN_DECIDE_U, bool GT = false>
 __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
                                               const float* __restrict__ prev, const float* __restrict__ cur,
                                               bool full, bool fresh_tail, const HprEmit& em, float* cur_stash = nullptr,
-                                              unsigned long long* stamps = nullptr, const float* next_hop = nullptr)
+                                              unsigned long long* stamps = nullptr, const float* next_hop = nullptr,
+                                              const HprTables* tb = nullptr, const HprPack* pk = nullptr)
 {
+	const float* const t_window = GT ? tb->window : P.window;
+	const float2* const t_tw = GT ? tb->tw : P.tw;
+	const float2* const t_twr = GT ? tb->twr : P.twr;
+	auto ldt = [](const auto* p) { return GT ? *p : __ldg(p); };
+	// diagnostics (tools/rt_phases.py): SM cycle counter at the phase boundaries.  Not %globaltimer: reading it takes
+	// a fraction of a microsecond, and thread 0 would hold every barrier of the hop back by that much.
 	auto stamp = [&](int idx) {
-		if (stamps && threadIdx.x == 0) {
-			unsigned long long t;
-			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-			stamps[idx] = t;
-		}
+		if (stamps && threadIdx.x == 0)
+			stamps[idx] = (unsigned long long)clock64();
 	};
 	stamp(0);
 	constexpr int M = NFFT / 2;   // complex FFT length; also nwin
@@ -318,14 +373,14 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
 			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
 		}
-		float2 w = __ldg(reinterpret_cast<const float2*>(P.window) + n);
+		float2 w = ldt(reinterpret_cast<const float2*>(t_window) + n);
 		sm.zbuf[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
 	}
 	__syncthreads();
 	stamp(1);
 
 	// ---- B. forward FFT (hps.cu:465)
-	fft_smem<M, NT, -1, 1, true, false>(sm.zbuf, P.tw, tid);
+	fft_smem<M, NT, -1, 1, true, false, GT>(sm.zbuf, t_tw, tid);
 	stamp(2);
 
 	// ---- C. split into the real-input spectrum X[0..M], magnitudes into the ring (hps.cu:469-472, 492-493)
@@ -349,7 +404,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 				float2 A = sm.zbuf[fpad(k)];
 				float2 B = cconj(sm.zbuf[fpad(M - k)]);
 				float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
-				float2 O = cmul(__ldg(&P.twr[k]), csub(A, B));
+				float2 O = cmul(ldt(&t_twr[k]), csub(A, B));
 				float2 D = make_float2(0.5f * O.y, -0.5f * O.x);
 				Xa = cadd(E, D);
 				Xb = cconj(csub(E, D));
@@ -574,10 +629,11 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 
 	// ---- G. per output: mask, inverse real FFT, overlap-add (hps.cu:498-579, 607-651)
 	// order P, H, R as in the reference; output index 0 = H, 1 = P, 2 = R
-	const int order[3] = {1, 0, 2};
+	// (no dynamically indexed local arrays: they would live in local memory, and a kernel launched per hop or a
+	// resident one after its system-wide fence finds none of it in L1)
 #pragma unroll 1
 	for (int oi = 0; oi < 3; ++oi) {
-		const int o = order[oi];
+		const int o = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
 		if (!(P.out_flags & (1 << o)))
 			continue;
 		if (o == 2 && (P.soft || P.sse))
@@ -611,32 +667,230 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			else {
 				float2 B = cconj(Yb);
 				float2 E2 = cadd(A, B);
-				float2 O2 = cmul(cconj(__ldg(&P.twr[k])), csub(A, B));
+				float2 O2 = cmul(cconj(ldt(&t_twr[k])), csub(A, B));
 				sm.zbuf[fpad(k)] = make_float2(E2.x - O2.y, E2.y + O2.x);
 				sm.zbuf[fpad(kb)] = make_float2(E2.x + O2.y, O2.x - E2.y);
 			}
 		}
 		__syncthreads();
 		stamp(6);
-		fft_smem<M, NT, +1, 1, false, true>(sm.zbuf, P.tw, tid);
+		fft_smem<M, NT, +1, 1, false, true, GT>(sm.zbuf, t_tw, tid);
 		stamp(7);
-		// overlap-add: out = tail + Re(y[0:hop]) * COLA ; tail' = Re(y[hop:nwin]) * COLA   (hps.h:68-80)
-		float* tail = st.tail[o];
-		for (int n = tid; n < HOP / 2; n += NT) {
-			float2 v = sm.zbuf[fpad(n)];
-			float2 t = fresh_tail ? make_float2(0.0f, 0.0f) : reinterpret_cast<const float2*>(tail)[n];
-			float2 r = make_float2(fmaf(v.x, P.cola, t.x), fmaf(v.y, P.cola, t.y));
-			if (em.a[o]) __stcs(reinterpret_cast<float2*>(em.a[o]) + n, r);  // written once, never re-read by the kernel
-			if (em.b[o]) __stcs(reinterpret_cast<float2*>(em.b[o]) + n, r);
-		}
-		__syncthreads();
-		for (int n = HOP / 2 + tid; n < HOP; n += NT) {
-			float2 v = sm.zbuf[fpad(n)];
-			reinterpret_cast<float2*>(tail)[n - HOP / 2] = make_float2(v.x * P.cola, v.y * P.cola);
-		}
-		__syncthreads();
+		float* const tail = o == 0 ? st.tail[0] : (o == 1 ? st.tail[1] : st.tail[2]);
+		float* const ea = o == 0 ? em.a[0] : (o == 1 ? em.a[1] : em.a[2]);
+		float* const eb = o == 0 ? em.b[0] : (o == 1 ? em.b[1] : em.b[2]);
+		uint4* const pdst = !pk ? nullptr : (o == 0 ? pk->dst[0] : (o == 1 ? pk->dst[1] : pk->dst[2]));
+		hpr_ola_emit<NFFT, NT>(P, sm.zbuf, tail, fresh_tail, ea, eb, pk ? pk->buf : nullptr, pdst, pk ? pk->tag : 0u);
 		stamp(8);
 	}
+}
+
+// ---- one real-time hop split over a thread-block cluster ---------------------
+// The resident kernel may run as a cluster of C CTAs (hpr_rt_kernel).  Every CTA takes the hop and runs the forward
+// FFT redundantly (it is latency-, not throughput-bound); the per-bin work that follows - split into the real-input
+// spectrum, |X|, time median, hard-mask decision by counting, masked spectrum - is divided by bin PAIRS (k, M-k):
+// CTA r owns pairs [r*Q, (r+1)*Q), i.e. the bin ranges A = [a0, a1) and B = [b0, b1), and analyses a halo of
+// midp + US bins around them for the frequency windows.  Each CTA keeps the |X| ring of its own bins only.  The masked
+// spectrum of output o is written straight into the receive buffer of the CTA that owns the output (distributed
+// shared memory); after one cluster barrier that CTA runs the inverse FFT and the overlap-add (hpr_split_synth).
+// Hard mask, copy-border, lag 1 only: the configuration of HPRRealtime's default path (hps.cu:282-427).
+struct HprSplit {
+	int rank, C;
+	int k0, k1;          // own pairs [k0, k1)
+	int a0, a1, b0, b1;  // own bins
+	float2* recv[3];     // per output (H, P, R): the owner's receive buffer, fpad_size(M) float2, or null when the output is off
+	int owner[3];        // rank of the CTA that synthesises output o (-1: off)
+};
+
+__host__ __device__ inline void hpr_split_ranges(int M, int rank, int C, int& k0, int& k1, int& a0, int& a1, int& b0, int& b1)
+{
+	const int Q = (M / 2 + 1 + C - 1) / C;
+	k0 = rank * Q < M / 2 + 1 ? rank * Q : M / 2 + 1;
+	k1 = k0 + Q < M / 2 + 1 ? k0 + Q : M / 2 + 1;
+	a0 = k0;
+	a1 = k1;
+	b0 = M - k1 + 1 > k1 ? M - k1 + 1 : k1;  // bin M/2 is its own partner
+	b1 = M - k0 + 1;
+	if (k0 >= k1) b0 = b1 = a1 = a0;
+}
+
+template <int NFFT, int NT, int US>
+__device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
+                                                  const float* __restrict__ prev, const float* __restrict__ cur, const HprTables& tb,
+                                                  const HprSplit& sp, unsigned long long* stamps)
+{
+	auto stamp = [&](int idx) {
+		if (stamps && threadIdx.x == 0)
+			stamps[idx] = (unsigned long long)clock64();
+	};
+	stamp(0);
+	constexpr int M = NFFT / 2;
+	constexpr int HOP = M / 2;
+	const int tid = threadIdx.x;
+	const int W = P.W;
+	const int eoff = P.midp;
+	for (int t = tid; t < P.n_taps; t += NT) {
+		int j = i - P.tap_age[t];
+		sm.taps[t] = j >= 0 ? (j % W) * (M + 1) : -1;
+	}
+	// ---- A. window (prev and cur are in shared memory)
+	for (int n = tid; n < HOP; n += NT) {
+		float2 x = n < HOP / 2 ? reinterpret_cast<const float2*>(prev)[n] : reinterpret_cast<const float2*>(cur)[n - HOP / 2];
+		float2 w = reinterpret_cast<const float2*>(tb.window)[n];
+		sm.zbuf[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
+	}
+	__syncthreads();
+	stamp(1);
+	// ---- B. forward FFT, whole frame
+	fft_smem<M, NT, -1, 1, true, false, true>(sm.zbuf, tb.tw, tid);
+	stamp(2);
+	// ---- C. real-input spectrum and |X| of the own pairs and their halo
+	const int halo = P.midp + US;
+	const int pl = max(0, sp.k0 - halo), ph = min(M / 2, sp.k1 - 1 + halo);
+	{
+		float* mag_row = st.mag_ring + (size_t)(i % W) * (M + 1);
+		for (int k = pl + tid; k <= ph; k += NT) {
+			float2 Xa, Xb;
+			const int ka = k, kb = M - k;
+			if (k == 0) {
+				float2 Z0 = sm.zbuf[fpad(0)];
+				Xa = make_float2(Z0.x + Z0.y, 0.0f);
+				Xb = make_float2(Z0.x - Z0.y, 0.0f);
+			}
+			else if (k == M / 2) {
+				Xa = cconj(sm.zbuf[fpad(M / 2)]);
+				Xb = Xa;
+			}
+			else {
+				float2 A = sm.zbuf[fpad(k)];
+				float2 B = cconj(sm.zbuf[fpad(M - k)]);
+				float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
+				float2 O = cmul(tb.twr[k], csub(A, B));
+				float2 D = make_float2(0.5f * O.y, -0.5f * O.x);
+				Xa = cadd(E, D);
+				Xb = cconj(csub(E, D));
+			}
+			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
+			mag_row[ka] = ma;
+			sm.xbuf[ka] = Xa;
+			sm.erow[eoff + ka] = ma;
+			if (kb != ka) {
+				mag_row[kb] = mb;
+				sm.xbuf[kb] = Xb;
+				sm.erow[eoff + kb] = mb;
+			}
+		}
+	}
+	__syncthreads();
+	stamp(3);
+	// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]| (only the CTAs whose windows reach them)
+	if (pl == 0) {
+		for (int t = tid; t < P.midp; t += NT) {
+			sm.erow[eoff - 1 - t] = sm.erow[eoff + 1 + t];
+			sm.erow[eoff + M + 1 + t] = sm.erow[eoff + M - 1 - t];
+		}
+	}
+	// ---- F'. time median of the own bins (the H row goes into zbuf, free until the next hop)
+	float* hrow = reinterpret_cast<float*>(sm.zbuf);
+	const int nA = sp.a1 - sp.a0, nB = sp.b1 - sp.b0;
+	{
+		const int nt = P.n_taps;
+		auto tap = [&](int t, int k) -> float {
+			int off = sm.taps[t];
+			return off >= 0 ? st.mag_ring[off + k] : 0.0f;
+		};
+		for (int idx = tid; idx < nA + nB; idx += NT) {
+			const int k = idx < nA ? sp.a0 + idx : sp.b0 + (idx - nA);
+			float H;
+			switch (nt) {
+			case 0: H = 0.0f; break;
+			case 1: H = tap(0, k); break;
+			case 3: H = median_fixed<3>([&](int t) { return tap(t, k); }); break;
+			case 5: H = median_fixed<5>([&](int t) { return tap(t, k); }); break;
+			case 7: H = median_fixed<7>([&](int t) { return tap(t, k); }); break;
+			case 9: H = median_fixed<9>([&](int t) { return tap(t, k); }); break;
+			case 11: H = median_fixed<11>([&](int t) { return tap(t, k); }); break;
+			case 13: H = median_fixed<13>([&](int t) { return tap(t, k); }); break;
+			default: H = median_generic([&](int t) { return tap(t, k); }, nt); break;
+			}
+			hrow[k] = H;
+		}
+	}
+	__syncthreads();
+	stamp(4);
+	// ---- E'. hard-mask decisions of the own bins (decide_group), codes as in hpr_iteration (bit0|bit1 P, bit2|bit3 H)
+	{
+		unsigned* codes = reinterpret_cast<unsigned*>(sm.prow);
+		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
+		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
+		const int gA = (nA + US - 1) / US, gB = (nB + US - 1) / US;
+		for (int g = tid; g < gA + gB; g += NT) {
+			const bool inA = g < gA;
+			const int kg = inA ? sp.a0 + g * US : sp.b0 + (g - gA) * US;
+			const int kmax = (inA ? sp.a1 : sp.b1) - 1;
+			unsigned fp, fh;
+			decide_group<US>(sm.erow, hrow, kg, kmax, 0, P.Lp, P.rule_p, P.rule_h, want_p, want_h, fp, fh);
+#pragma unroll
+			for (int u = 0; u < US; ++u) {
+				const int k = kg + u;
+				if (k <= kmax) {
+					const unsigned p0 = (fp >> u) & 1u, h0 = (fh >> u) & 1u;
+					codes[k] = p0 * 3u | (h0 * 3u) << 2;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	stamp(5);
+	// ---- G (first half). masked spectrum of the own pairs, packed for the M-point inverse FFT, into the owners' buffers
+	{
+		const unsigned* codes = reinterpret_cast<const unsigned*>(sm.prow);
+		for (int k = sp.k0 + tid; k < sp.k1; k += NT) {
+			const int kb = M - k;
+			const unsigned ca = codes[k], cb = codes[kb];
+			const float mpa = 0.5f * (float)((ca & 1u) + ((ca >> 1) & 1u)), mha = 0.5f * (float)(((ca >> 2) & 1u) + ((ca >> 3) & 1u));
+			const float mpb = 0.5f * (float)((cb & 1u) + ((cb >> 1) & 1u)), mhb = 0.5f * (float)(((cb >> 2) & 1u) + ((cb >> 3) & 1u));
+			const float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];
+			const float2 twc = cconj(tb.twr[k]);
+#pragma unroll
+			for (int o = 0; o < 3; ++o) {
+				float2* zb = sp.recv[o];
+				if (!zb)
+					continue;
+				const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
+				const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
+				const float2 A = make_float2(Xa.x * ma, Xa.y * ma);   // hps.h:58-66
+				const float2 Yb = make_float2(Xb.x * mb, Xb.y * mb);
+				if (k == 0) {
+					zb[fpad(0)] = make_float2(A.x + Yb.x, A.x - Yb.x);
+				}
+				else if (k == M / 2) {
+					zb[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
+				}
+				else {
+					const float2 B = cconj(Yb);
+					const float2 E2 = cadd(A, B);
+					const float2 O2 = cmul(twc, csub(A, B));
+					zb[fpad(k)] = make_float2(E2.x - O2.y, E2.y + O2.x);
+					zb[fpad(kb)] = make_float2(E2.x + O2.y, O2.x - E2.y);
+				}
+			}
+		}
+	}
+}
+
+// G (second half), run by the CTA that owns output o after the cluster barrier: inverse FFT of the received masked
+// spectrum, overlap-add, emission.
+template <int NFFT, int NT>
+__device__ __forceinline__ void hpr_split_synth(const HprDev& P, float2* zb, float* tail, float* ea, float* eb, float* pbuf, uint4* pdst,
+                                                unsigned ptag, const HprTables& tb, unsigned long long* stamps)
+{
+	constexpr int M = NFFT / 2;
+	if (stamps && threadIdx.x == 0) stamps[6] = (unsigned long long)clock64();
+	fft_smem<M, NT, +1, 1, false, true, true>(zb, tb.tw, threadIdx.x);
+	if (stamps && threadIdx.x == 0) stamps[7] = (unsigned long long)clock64();
+	hpr_ola_emit<NFFT, NT>(P, zb, tail, false, ea, eb, pbuf, pdst, ptag);
+	if (stamps && threadIdx.x == 0) stamps[8] = (unsigned long long)clock64();
 }
 
 }  // namespace zen_b200

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <xmmintrin.h>
+#include <emmintrin.h>
 
 #include "hpr_launch.cuh"
 
@@ -246,6 +247,18 @@ struct zen_hpr {
 	unsigned rt_seq = 0;
 	bool rt_args_valid = false;  // the resident kernel holds the pointers of the previous call
 	unsigned long long rt_idle_ns = 250ull * 1000 * 1000;
+	// tagged staging buffers of the resident kernel (mapped pinned host memory, see RtCtrl)
+	uint4* rt_stage_in = nullptr;
+	uint4* rt_stage_in_dev = nullptr;
+	uint4* rt_stage_out[3] = {nullptr, nullptr, nullptr};
+	uint4* rt_stage_out_dev[3] = {nullptr, nullptr, nullptr};
+	int rt_groups = 0;               // ceil(hop / 3)
+	bool rt_push = true;             // ZEN_B200_RT_PUSH=0: the kernel pulls the hop / writes the outputs itself
+	const float* rt_in_host = nullptr;          // host alias of the current `in` pointer (null: device memory)
+	float* rt_out_host[3] = {nullptr, nullptr, nullptr};
+	bool rt_out_all_host = false;    // every non-null destination of the current call is host memory
+	bool rt_stamps = false;          // ZEN_B200_RT_STAMPS=1: the kernel records its phase boundaries (diagnostics)
+	int rt_cluster = 4;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop
 };
 
 namespace {
@@ -287,6 +300,18 @@ int rebuild_plan_fwd(zen_hpr* h);
 
 // ---- persistent real-time session -------------------------------------------
 
+// host alias of a device-visible pointer into mapped pinned host memory, or null for device memory
+void* rt_host_alias(const void* p)
+{
+	if (!p) return nullptr;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return at.type == cudaMemoryTypeHost ? at.hostPointer : nullptr;
+}
+
 int rt_launch(zen_hpr* h)
 {
 	if (!h->rt_ctrl) {
@@ -299,6 +324,36 @@ int rt_launch(zen_hpr* h)
 			long ms = std::atol(e);
 			if (ms > 0) h->rt_idle_ns = (unsigned long long)ms * 1000ull * 1000ull;
 		}
+		if (const char* e = std::getenv("ZEN_B200_RT_PUSH"))
+			h->rt_push = std::atoi(e) != 0;
+		if (const char* e = std::getenv("ZEN_B200_RT_STAMPS"))
+			h->rt_stamps = std::atoi(e) != 0;
+		if (const char* e = std::getenv("ZEN_B200_RT_CLUSTER")) {
+			const int c = std::atoi(e);
+			if (c == 1 || c == 2 || c == 4 || c == 8) h->rt_cluster = c;
+		}
+	}
+	const int groups = (h->hop + 2) / 3;
+	if (!h->rt_stage_in || h->rt_groups != groups) {
+		// one allocation: request / input groups, then the three output group arrays
+		if (h->rt_stage_in) cudaFreeHost(h->rt_stage_in);
+		h->rt_stage_in = nullptr;
+		const size_t per = ((size_t)groups * sizeof(uint4) + 127) & ~(size_t)127;
+		unsigned char* base = nullptr;
+		ZEN_CUDA_CHECK(cudaHostAlloc((void**)&base, 4 * per, cudaHostAllocMapped | cudaHostAllocPortable));
+		std::memset(base, 0, 4 * per);
+		unsigned char* base_dev = nullptr;
+		ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&base_dev, base, 0));
+		h->rt_stage_in = reinterpret_cast<uint4*>(base);
+		h->rt_stage_in_dev = reinterpret_cast<uint4*>(base_dev);
+		for (int o = 0; o < 3; ++o) {
+			h->rt_stage_out[o] = reinterpret_cast<uint4*>(base + (size_t)(o + 1) * per);
+			h->rt_stage_out_dev[o] = reinterpret_cast<uint4*>(base_dev + (size_t)(o + 1) * per);
+		}
+		h->rt_groups = groups;
+		// tags of the sequence number already served, so that a fresh kernel does not take stale groups for a request
+		for (int g = 0; g < groups; ++g)
+			h->rt_stage_in[g].w = h->rt_seq << 8;
 	}
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	int it = (int)h->iter;
@@ -306,6 +361,9 @@ int rt_launch(zen_hpr* h)
 	RtArgs a;
 	a.dev = h->plan.dev;
 	a.ctrl = h->rt_ctrl_dev;
+	a.stage_in = h->rt_stage_in_dev;
+	for (int o = 0; o < 3; ++o)
+		a.stage_out[o] = h->rt_stage_out_dev[o];
 	a.mag_ring = h->d_mag_ring;
 	a.input = h->d_input;
 	for (int o = 0; o < 3; ++o)
@@ -321,9 +379,18 @@ int rt_launch(zen_hpr* h)
 	_mm_sfence();
 	int rc = ZEN_ERR_UNSUPPORTED;
 	const size_t limit = 227 * 1024;
+	// The hop is split over a thread-block cluster (hpr_split_analyse) for the default real-time path: hard mask decided
+	// by counting, copy-border, one CTA per output at most, everything resident in shared memory.
+	const HprDev& d = a.dev;
+	int n_out = 0;
+	for (int o = 0; o < 3; ++o)
+		n_out += (d.out_flags >> o) & 1;
+	const bool can_split = h->rt_cluster > 1 && d.decide && !d.sse && !d.soft && d.copy_bord && d.lag == 1 && d.Lp >= 8
+	                       && n_out >= 1 && n_out <= h->rt_cluster && h->plan.nfft >= 256;
 #define ZEN_RT_CASE(N)                                                            \
 	case N:                                                                       \
-		a.state_in_smem = rt_smem_bytes<N>(a.dev, 1) <= limit ? 1 : 0;            \
+		a.cluster = (can_split && rt_smem_bytes<N>(a.dev, 3, h->rt_cluster) <= limit) ? h->rt_cluster : 1; \
+		a.state_in_smem = rt_smem_bytes<N>(a.dev, 3, a.cluster) <= limit ? 3 : (rt_smem_bytes<N>(a.dev, 1, 1) <= limit ? 1 : (rt_smem_bytes<N>(a.dev, 2, 1) <= limit ? 2 : 0)); \
 		rc = launch_rt_impl<N>(a);                                                \
 		break;
 	switch (h->plan.nfft) {
@@ -357,6 +424,55 @@ int rt_collect(zen_hpr* h)
 	return ZEN_OK;
 }
 
+// publish one request: tag every group of the staging buffer; with `src` the groups carry the hop
+void rt_publish(zen_hpr* h, unsigned tag, const float* src)
+{
+	uint4* st = h->rt_stage_in;
+	const int hop = h->hop, groups = h->rt_groups;
+	if (src) {
+		const __m128 tagv = _mm_castsi128_ps(_mm_set_epi32((int)tag, 0, 0, 0));
+		const __m128 keep = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
+		const int full = (hop - 1) / 3;  // groups whose 16-byte read stays inside the hop (3g + 3 < hop)
+		int g = 0;
+		for (; g < full; ++g)
+			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_loadu_ps(src + 3 * g), keep), tagv));
+		for (; g < groups; ++g) {
+			float x0 = src[3 * g], x1 = 3 * g + 1 < hop ? src[3 * g + 1] : 0.0f, x2 = 3 * g + 2 < hop ? src[3 * g + 2] : 0.0f;
+			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_set_ps(0.0f, x2, x1, x0), keep), tagv));
+		}
+	}
+	else {
+		for (int g = 0; g < groups; ++g)
+			*reinterpret_cast<volatile unsigned*>(&st[g].w) = tag;
+	}
+}
+
+// all groups of output o carry `tag`: unpack them into dst; false if some group is still old
+bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst)
+{
+	const uint4* st = h->rt_stage_out[o];
+	const int hop = h->hop, groups = h->rt_groups;
+	const int full = hop / 3;  // groups with three samples
+	for (int g = 0; g < full; ++g) {
+		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
+		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
+			return false;
+		// three floats; the fourth lane would spill into the next group's slot of dst, so store 8 + 4 bytes
+		_mm_storel_pi(reinterpret_cast<__m64*>(dst + 3 * g), _mm_castsi128_ps(v));
+		_mm_store_ss(dst + 3 * g + 2, _mm_movehl_ps(_mm_castsi128_ps(v), _mm_castsi128_ps(v)));
+	}
+	for (int g = full; g < groups; ++g) {
+		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
+		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
+			return false;
+		alignas(16) float t[4];
+		_mm_store_ps(t, _mm_castsi128_ps(v));
+		for (int j = 0; 3 * g + j < hop; ++j)
+			dst[3 * g + j] = t[j];
+	}
+	return true;
+}
+
 int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, float* o2, int which)
 {
 	if (h->plan_dirty) {
@@ -379,27 +495,78 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 		c->out[2] = o2;
 		c->which = which;
 		h->rt_args_valid = true;
+		// which of them can the host itself read / write?  (mapped pinned memory: IOGPU)
+		float* outs[3] = {o0, o1, o2};
+		h->rt_in_host = h->rt_push ? static_cast<const float*>(rt_host_alias(in)) : nullptr;
+		h->rt_out_all_host = h->rt_push;
+		for (int o = 0; o < 3; ++o) {
+			h->rt_out_host[o] = h->rt_push ? static_cast<float*>(rt_host_alias(outs[o])) : nullptr;
+			if (outs[o] && !h->rt_out_host[o]) h->rt_out_all_host = false;
+		}
 	}
-	c->op = op | (same ? 0u : (unsigned)RT_OP_NEW_ARGS);
-	_mm_sfence();  // the caller's samples sit in write-combined memory (IOGPU::host_in): drain them first
-	c->seq_in = target;
+	unsigned opw = op | (same ? 0u : (unsigned)RT_F_NEW_ARGS);
+	// outputs the kernel will emit for this call (hpr_iteration step G)
+	bool wait_out[3] = {false, false, false};
+	bool any_out = false;
+	const float* push_src = nullptr;
+	if (op == RT_OP_PROCESS) {
+		if (h->rt_stamps) opw |= RT_F_STAMPS;
+		if (h->rt_in_host) {
+			opw |= RT_F_PUSH_IN;
+			push_src = h->rt_in_host;
+		}
+		if (h->rt_out_all_host) {
+			const unsigned of = (unsigned)h->plan.dev.out_flags;
+			for (int o = 0; o < 3; ++o) {
+				const bool emitted = (of & (1u << o)) && !(o == 2 && (h->plan.dev.soft || h->plan.dev.sse));
+				wait_out[o] = h->rt_out_host[o] && emitted;
+				any_out = any_out || wait_out[o];
+			}
+			if (any_out) opw |= RT_F_TAG_OUT;
+		}
+	}
+	unsigned tag = (target << 8) | opw;
+	c->op = opw;
+	_mm_sfence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
+	rt_publish(h, tag, push_src);
+	if (any_out && (h->plan.dev.out_flags & ZEN_OUTPUT_RESIDUAL) && (h->plan.dev.soft || h->plan.dev.sse) && h->rt_out_host[2])
+		std::memset(h->rt_out_host[2], 0, sizeof(float) * (size_t)h->hop);  // the reference's rotate-and-zero (hps.cu:435-449)
 	const auto t0 = std::chrono::steady_clock::now();
 	unsigned spins = 0;
-	while (c->seq_out != target) {
+	// the kernel emits P, H, R in that order (hps.cu:498-579): watch the last group of the last output first
+	int last_o = -1;
+	if (any_out) last_o = wait_out[2] ? 2 : (wait_out[0] ? 0 : 1);
+	for (;;) {
+		if (any_out) {
+			if (*reinterpret_cast<volatile unsigned*>(&h->rt_stage_out[last_o][h->rt_groups - 1].w) == tag) {
+				bool ok = true;
+				for (int o = 0; o < 3 && ok; ++o)
+					if (wait_out[o]) ok = rt_unpack(h, o, tag, h->rt_out_host[o]);
+				if (ok) break;
+			}
+		}
+		else if (c->seq_out == target)
+			break;
 		if ((++spins & 1023u) == 0) {
 			if (!c->alive) {
-				if (c->seq_out == target)
+				if (c->seq_out == target && !any_out)
 					break;
-				// the kernel timed out between our check and the doorbell: bring it back, it will see the doorbell
-				int rc = rt_collect(h);
-				if (rc == ZEN_OK && op != RT_OP_STOP) {
-					c->op = op | (unsigned)RT_OP_NEW_ARGS;  // the new kernel has no cached pointers
-					_mm_sfence();
-					rc = rt_launch(h);
-					h->rt_args_valid = true;
+				if (c->seq_out != target) {
+					// the kernel left (idle time-out) before it saw the request: bring it back.  The new kernel has no
+					// cached pointers, so the request is published again with RT_F_NEW_ARGS (nobody reads the staging
+					// buffer between rt_collect and rt_launch).
+					int rc = rt_collect(h);
+					if (rc == ZEN_OK && op != RT_OP_STOP) {
+						opw |= (unsigned)RT_F_NEW_ARGS;
+						tag = (target << 8) | opw;
+						c->op = opw;
+						rt_publish(h, tag, push_src);
+						rc = rt_launch(h);
+						h->rt_args_valid = true;
+					}
+					if (rc != ZEN_OK) return rc;
+					if (op == RT_OP_STOP) break;
 				}
-				if (rc != ZEN_OK) return rc;
-				if (op == RT_OP_STOP) break;
 			}
 			if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
 				std::fprintf(stderr, "zen_b200: the resident real-time kernel did not answer within 5 s\n");
@@ -487,6 +654,7 @@ void zen_hpr_destroy(zen_hpr* h)
 		return;
 	rt_pause(h);
 	if (h->rt_ctrl) cudaFreeHost((void*)h->rt_ctrl);
+	if (h->rt_stage_in) cudaFreeHost((void*)h->rt_stage_in);
 	if (h->rt_stream) cudaStreamDestroy(h->rt_stream);
 	cudaFree(h->d_iter);
 	if (h->stream) cudaStreamSynchronize(h->stream);

@@ -3,6 +3,8 @@
 #pragma once
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "hpr_core.cuh"
 
 namespace zen_b200 {
@@ -51,33 +53,43 @@ struct HopArgs {
 };
 
 // Control block of the persistent real-time kernel, in mapped pinned host memory.
-// Host -> device: fill the arguments, then publish seq_in (the doorbell).
-// Device -> host: seq_out = the sequence number just completed.
+//
+// Host -> device.  A request is published by TAGGING the staging buffer `stage_in`: ceil(hop/3) groups of
+// 16 bytes {x[3g], x[3g+1], x[3g+2], tag}, tag = (sequence number << 8) | op bits.  The CTA's threads poll
+// their own groups, so with RT_F_PUSH_IN the doorbell and the samples arrive in the SAME PCIe round trip
+// (a doorbell word followed by a read of the hop costs two).  A group is written with one aligned 16-byte
+// store and read with one 16-byte load, so it is seen either old or complete.  Arguments that changed since
+// the previous request (RT_F_NEW_ARGS) are written to this block BEFORE the tags.
+// Device -> host.  With RT_F_TAG_OUT every emitted hop is written as tagged groups to stage_out[o] and the
+// host unpacks it as soon as all tags match; seq_out (behind a system-wide fence) completes everything else.
 struct RtCtrl {
-	volatile unsigned seq_in;
-	volatile unsigned op;          // RT_OP_*
-	const float* in;               // device-visible pointer to the incoming hop
-	float* out[3];                 // device-visible destinations of the emitted hop (H, P, R) or null
+	volatile unsigned seq_in;      // unused by the tagged protocol (kept for diagnostics)
+	volatile unsigned op;
+	const float* in;               // device-visible pointer to the incoming hop (when it is not pushed)
+	float* out[3];                 // device-visible destinations of the emitted hop (H, P, R) or null (when not tagged)
 	int which;                     // RT_OP_COPY: which output
 	unsigned pad0[16];
 	volatile unsigned seq_out;     // own cache line
 	volatile unsigned alive;       // 1 while the kernel is resident
 	volatile unsigned exit_reason; // 1 stop requested, 2 idle time-out
 	unsigned pad1[13];
-	unsigned long long stamps[16]; // globaltimer at the phase boundaries of the last hop (diagnostics)
+	unsigned long long stamps[16]; // RT_F_STAMPS: SM cycle counter at the phase boundaries of the last hop, [9]/[12] globaltimer
 };
-enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3, RT_OP_NEW_ARGS = 0x100 };
+enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3, RT_OP_MASK = 0x0f, RT_F_NEW_ARGS = 0x10, RT_F_PUSH_IN = 0x20, RT_F_TAG_OUT = 0x40, RT_F_STAMPS = 0x80 };
 
 struct RtArgs {
 	HprDev dev;
 	RtCtrl* ctrl;          // device alias of the control block
+	const uint4* stage_in; // device alias of the tagged request / input staging buffer
+	uint4* stage_out[3];   // device aliases of the tagged output staging buffers
 	float* mag_ring;       // global state, loaded at start and written back at exit
 	float* input;          // nwin
 	float* ola[3];         // nwin each
 	int* iter;             // frame counter, read at start, written back at exit
 	unsigned seq0;         // last sequence number already served
 	unsigned long long idle_ns;
-	int state_in_smem;     // ring + tails resident in shared memory
+	int state_in_smem;     // bit 0: ring + tails + previous hop resident in shared memory; bit 1: window / twiddle tables too
+	int cluster;           // CTAs of the thread-block cluster that serves the stream (1: a single CTA)
 	cudaStream_t stream;
 };
 
@@ -87,6 +99,12 @@ constexpr int nt_rt_for()
 	// measured on a B200 (tools/rt_phases.py): 512 threads are the sweet spot at nfft 4096 (1024 threads spill in
 	// the FFT stages); the large transforms want 1024, the small ones nfft/4
 	return NFFT == 4096 ? 512 : ((NFFT / 4) < 128 ? 128 : ((NFFT / 4) > 1024 ? 1024 : (NFFT / 4)));
+}
+// the cluster-split hop leaves little per-bin work to each CTA: one thread per radix-8 butterfly
+template <int NFFT>
+constexpr int nt_rt_split_for()
+{
+	return (NFFT / 16) < 128 ? 128 : ((NFFT / 16) > 512 ? 512 : (NFFT / 16));
 }
 template <int NFFT>
 constexpr int rt_u_for()
@@ -98,7 +116,7 @@ template <int NFFT> int launch_tile_impl(const TileArgs& a);
 template <int NFFT> int tile_resident_ctas(const HprDev& d);
 template <int NFFT> int launch_hop_impl(const HopArgs& a);
 template <int NFFT> int launch_rt_impl(const RtArgs& a);
-template <int NFFT> size_t rt_smem_bytes(const HprDev& d, int state_in_smem);
+template <int NFFT> size_t rt_smem_bytes(const HprDev& d, int smem_flags, int cluster);
 
 }  // namespace zen_b200
 
@@ -212,13 +230,13 @@ __global__ void __launch_bounds__(NT, 1) hpr_hop_kernel(const __grid_constant__ 
 
 
 // Persistent real-time kernel: one resident CTA serves one stream hop after hop.
-// The host writes the hop into mapped memory and rings a doorbell; the CTA polls
-// it, runs the fused step with ring / overlap-add tails / previous hop held in
-// SHARED memory, writes the outputs straight to mapped host memory and publishes
-// the completion flag.  No launch and no stream synchronisation per hop (those
-// alone cost ~9 us on this box).  The kernel leaves on RT_OP_STOP or after
-// idle_ns without a doorbell, writing its state back to global memory so the
-// per-launch kernels (or a later session) continue seamlessly.
+// The host tags the staging buffer (see RtCtrl); the CTA polls it, runs the fused
+// step with the |X| ring, the overlap-add tails, the previous hop AND the window /
+// twiddle tables held in SHARED memory, writes the outputs straight to mapped host
+// memory (tagged groups) and publishes the completion flag.  No launch and no
+// stream synchronisation per hop (those alone cost ~9 us on this box).  The kernel
+// leaves on RT_OP_STOP or after idle_ns without a request, writing its state back
+// to global memory so the per-launch kernels (or a later session) continue seamlessly.
 __device__ __forceinline__ unsigned long long rt_globaltimer()
 {
 	unsigned long long t;
@@ -226,149 +244,377 @@ __device__ __forceinline__ unsigned long long rt_globaltimer()
 	return t;
 }
 
-template <int NFFT, int NT>
-__global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ HprDev P, RtCtrl* ctrl, float* g_ring, float* g_input,
-                                                       float* g_ola_h, float* g_ola_p, float* g_ola_r, int* g_iter, unsigned seq0,
-                                                       unsigned long long idle_ns, int state_in_smem)
+template <int NFFT>
+constexpr int rt_table_floats()
 {
+	// window (nwin) + per-stage twiddles + split twiddles, as floats
+	return NFFT / 2 + 2 * fft_twiddle_count<NFFT / 2>() + 2 * (NFFT / 4 + 1);
+}
+// bins decided per thread in the cluster-split hop: a quarter of the half spectrum over NT threads
+template <int NFFT, int NT>
+constexpr int rt_us_for()
+{
+	return (NFFT / 8 + 1 + NT - 1) / NT;
+}
+
+// Everything the resident kernel needs from one hop to the next lives in SHARED memory, not in registers or local
+// memory: the completion flag's system-wide fence invalidates L1 (CCTL.IVALL), so a spilled pointer or a dynamically
+// indexed local array costs an L2 round trip at every use in the next hop.
+template <int NFFT>
+struct RtShared {
+	HprState st;
+	HprTables tb;
+	HprEmit em;           // per request
+	HprPack pk;           // per request
+	HprSplit sp;
+	float* hopbuf[2];
+	unsigned zrecv_off;   // cluster mode: byte offset (in the dynamic shared memory) of the receive buffer of the masked spectrum
+	const float* in;      // cached request arguments
+	float* out[3];
+	int which;
+	unsigned op;
+	unsigned timeout[2];
+	unsigned verdict;
+	unsigned go;                  // cluster mode: request number released by the leader CTA (written through DSMEM)
+	unsigned exit_flag;           // cluster mode: the leader leaves (idle time-out)
+	unsigned long long stamps[16];
+};
+
+// SPLIT: the kernel runs as a thread-block cluster and serves every hop with hpr_split_analyse / hpr_split_synth
+// (only that path is compiled in: the two variants stay small enough to keep their state in registers).
+template <int NFFT, int NT, bool SPLIT>
+__global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ HprDev P, RtCtrl* ctrl, const uint4* stage_in,
+                                                       uint4* stage_out_h, uint4* stage_out_p, uint4* stage_out_r, float* g_ring,
+                                                       float* g_input, float* g_ola_h, float* g_ola_p, float* g_ola_r, int* g_iter,
+                                                       unsigned seq0, unsigned long long idle_ns, int smem_flags)
+{
+	namespace cg = cooperative_groups;
 	constexpr int M = NFFT / 2, HOP = M / 2;
+	constexpr int NG = (HOP + 2) / 3;        // tagged groups per hop
+	constexpr int PER = (NG + NT - 1) / NT;  // groups polled by one thread
+	constexpr int US = rt_us_for<NFFT, NT>();
+	(void)US;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	__shared__ RtShared<NFFT> S;
+	// the working buffers are addressed off smem_raw directly (the compiler then knows they are shared memory:
+	// 32-bit addresses, LDS/STS), everything else through S
 	HprSmem<NFFT> sm;
 	sm.carve(smem_raw, P.Lp);
-	float* extra = reinterpret_cast<float*>(smem_raw + ((HprSmem<NFFT>::bytes(P.Lp) + 15) & ~(size_t)15));
-	// double buffer: previous hop / incoming hop (in global memory, i.e. the `input` vector itself, when smem is short)
-	float* hopbuf[2] = {state_in_smem ? extra : g_input, state_in_smem ? extra + HOP : g_input + HOP};
-	if (state_in_smem) extra += 2 * HOP;
 	const int tid = threadIdx.x;
+	// the cluster spans the whole grid: CTA rank == blockIdx.x.  C == 1 is an ordinary launch.
+	const int rank = SPLIT ? blockIdx.x : 0, C = SPLIT ? gridDim.x : 1;
+	const bool leader = rank == 0;
+	const int state_in_smem = smem_flags & 1;
 	const int ring_n = P.W * (M + 1);
-	float* g_ola[3] = {g_ola_h, g_ola_p, g_ola_r};
-	HprState st;
-	st.x_ring = nullptr;
-	st.xdepth = 0;
-	if (state_in_smem) {
-		st.mag_ring = extra;
-		extra += (ring_n + 3) & ~3;
-		for (int o = 0; o < 3; ++o)
-			st.tail[o] = extra + o * HOP;
-		for (int n = tid; n < ring_n; n += NT)
-			st.mag_ring[n] = g_ring[n];
-		for (int o = 0; o < 3; ++o)
-			for (int n = tid; n < HOP; n += NT)
-				st.tail[o][n] = g_ola[o][HOP + n];
-	}
-	else {
-		st.mag_ring = g_ring;
-		for (int o = 0; o < 3; ++o)
-			st.tail[o] = g_ola[o] + HOP;
-	}
-	if (state_in_smem) {
-		for (int n = tid; n < HOP; n += NT) {
-			hopbuf[0][n] = g_input[n];          // older hop (only kept so `input` can be written back)
-			hopbuf[1][n] = g_input[HOP + n];    // the previous hop
+
+	if (tid == 0) {
+		float* extra = reinterpret_cast<float*>(smem_raw + ((HprSmem<NFFT>::bytes(P.Lp) + 15) & ~(size_t)15));
+		S.pk.buf = extra;  // HOP floats: the emitted hop before it is packed into tagged groups
+		extra += HOP;
+		// double buffer: previous hop / incoming hop (in global memory, i.e. the `input` vector itself, when smem is short)
+		S.hopbuf[0] = state_in_smem ? extra : g_input;
+		S.hopbuf[1] = state_in_smem ? extra + HOP : g_input + HOP;
+		if (state_in_smem) {
+			extra += 2 * HOP;
+			S.st.mag_ring = extra;
+			extra += (ring_n + 3) & ~3;
+			for (int o = 0; o < 3; ++o)
+				S.st.tail[o] = extra + o * HOP;
+			extra += 3 * HOP;
 		}
+		else {
+			S.st.mag_ring = g_ring;
+			S.st.tail[0] = g_ola_h + HOP;
+			S.st.tail[1] = g_ola_p + HOP;
+			S.st.tail[2] = g_ola_r + HOP;
+		}
+		S.st.x_ring = nullptr;
+		S.st.xdepth = 0;
+		S.tb.window = P.window;
+		S.tb.tw = P.tw;
+		S.tb.twr = P.twr;
+		if (smem_flags & 2) {
+			constexpr int NTW = fft_twiddle_count<M>();
+			float* w_s = extra;
+			float2* tw_s = reinterpret_cast<float2*>(w_s + M);
+			S.tb.window = w_s;
+			S.tb.tw = tw_s;
+			S.tb.twr = tw_s + NTW;
+			extra += rt_table_floats<NFFT>();
+		}
+		S.zrecv_off = (unsigned)(reinterpret_cast<unsigned char*>(extra) - smem_raw);  // only carved (and only used) in cluster mode
+		// cluster split: own pairs / bins, owners of the outputs in emission order P, H, R
+		S.sp.rank = rank;
+		S.sp.C = C;
+		hpr_split_ranges(M, rank, C, S.sp.k0, S.sp.k1, S.sp.a0, S.sp.a1, S.sp.b0, S.sp.b1);
+		int n_on = 0;
+		for (int oi = 0; oi < 3; ++oi) {
+			const int o = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
+			const bool on = (P.out_flags & (1 << o)) != 0 && !(o == 2 && (P.soft || P.sse));
+			S.sp.owner[o] = on ? (n_on++ % C) : -1;
+			S.sp.recv[o] = nullptr;
+			if (SPLIT && on) S.sp.recv[o] = cg::this_cluster().map_shared_rank(reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.sp.owner[o]);
+		}
+		S.in = nullptr;
+		S.out[0] = S.out[1] = S.out[2] = nullptr;
+		S.which = 0;
+		S.timeout[0] = S.timeout[1] = 0u;
+		S.go = seq0;
+		S.exit_flag = 0u;
+	}
+	__syncthreads();
+	if (state_in_smem) {
+		float* ring = S.st.mag_ring;
+		for (int n = tid; n < ring_n; n += NT)
+			ring[n] = g_ring[n];
+		for (int n = tid; n < HOP; n += NT) {
+			S.st.tail[0][n] = g_ola_h[HOP + n];
+			S.st.tail[1][n] = g_ola_p[HOP + n];
+			S.st.tail[2][n] = g_ola_r[HOP + n];
+			S.hopbuf[0][n] = g_input[n];          // older hop (only kept so `input` can be written back)
+			S.hopbuf[1][n] = g_input[HOP + n];    // the previous hop
+		}
+	}
+	if (smem_flags & 2) {
+		// tables: every load of the per-hop path then has shared-memory latency
+		constexpr int NTW = fft_twiddle_count<M>();
+		float* w_s = const_cast<float*>(S.tb.window);
+		float2* tw_s = const_cast<float2*>(S.tb.tw);
+		float2* twr_s = const_cast<float2*>(S.tb.twr);
+		for (int n = tid; n < M; n += NT)
+			w_s[n] = P.window[n];
+		for (int n = tid; n < NTW; n += NT)
+			tw_s[n] = P.tw[n];
+		for (int n = tid; n <= M / 2; n += NT)
+			twr_s[n] = P.twr[n];
 	}
 	int prev_idx = 1;
 	int iter = *g_iter;
 	unsigned seq = seq0;
-	__shared__ unsigned s_op, s_seq;
-	__shared__ unsigned long long s_stamps[16];
-	__shared__ const float* s_in;
-	__shared__ float* s_out[3];
-	__shared__ int s_which;
+	unsigned exit_reason = 0;
 	__syncthreads();
+	if (SPLIT) cg::this_cluster().sync();  // every CTA's flags are initialised before the leader may write them
 
 	for (;;) {
-		if (tid == 0) {
-			const unsigned long long t0 = rt_globaltimer();
-			unsigned now = seq, opw = 0;
-			unsigned spins = 0;
-			for (;;) {
-				// doorbell and op code share one 8-byte word: one PCIe read per poll
-				asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(now), "=r"(opw) : "l"(&ctrl->seq_in) : "memory");
-				if (now != seq)
-					break;
-				if ((++spins & 63u) == 0 && rt_globaltimer() - t0 > idle_ns)
-					break;
-			}
-			if (now == seq) {
-				s_op = 0xffffffffu;  // idle time-out
-			}
-			else {
-				if (opw & RT_OP_NEW_ARGS) {
-					// pointers changed since the last hop: fetch them (one more round trip), else reuse the cached ones
-					__threadfence_system();
-					s_in = ctrl->in;
-					s_out[0] = ctrl->out[0];
-					s_out[1] = ctrl->out[1];
-					s_out[2] = ctrl->out[2];
-					s_which = ctrl->which;
+		// ---- wait for the next request: every thread polls its own tagged group(s)
+		const unsigned want = (seq + 1u) << 8;
+		uint4 v[PER];
+		unsigned pending = 0u;
+#pragma unroll
+		for (int b = 0; b < PER; ++b) {
+			v[b] = make_uint4(0u, 0u, 0u, ~want);
+			if (tid + b * NT < NG) pending |= 1u << b;
+		}
+		bool got = pending == 0u;
+		unsigned round = 0;
+		bool all = false;
+		unsigned long long t0 = 0;
+		if (tid == 0 && leader) t0 = rt_globaltimer();
+		for (;;) {
+#pragma unroll
+			for (int b = 0; b < PER; ++b) {
+				if (pending & (1u << b)) {
+					asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+					             : "=r"(v[b].x), "=r"(v[b].y), "=r"(v[b].z), "=r"(v[b].w)
+					             : "l"(stage_in + tid + b * NT)
+					             : "memory");
+					if ((v[b].w ^ want) <= 0xffu) pending &= ~(1u << b);
 				}
-				s_op = opw & 0xffu;
 			}
-			s_seq = now;
+			got = pending == 0u;
+			if (tid == 0) {
+				// the leader decides the idle time-out; the other CTAs of a cluster leave when it tells them to
+				unsigned to = 0u;
+				if (!got) to = leader ? (((round & 63u) == 63u && rt_globaltimer() - t0 > idle_ns) ? 1u : 0u) : *reinterpret_cast<volatile unsigned*>(&S.exit_flag);
+				S.timeout[round & 1u] = to;
+			}
+			const int n_got = __syncthreads_count(got);
+			if (n_got == NT) {
+				all = true;
+				break;
+			}
+			if (S.timeout[round & 1u])
+				break;
+			++round;
+		}
+		if (!all) {  // (uniform: the count and the flag are the same for every thread)
+			exit_reason = 2u;
+			if (SPLIT && leader && tid > 0 && tid < C) *reinterpret_cast<volatile unsigned*>(cg::this_cluster().map_shared_rank(&S.exit_flag, tid)) = 1u;
+			break;
+		}
+		++seq;
+		if (SPLIT && leader && tid > 0 && tid < C) *reinterpret_cast<volatile unsigned*>(cg::this_cluster().map_shared_rank(&S.go, tid)) = seq;  // release request `seq`
+		if (tid == 0) {
+			const unsigned opw = v[0].w & 0xffu;
+			if (opw & RT_F_NEW_ARGS) {
+				// pointers changed since the last request: fetch them (one more round trip), else reuse the cached ones
+				S.in = *reinterpret_cast<const float* volatile*>(&ctrl->in);
+				S.out[0] = *reinterpret_cast<float* volatile*>(&ctrl->out[0]);
+				S.out[1] = *reinterpret_cast<float* volatile*>(&ctrl->out[1]);
+				S.out[2] = *reinterpret_cast<float* volatile*>(&ctrl->out[2]);
+				S.which = *reinterpret_cast<volatile int*>(&ctrl->which);
+			}
+			S.op = opw;
+			if (opw & RT_F_STAMPS) {
+				S.stamps[9] = rt_globaltimer();
+				S.stamps[10] = (unsigned long long)clock64();
+			}
+			const bool tagged = (opw & RT_F_TAG_OUT) != 0;
+			S.pk.tag = (seq << 8) | opw;
+			S.em.a[0] = (P.out_flags & 1) ? g_ola_h : nullptr;   // keep the public *_out vectors current (hps.h:195-197)
+			S.em.a[1] = (P.out_flags & 2) ? g_ola_p : nullptr;
+			S.em.a[2] = (P.out_flags & 4) ? g_ola_r : nullptr;
+			S.em.b[0] = ((P.out_flags & 1) && !tagged) ? S.out[0] : nullptr;
+			S.em.b[1] = ((P.out_flags & 2) && !tagged) ? S.out[1] : nullptr;
+			S.em.b[2] = ((P.out_flags & 4) && !tagged) ? S.out[2] : nullptr;
+			S.pk.dst[0] = ((P.out_flags & 1) && tagged) ? stage_out_h : nullptr;
+			S.pk.dst[1] = ((P.out_flags & 2) && tagged) ? stage_out_p : nullptr;
+			S.pk.dst[2] = ((P.out_flags & 4) && tagged) ? stage_out_r : nullptr;
+		}
+		{
+			float* stash = S.hopbuf[prev_idx ^ 1];
+#pragma unroll
+			for (int b = 0; b < PER; ++b) {
+				const int g = tid + b * NT;
+				if (g < NG && (v[b].w & RT_F_PUSH_IN) && (v[b].w & RT_OP_MASK) == RT_OP_PROCESS) {
+					stash[3 * g] = __uint_as_float(v[b].x);
+					if (3 * g + 1 < HOP) stash[3 * g + 1] = __uint_as_float(v[b].y);
+					if (3 * g + 2 < HOP) stash[3 * g + 2] = __uint_as_float(v[b].z);
+				}
+			}
 		}
 		__syncthreads();
-		const unsigned op = s_op;
-		if (op == 0xffffffffu || op == RT_OP_STOP) {
-			if (tid == 0) ctrl->exit_reason = (op == RT_OP_STOP) ? 1u : 2u;
-			if (op == RT_OP_STOP) seq = s_seq;
+		const unsigned opw = S.op;
+		const unsigned op = opw & RT_OP_MASK;
+		if (SPLIT && !leader && op != RT_OP_PROCESS) {
+			// not speculated on: wait until the leader has released this request (or leaves)
+			if (tid == 0) {
+				volatile unsigned* go = &S.go;
+				volatile unsigned* ex = &S.exit_flag;
+				while (*go != seq && !*ex) {
+				}
+				S.verdict = (*go == seq) ? 1u : 0u;
+			}
+			__syncthreads();
+			if (!S.verdict) {
+				exit_reason = 2u;
+				break;
+			}
+		}
+		if (op == RT_OP_STOP) {
+			exit_reason = 1u;
 			break;
 		}
 		if (op == RT_OP_PROCESS) {
-			HprEmit em;
-			for (int o = 0; o < 3; ++o) {
-				const bool on = (P.out_flags & (1 << o)) != 0;
-				em.a[o] = on ? g_ola[o] : nullptr;   // keep the public *_out vectors current (hps.h:195-197)
-				em.b[o] = on ? s_out[o] : nullptr;
+			const bool pushed = (opw & RT_F_PUSH_IN) != 0;
+			unsigned long long* stamps = (opw & RT_F_STAMPS) ? S.stamps : nullptr;
+			if constexpr (!SPLIT) {
+				hpr_iteration<NFFT, NT, rt_u_for<NFFT>(), true>(P, sm, S.st, iter, S.hopbuf[prev_idx],
+				                                                pushed ? S.hopbuf[prev_idx ^ 1] : S.in, true, false, S.em,
+				                                                pushed ? nullptr : S.hopbuf[prev_idx ^ 1], stamps, nullptr, &S.tb, &S.pk);
+				if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && !(opw & RT_F_TAG_OUT) && S.out[2])
+					for (int n = tid; n < HOP; n += NT)
+						S.out[2][n] = 0.0f;
 			}
-			float* stash = hopbuf[prev_idx ^ 1];
-			if (tid == 0) {
-				s_stamps[9] = rt_globaltimer();
-				s_stamps[10] = (unsigned long long)clock64();
+			else {
+				if (!pushed) {  // pulled hop: every CTA fetches it into its own stash first
+					const float* src = S.in;
+					float* stash = S.hopbuf[prev_idx ^ 1];
+					for (int n = tid; n < HOP; n += NT)
+						stash[n] = src[n];
+					__syncthreads();
+				}
+				// speculative: nothing below is irreversible before the leader's release (the ring slot written here is
+				// rewritten with the same values when the request is served again after a time-out race)
+				hpr_split_analyse<NFFT, NT, US>(P, sm, S.st, iter, S.hopbuf[prev_idx], S.hopbuf[prev_idx ^ 1], S.tb, S.sp,
+				                                leader ? stamps : nullptr);
+				if (!leader) {
+					if (tid == 0) {
+						volatile unsigned* go = &S.go;
+						volatile unsigned* ex = &S.exit_flag;
+						while (*go != seq && !*ex) {
+						}
+						S.verdict = (*go == seq) ? 1u : 0u;
+					}
+					__syncthreads();
+					if (!S.verdict) {
+						exit_reason = 2u;
+						break;
+					}
+				}
+				cg::this_cluster().sync();  // the masked spectra have arrived at their owners
+				if (S.sp.owner[1] == rank)
+					hpr_split_synth<NFFT, NT>(P, reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.st.tail[1], S.em.a[1], S.em.b[1], S.pk.buf, S.pk.dst[1], S.pk.tag, S.tb,
+					                          leader ? stamps : nullptr);
+				if (S.sp.owner[0] == rank)
+					hpr_split_synth<NFFT, NT>(P, reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.st.tail[0], S.em.a[0], S.em.b[0], S.pk.buf, S.pk.dst[0], S.pk.tag, S.tb, nullptr);
+				if (S.sp.owner[2] == rank)
+					hpr_split_synth<NFFT, NT>(P, reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.st.tail[2], S.em.a[2], S.em.b[2], S.pk.buf, S.pk.dst[2], S.pk.tag, S.tb, nullptr);
 			}
-			hpr_iteration<NFFT, NT, rt_u_for<NFFT>()>(P, sm, st, iter, hopbuf[prev_idx], s_in, true, false, em, stash, s_stamps);
-			if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && s_out[2])
-				for (int n = tid; n < HOP; n += NT)
-					s_out[2][n] = 0.0f;
 			prev_idx ^= 1;
 			++iter;
-			if (tid == 0) s_stamps[11] = (unsigned long long)clock64();
+			if (tid == 0 && leader && stamps) {
+				S.stamps[11] = (unsigned long long)clock64();
+				S.stamps[12] = rt_globaltimer();
+			}
 		}
-		else if (op == RT_OP_COPY) {
-			const float* src = g_ola[s_which];
-			float* dst = s_out[0];
+		else if (op == RT_OP_COPY && leader) {
+			const float* src = S.which == 0 ? g_ola_h : (S.which == 1 ? g_ola_p : g_ola_r);
+			float* dst = S.out[0];
 			for (int n = tid; n < HOP; n += NT)
-				dst[n] = src[n];
+				dst[n] = __ldcg(src + n);  // written by another CTA in cluster mode: not through this SM's L1
 		}
-		__syncthreads();
-		seq = s_seq;
-		if (tid == 0) {
-			__threadfence_system();
-			ctrl->seq_out = seq;
+		if (SPLIT)
+			cg::this_cluster().sync();  // every CTA is done with this request (and with the receive buffers)
+		else
+			__syncthreads();
+		if (leader) {
+			// Completion flag, needed only when the host is not already watching the tagged output groups.  A release
+			// store: the fence in front of it orders the plain output stores, and - unlike __threadfence_system() -
+			// no L1 invalidation follows it.
+			if (tid == 0 && !(op == RT_OP_PROCESS && (opw & RT_F_TAG_OUT)))
+				asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&ctrl->seq_out), "r"(seq) : "memory");
+			if (tid < 16 && op == RT_OP_PROCESS && (opw & RT_F_STAMPS))
+				ctrl->stamps[tid] = S.stamps[tid];  // diagnostics
 		}
-		if (tid < 16 && op == RT_OP_PROCESS)
-			ctrl->stamps[tid] = s_stamps[tid];  // diagnostics, after the completion flag
 	}
 
-	// write the state back
+	// ---- leave: write the state back (each CTA the part it owns)
+	__syncthreads();
 	if (state_in_smem) {
-		for (int n = tid; n < ring_n; n += NT)
-			g_ring[n] = st.mag_ring[n];
-		for (int o = 0; o < 3; ++o)
-			for (int n = tid; n < HOP; n += NT)
-				g_ola[o][HOP + n] = st.tail[o][n];
-	}
-	if (state_in_smem || prev_idx == 0) {
-		// `input` must read [older hop | newest hop]; when it served as the double buffer itself, swap the halves if needed
+		const float* ring = S.st.mag_ring;
+		const int a0 = S.sp.a0, nA = S.sp.a1 - S.sp.a0, b0 = S.sp.b0, nB = S.sp.b1 - S.sp.b0;
+		for (int r = 0; r < P.W; ++r)
+			for (int idx = tid; idx < nA + nB; idx += NT) {
+				const int k = idx < nA ? a0 + idx : b0 + (idx - nA);
+				g_ring[(size_t)r * (M + 1) + k] = ring[(size_t)r * (M + 1) + k];
+			}
+		// overlap-add tails: the owner of an output; the tails of disabled outputs pass through the leader unchanged
+		const bool w0 = S.sp.owner[0] == rank || (S.sp.owner[0] < 0 && leader);
+		const bool w1 = S.sp.owner[1] == rank || (S.sp.owner[1] < 0 && leader);
+		const bool w2 = S.sp.owner[2] == rank || (S.sp.owner[2] < 0 && leader);
 		for (int n = tid; n < HOP; n += NT) {
-			float older = hopbuf[prev_idx ^ 1][n], newest = hopbuf[prev_idx][n];
+			if (w0) g_ola_h[HOP + n] = S.st.tail[0][n];
+			if (w1) g_ola_p[HOP + n] = S.st.tail[1][n];
+			if (w2) g_ola_r[HOP + n] = S.st.tail[2][n];
+		}
+	}
+	if (leader && (state_in_smem || prev_idx == 0)) {
+		// `input` must read [older hop | newest hop]; when it served as the double buffer itself, swap the halves if needed
+		const float* ho = S.hopbuf[prev_idx ^ 1];
+		const float* hn = S.hopbuf[prev_idx];
+		for (int n = tid; n < HOP; n += NT) {
+			float older = ho[n], newest = hn[n];
 			g_input[n] = older;
 			g_input[HOP + n] = newest;
 		}
 	}
-	if (tid == 0) *g_iter = iter;
+	if (leader && tid == 0) *g_iter = iter;
 	__syncthreads();
-	if (tid == 0) {
+	if (SPLIT) cg::this_cluster().sync();  // nobody touches another CTA's shared memory after this point
+	if (leader && tid == 0) {
+		// (a request the leader never released - time-out race - is not counted: the host publishes it again)
+		ctrl->exit_reason = exit_reason;
 		__threadfence_system();
 		ctrl->seq_out = seq;
 		ctrl->alive = 0u;
@@ -431,33 +677,56 @@ int launch_hop_impl(const HopArgs& a)
 }
 
 template <int NFFT>
-size_t rt_smem_bytes(const HprDev& d, int state_in_smem)
+size_t rt_smem_bytes(const HprDev& d, int smem_flags, int cluster)
 {
 	constexpr int M = NFFT / 2, HOP = M / 2;
 	size_t b = (HprSmem<NFFT>::bytes(d.Lp) + 15) & ~(size_t)15;
-	if (state_in_smem)
+	b += sizeof(float) * (size_t)HOP;  // packbuf
+	if (smem_flags & 1)
 		b += sizeof(float) * (2 * (size_t)HOP + (((size_t)d.W * (M + 1) + 3) & ~(size_t)3) + 3 * (size_t)HOP);
+	if (smem_flags & 2)
+		b += sizeof(float) * (size_t)rt_table_floats<NFFT>();
+	if (cluster > 1)
+		b += sizeof(float2) * (size_t)fpad_size(M);  // receive buffer of the masked spectrum
 	return b;
+}
+
+template <int NFFT, int NT, bool SPLIT>
+int launch_rt_variant(const RtArgs& a)
+{
+	auto kern = hpr_rt_kernel<NFFT, NT, SPLIT>;
+	size_t smem = rt_smem_bytes<NFFT>(a.dev, a.state_in_smem, a.cluster);
+	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)a.cluster);
+	cfg.blockDim = dim3(NT);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = a.stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned)a.cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = SPLIT ? 1 : 0;
+	ZEN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.dev, a.ctrl, a.stage_in, a.stage_out[0], a.stage_out[1], a.stage_out[2], a.mag_ring,
+	                                  a.input, a.ola[0], a.ola[1], a.ola[2], a.iter, a.seq0, a.idle_ns, a.state_in_smem));
+	return ZEN_OK;
 }
 
 template <int NFFT>
 int launch_rt_impl(const RtArgs& a)
 {
-	constexpr int NT = nt_rt_for<NFFT>();
-	auto kern = hpr_rt_kernel<NFFT, NT>;
-	size_t smem = rt_smem_bytes<NFFT>(a.dev, a.state_in_smem);
-	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	kern<<<1, NT, smem, a.stream>>>(a.dev, a.ctrl, a.mag_ring, a.input, a.ola[0], a.ola[1], a.ola[2], a.iter, a.seq0, a.idle_ns,
-	                                a.state_in_smem);
-	ZEN_CUDA_CHECK(cudaGetLastError());
-	return ZEN_OK;
+	if (a.cluster > 1)
+		return launch_rt_variant<NFFT, nt_rt_split_for<NFFT>(), true>(a);
+	return launch_rt_variant<NFFT, nt_rt_for<NFFT>(), false>(a);
 }
 
 template int launch_tile_impl<ZEN_HPR_INSTANTIATE>(const TileArgs&);
 template int tile_resident_ctas<ZEN_HPR_INSTANTIATE>(const HprDev&);
 template int launch_hop_impl<ZEN_HPR_INSTANTIATE>(const HopArgs&);
 template int launch_rt_impl<ZEN_HPR_INSTANTIATE>(const RtArgs&);
-template size_t rt_smem_bytes<ZEN_HPR_INSTANTIATE>(const HprDev&, int);
+template size_t rt_smem_bytes<ZEN_HPR_INSTANTIATE>(const HprDev&, int, int);
 
 }  // namespace zen_b200
 #endif
