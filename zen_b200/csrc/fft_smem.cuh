@@ -201,4 +201,78 @@ __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__
 	}
 }
 
+// ---- out-of-place (ping-pong) variant --------------------------------------
+// Each stage reads src and writes dst, so one barrier per stage suffices (the in-place stage needs one between its
+// loads and its stores as well).  Used where latency, not shared-memory footprint, matters: the resident real-time
+// kernel.  fft_smem_pp returns the buffer that holds the result (a after an even number of stages, else b).
+template <int M, int NS = 1>
+constexpr int fft_stage_count()
+{
+	if constexpr (NS >= M) {
+		return 0;
+	}
+	else {
+		constexpr int rem = M / NS;
+		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		return 1 + fft_stage_count<M, NS * R>();
+	}
+}
+
+template <int M, int NT, int S, int R, int NS, bool ZIN = false, bool HOUT = false, bool GT = false>
+__device__ __forceinline__ void fft_stage_pp(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw, int tid)
+{
+	constexpr int NB = M / R;
+	constexpr int PER = (NB + NT - 1) / NT;
+#pragma unroll
+	for (int b = 0; b < PER; ++b) {
+		int j = tid + b * NT;
+		if ((NB % NT == 0) || j < NB) {
+			float2 v[R];
+			int k = j & (NS - 1);
+			float2 w[R];
+			if constexpr (NS > 1) {
+#pragma unroll
+				for (int r = 1; r < R; ++r)
+					w[r] = GT ? tw[(r - 1) * NS + k] : __ldg(&tw[(r - 1) * NS + k]);
+			}
+#pragma unroll
+			for (int r = 0; r < R; ++r) {
+				if (ZIN && r >= R / 2)
+					v[r] = make_float2(0.0f, 0.0f);
+				else
+					v[r] = src[fpad(j + r * NB)];
+			}
+			if constexpr (NS > 1) {
+#pragma unroll
+				for (int r = 1; r < R; ++r) {
+					if (S > 0)
+						w[r].y = -w[r].y;
+					v[r] = cmul(v[r], w[r]);
+				}
+			}
+			dftR<S, R>(v);
+			int j0 = (j - k) * R + k;
+#pragma unroll
+			for (int r = 0; r < R; ++r)
+				if (!(HOUT && r >= R / 2))
+					dst[fpad(j0 + r * NS)] = v[r];
+		}
+	}
+	__syncthreads();
+}
+
+template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
+__device__ __forceinline__ float2* fft_smem_pp(float2* a, float2* b, const float2* __restrict__ tw, int tid)
+{
+	if constexpr (NS < M) {
+		constexpr int rem = M / NS;
+		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		fft_stage_pp<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M), GT>(a, b, tw, tid);
+		return fft_smem_pp<M, NT, S, NS * R, ZIN, HOUT, GT>(b, a, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
+	}
+	else {
+		return a;
+	}
+}
+
 }  // namespace zen_b200

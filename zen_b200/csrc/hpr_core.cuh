@@ -716,8 +716,8 @@ __host__ __device__ inline void hpr_split_ranges(int M, int rank, int C, int& k0
 
 template <int NFFT, int NT, int US>
 __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>& sm, const HprState& st, const int i,
-                                                  const float* __restrict__ prev, const float* __restrict__ cur, const HprTables& tb,
-                                                  const HprSplit& sp, unsigned long long* stamps)
+                                                  const float* __restrict__ prev, const float* __restrict__ cur, float* cur_stash,
+                                                  const HprTables& tb, const HprSplit& sp, float2* zpp, int recv_off, unsigned long long* stamps)
 {
 	auto stamp = [&](int idx) {
 		if (stamps && threadIdx.x == 0)
@@ -733,16 +733,26 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 		int j = i - P.tap_age[t];
 		sm.taps[t] = j >= 0 ? (j % W) * (M + 1) : -1;
 	}
-	// ---- A. window (prev and cur are in shared memory)
+	// ---- A. window (prev is in this CTA's shared memory, cur in this or in the leader CTA's).  The forward FFT
+	// ping-pongs between zbuf and zpp; it starts in the one that makes it END in zbuf.
+	float2* const za = (fft_stage_count<M>() % 2 == 0) ? sm.zbuf : zpp;
+	float2* const zb2 = (fft_stage_count<M>() % 2 == 0) ? zpp : sm.zbuf;
+#pragma unroll 4
 	for (int n = tid; n < HOP; n += NT) {
-		float2 x = n < HOP / 2 ? reinterpret_cast<const float2*>(prev)[n] : reinterpret_cast<const float2*>(cur)[n - HOP / 2];
+		float2 x;
+		if (n < HOP / 2)
+			x = reinterpret_cast<const float2*>(prev)[n];
+		else {
+			x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
+			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
+		}
 		float2 w = reinterpret_cast<const float2*>(tb.window)[n];
-		sm.zbuf[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
+		za[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
 	}
 	__syncthreads();
 	stamp(1);
 	// ---- B. forward FFT, whole frame
-	fft_smem<M, NT, -1, 1, true, false, true>(sm.zbuf, tb.tw, tid);
+	fft_smem_pp<M, NT, -1, 1, true, false, true>(za, zb2, tb.tw, tid);
 	stamp(2);
 	// ---- C. real-input spectrum and |X| of the own pairs and their halo
 	const int halo = P.midp + US;
@@ -854,9 +864,9 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 			const float2 twc = cconj(tb.twr[k]);
 #pragma unroll
 			for (int o = 0; o < 3; ++o) {
-				float2* zb = sp.recv[o];
-				if (!zb)
+				if (!sp.recv[o])
 					continue;
+				float2* zb = sp.recv[o] + recv_off;
 				const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 				const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
 				const float2 A = make_float2(Xa.x * ma, Xa.y * ma);   // hps.h:58-66
@@ -882,14 +892,14 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 // G (second half), run by the CTA that owns output o after the cluster barrier: inverse FFT of the received masked
 // spectrum, overlap-add, emission.
 template <int NFFT, int NT>
-__device__ __forceinline__ void hpr_split_synth(const HprDev& P, float2* zb, float* tail, float* ea, float* eb, float* pbuf, uint4* pdst,
-                                                unsigned ptag, const HprTables& tb, unsigned long long* stamps)
+__device__ __forceinline__ void hpr_split_synth(const HprDev& P, float2* zb, float2* zpp, float* tail, float* ea, float* eb, float* pbuf,
+                                                uint4* pdst, unsigned ptag, const HprTables& tb, unsigned long long* stamps)
 {
 	constexpr int M = NFFT / 2;
 	if (stamps && threadIdx.x == 0) stamps[6] = (unsigned long long)clock64();
-	fft_smem<M, NT, +1, 1, false, true, true>(zb, tb.tw, threadIdx.x);
+	const float2* y = fft_smem_pp<M, NT, +1, 1, false, true, true>(zb, zpp, tb.tw, threadIdx.x);
 	if (stamps && threadIdx.x == 0) stamps[7] = (unsigned long long)clock64();
-	hpr_ola_emit<NFFT, NT>(P, zb, tail, false, ea, eb, pbuf, pdst, ptag);
+	hpr_ola_emit<NFFT, NT>(P, y, tail, false, ea, eb, pbuf, pdst, ptag);
 	if (stamps && threadIdx.x == 0) stamps[8] = (unsigned long long)clock64();
 }
 

@@ -259,6 +259,10 @@ struct zen_hpr {
 	bool rt_out_all_host = false;    // every non-null destination of the current call is host memory
 	bool rt_stamps = false;          // ZEN_B200_RT_STAMPS=1: the kernel records its phase boundaries (diagnostics)
 	int rt_cluster = 4;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop
+	// ZEN_B200_RT_TRACE=1: host-side split of the per-hop time (publish / wait for the device / unpack), printed on destroy
+	bool rt_trace = false;
+	double rt_trace_ns[3] = {0.0, 0.0, 0.0};
+	long rt_trace_n = 0;
 };
 
 namespace {
@@ -328,6 +332,8 @@ int rt_launch(zen_hpr* h)
 			h->rt_push = std::atoi(e) != 0;
 		if (const char* e = std::getenv("ZEN_B200_RT_STAMPS"))
 			h->rt_stamps = std::atoi(e) != 0;
+		if (const char* e = std::getenv("ZEN_B200_RT_TRACE"))
+			h->rt_trace = std::atoi(e) != 0;
 		if (const char* e = std::getenv("ZEN_B200_RT_CLUSTER")) {
 			const int c = std::atoi(e);
 			if (c == 1 || c == 2 || c == 4 || c == 8) h->rt_cluster = c;
@@ -372,6 +378,9 @@ int rt_launch(zen_hpr* h)
 	a.seq0 = h->rt_seq;
 	a.idle_ns = h->rt_idle_ns;
 	a.stream = h->rt_stream;
+	a.alt_nt = 0;
+	if (const char* e = std::getenv("ZEN_B200_RT_SPLIT_NT"))
+		a.alt_nt = std::atoi(e);
 	h->rt_args_valid = false;
 	h->rt_ctrl->seq_out = h->rt_seq;
 	h->rt_ctrl->exit_reason = 0;
@@ -526,9 +535,12 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 		}
 	}
 	unsigned tag = (target << 8) | opw;
+	const auto tr0 = std::chrono::steady_clock::now();
 	c->op = opw;
 	_mm_sfence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
 	rt_publish(h, tag, push_src);
+	const auto tr1 = std::chrono::steady_clock::now();
+	auto tr2 = tr1;
 	if (any_out && (h->plan.dev.out_flags & ZEN_OUTPUT_RESIDUAL) && (h->plan.dev.soft || h->plan.dev.sse) && h->rt_out_host[2])
 		std::memset(h->rt_out_host[2], 0, sizeof(float) * (size_t)h->hop);  // the reference's rotate-and-zero (hps.cu:435-449)
 	const auto t0 = std::chrono::steady_clock::now();
@@ -539,6 +551,7 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 	for (;;) {
 		if (any_out) {
 			if (*reinterpret_cast<volatile unsigned*>(&h->rt_stage_out[last_o][h->rt_groups - 1].w) == tag) {
+				if (h->rt_trace) tr2 = std::chrono::steady_clock::now();
 				bool ok = true;
 				for (int o = 0; o < 3 && ok; ++o)
 					if (wait_out[o]) ok = rt_unpack(h, o, tag, h->rt_out_host[o]);
@@ -575,6 +588,13 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 		}
 	}
 	h->rt_seq = target;
+	if (h->rt_trace && any_out) {
+		const auto tr3 = std::chrono::steady_clock::now();
+		h->rt_trace_ns[0] += std::chrono::duration<double, std::nano>(tr1 - tr0).count();
+		h->rt_trace_ns[1] += std::chrono::duration<double, std::nano>(tr2 - tr1).count();
+		h->rt_trace_ns[2] += std::chrono::duration<double, std::nano>(tr3 - tr2).count();
+		h->rt_trace_n++;
+	}
 	return ZEN_OK;
 }
 
@@ -653,6 +673,9 @@ void zen_hpr_destroy(zen_hpr* h)
 	if (!h)
 		return;
 	rt_pause(h);
+	if (h->rt_trace && h->rt_trace_n > 0)
+		std::fprintf(stderr, "zen_b200 rt trace: %ld hops, publish %.0f ns, wait for the device %.0f ns, unpack %.0f ns per hop\n", h->rt_trace_n,
+		             h->rt_trace_ns[0] / h->rt_trace_n, h->rt_trace_ns[1] / h->rt_trace_n, h->rt_trace_ns[2] / h->rt_trace_n);
 	if (h->rt_ctrl) cudaFreeHost((void*)h->rt_ctrl);
 	if (h->rt_stage_in) cudaFreeHost((void*)h->rt_stage_in);
 	if (h->rt_stream) cudaStreamDestroy(h->rt_stream);
@@ -747,6 +770,9 @@ int zen_hpr_copy_residual(zen_hpr* h, float* d_out) { return copy_out(h, 2, d_ou
 int zen_hpr_synchronize(zen_hpr* h)
 {
 	if (!h) return ZEN_ERR_ARG;
+	// real-time session: every call is served synchronously by the resident kernel and nothing is ever queued on the
+	// object's stream (rt_launch drains it) - a cudaStreamSynchronize here would only add its ~1.5 us to each hop
+	if (h->rt_mode && h->rt_running) return ZEN_OK;
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	return ZEN_OK;
 }
@@ -861,6 +887,9 @@ extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const 
 	for (long i = 0; i < n_hops && rc == ZEN_OK; ++i) {
 		auto t1 = std::chrono::high_resolution_clock::now();
 		std::memcpy(io.host_in, h_audio + (size_t)i * hop, sizeof(float) * hop);
+		// the destination of this hop's output is cold: ask for its lines while the device works
+		for (int b = 0; b < hop * (int)sizeof(float); b += 64)
+			__builtin_prefetch(reinterpret_cast<const char*>(h_perc_out + (size_t)i * hop) + b, 1, 3);
 		if (fused) {
 			rc = zen_hpr_process_hop_io(h, io.device_in, nullptr, io.device_out, nullptr);
 			if (rc == ZEN_OK) rc = zen_hpr_synchronize(h);

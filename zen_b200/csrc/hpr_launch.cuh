@@ -75,7 +75,7 @@ struct RtCtrl {
 	unsigned pad1[13];
 	unsigned long long stamps[16]; // RT_F_STAMPS: SM cycle counter at the phase boundaries of the last hop, [9]/[12] globaltimer
 };
-enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3, RT_OP_MASK = 0x0f, RT_F_NEW_ARGS = 0x10, RT_F_PUSH_IN = 0x20, RT_F_TAG_OUT = 0x40, RT_F_STAMPS = 0x80 };
+enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3, RT_OP_EXIT = 4 /* device-internal: idle time-out */, RT_OP_MASK = 0x0f, RT_F_NEW_ARGS = 0x10, RT_F_PUSH_IN = 0x20, RT_F_TAG_OUT = 0x40, RT_F_STAMPS = 0x80 };
 
 struct RtArgs {
 	HprDev dev;
@@ -90,6 +90,7 @@ struct RtArgs {
 	unsigned long long idle_ns;
 	int state_in_smem;     // bit 0: ring + tails + previous hop resident in shared memory; bit 1: window / twiddle tables too
 	int cluster;           // CTAs of the thread-block cluster that serves the stream (1: a single CTA)
+	int alt_nt;            // measurement knob (ZEN_B200_RT_SPLIT_NT): alternative thread count of the split kernel
 	cudaStream_t stream;
 };
 
@@ -104,7 +105,7 @@ constexpr int nt_rt_for()
 template <int NFFT>
 constexpr int nt_rt_split_for()
 {
-	return (NFFT / 16) < 128 ? 128 : ((NFFT / 16) > 512 ? 512 : (NFFT / 16));
+	return (NFFT / 8) < 128 ? 128 : ((NFFT / 8) > 512 ? 512 : (NFFT / 8));
 }
 template <int NFFT>
 constexpr int rt_u_for()
@@ -273,10 +274,8 @@ struct RtShared {
 	float* out[3];
 	int which;
 	unsigned op;
+	unsigned cmd;         // cluster mode: (request number << 8) | op bits, written by the leader CTA through DSMEM
 	unsigned timeout[2];
-	unsigned verdict;
-	unsigned go;                  // cluster mode: request number released by the leader CTA (written through DSMEM)
-	unsigned exit_flag;           // cluster mode: the leader leaves (idle time-out)
 	unsigned long long stamps[16];
 };
 
@@ -359,8 +358,7 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 		S.out[0] = S.out[1] = S.out[2] = nullptr;
 		S.which = 0;
 		S.timeout[0] = S.timeout[1] = 0u;
-		S.go = seq0;
-		S.exit_flag = 0u;
+		S.cmd = seq0 << 8;
 	}
 	__syncthreads();
 	if (state_in_smem) {
@@ -393,126 +391,156 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	unsigned seq = seq0;
 	unsigned exit_reason = 0;
 	__syncthreads();
-	if (SPLIT) cg::this_cluster().sync();  // every CTA's flags are initialised before the leader may write them
+	if (SPLIT) cg::this_cluster().sync();  // every CTA's shared memory is set up before the leader may write into it
+
+	// thread 0: everything the CTA needs to know about request `seqn` goes into S before the barrier that starts it
+	auto fill_request = [&](unsigned opw_, unsigned seqn) {
+		const bool tagged = (opw_ & RT_F_TAG_OUT) != 0;
+		S.op = opw_;
+		S.pk.tag = (seqn << 8) | opw_;
+		S.em.a[0] = (P.out_flags & 1) ? g_ola_h : nullptr;   // keep the public *_out vectors current (hps.h:195-197)
+		S.em.a[1] = (P.out_flags & 2) ? g_ola_p : nullptr;
+		S.em.a[2] = (P.out_flags & 4) ? g_ola_r : nullptr;
+		S.em.b[0] = ((P.out_flags & 1) && !tagged) ? S.out[0] : nullptr;
+		S.em.b[1] = ((P.out_flags & 2) && !tagged) ? S.out[1] : nullptr;
+		S.em.b[2] = ((P.out_flags & 4) && !tagged) ? S.out[2] : nullptr;
+		S.pk.dst[0] = ((P.out_flags & 1) && tagged) ? stage_out_h : nullptr;
+		S.pk.dst[1] = ((P.out_flags & 2) && tagged) ? stage_out_p : nullptr;
+		S.pk.dst[2] = ((P.out_flags & 4) && tagged) ? stage_out_r : nullptr;
+	};
 
 	for (;;) {
-		// ---- wait for the next request: every thread polls its own tagged group(s)
-		const unsigned want = (seq + 1u) << 8;
-		uint4 v[PER];
-		unsigned pending = 0u;
-#pragma unroll
-		for (int b = 0; b < PER; ++b) {
-			v[b] = make_uint4(0u, 0u, 0u, ~want);
-			if (tid + b * NT < NG) pending |= 1u << b;
-		}
-		bool got = pending == 0u;
-		unsigned round = 0;
-		bool all = false;
-		unsigned long long t0 = 0;
-		if (tid == 0 && leader) t0 = rt_globaltimer();
-		for (;;) {
+		unsigned opw = 0u;
+		if (leader) {
+			// ---- wait for the next request: every thread polls its own tagged group(s).  In a cluster only the leader
+			// polls (PCIe read requests are the scarce resource: four CTAs polling cost 4-5 us per hop); it forwards the
+			// hop and the command to the other CTAs through distributed shared memory.
+			const unsigned want = (seq + 1u) << 8;
+			uint4 v[PER];
+			unsigned pending = 0u;
 #pragma unroll
 			for (int b = 0; b < PER; ++b) {
-				if (pending & (1u << b)) {
-					asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-					             : "=r"(v[b].x), "=r"(v[b].y), "=r"(v[b].z), "=r"(v[b].w)
-					             : "l"(stage_in + tid + b * NT)
-					             : "memory");
-					if ((v[b].w ^ want) <= 0xffu) pending &= ~(1u << b);
+				v[b] = make_uint4(0u, 0u, 0u, ~want);
+				if (tid + b * NT < NG) pending |= 1u << b;
+			}
+			bool got = pending == 0u;
+			unsigned round = 0;
+			bool all = false;
+			unsigned long long t0 = 0;
+			if (tid == 0) t0 = rt_globaltimer();
+			for (;;) {
+#pragma unroll
+				for (int b = 0; b < PER; ++b) {
+					if (pending & (1u << b)) {
+						asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+						             : "=r"(v[b].x), "=r"(v[b].y), "=r"(v[b].z), "=r"(v[b].w)
+						             : "l"(stage_in + tid + b * NT)
+						             : "memory");
+						if ((v[b].w ^ want) <= 0xffu) pending &= ~(1u << b);
+					}
+				}
+				got = pending == 0u;
+				if (tid == 0)
+					S.timeout[round & 1u] = (!got && (round & 63u) == 63u && rt_globaltimer() - t0 > idle_ns) ? 1u : 0u;
+				const int n_got = __syncthreads_count(got);
+				if (n_got == NT) {
+					all = true;
+					break;
+				}
+				if (S.timeout[round & 1u])
+					break;
+				++round;
+			}
+			// (uniform from here: the count and the flag are the same for every thread)
+			if (all) {
+				opw = v[0].w & 0xffu;
+				if (tid == 0) {
+					if (opw & RT_F_NEW_ARGS) {
+						// pointers changed since the last request: fetch them (one more round trip), else reuse the cached ones
+						S.in = *reinterpret_cast<const float* volatile*>(&ctrl->in);
+						S.out[0] = *reinterpret_cast<float* volatile*>(&ctrl->out[0]);
+						S.out[1] = *reinterpret_cast<float* volatile*>(&ctrl->out[1]);
+						S.out[2] = *reinterpret_cast<float* volatile*>(&ctrl->out[2]);
+						S.which = *reinterpret_cast<volatile int*>(&ctrl->which);
+					}
+					if (opw & RT_F_STAMPS) {
+						S.stamps[9] = rt_globaltimer();
+						S.stamps[10] = (unsigned long long)clock64();
+					}
 				}
 			}
-			got = pending == 0u;
-			if (tid == 0) {
-				// the leader decides the idle time-out; the other CTAs of a cluster leave when it tells them to
-				unsigned to = 0u;
-				if (!got) to = leader ? (((round & 63u) == 63u && rt_globaltimer() - t0 > idle_ns) ? 1u : 0u) : *reinterpret_cast<volatile unsigned*>(&S.exit_flag);
-				S.timeout[round & 1u] = to;
+			else {
+				opw = RT_OP_EXIT;  // idle time-out
 			}
-			const int n_got = __syncthreads_count(got);
-			if (n_got == NT) {
-				all = true;
-				break;
+			const bool pushed = (opw & RT_F_PUSH_IN) && (opw & RT_OP_MASK) == RT_OP_PROCESS;
+			float* stash = S.hopbuf[prev_idx ^ 1];
+			if (pushed) {
+#pragma unroll
+				for (int b = 0; b < PER; ++b) {
+					const int g = tid + b * NT;
+					if (g < NG) {
+						stash[3 * g] = __uint_as_float(v[b].x);
+						if (3 * g + 1 < HOP) stash[3 * g + 1] = __uint_as_float(v[b].y);
+						if (3 * g + 2 < HOP) stash[3 * g + 2] = __uint_as_float(v[b].z);
+					}
+				}
 			}
-			if (S.timeout[round & 1u])
-				break;
-			++round;
+			if (tid == 0) fill_request(opw, seq + 1u);
+			__syncthreads();  // the request starts here: the stash and S are complete
+			if constexpr (SPLIT) {
+				// The command goes to the other CTAs by a few remote stores; the hop itself stays here and is PULLED by
+				// them while they window it (rt_microbench: pushing 1026 floats costs ~0.7 us per CTA with 4-byte stores,
+				// pulling them ~0.35 us for all CTAs at once).  The command word doubles as the flag the other CTAs spin
+				// on: no cluster barrier (0.2 us + the leader waiting for it) at the start of a hop.
+				// (thread 0 signals after the barrier, while the other warps already start on the hop)
+				if (tid == 0) {
+					for (int r = 1; r < C && (opw & RT_F_NEW_ARGS); ++r) {
+						RtShared<NFFT>* R = cg::this_cluster().map_shared_rank(&S, r);
+						R->in = S.in;
+						R->out[0] = S.out[0];
+						R->out[1] = S.out[1];
+						R->out[2] = S.out[2];
+						R->which = S.which;
+					}
+					asm volatile("fence.acq_rel.cluster;" ::: "memory");
+					for (int r = 1; r < C; ++r)
+						*reinterpret_cast<volatile unsigned*>(&cg::this_cluster().map_shared_rank(&S, r)->cmd) = ((seq + 1u) << 8) | opw;
+				}
+			}
 		}
-		if (!all) {  // (uniform: the count and the flag are the same for every thread)
+		else {
+			// the other CTAs of the cluster wait for the leader's command word
+			if (tid == 0) {
+				volatile unsigned* cmd = &S.cmd;
+				unsigned c;
+				do {
+					c = *cmd;
+				} while (((c ^ ((seq + 1u) << 8)) >> 8) != 0u);
+				asm volatile("fence.acq_rel.cluster;" ::: "memory");
+				fill_request(c & 0xffu, seq + 1u);
+			}
+			__syncthreads();
+		}
+		opw = S.op;
+		const unsigned op = opw & RT_OP_MASK;
+		if (op == RT_OP_EXIT) {
 			exit_reason = 2u;
-			if (SPLIT && leader && tid > 0 && tid < C) *reinterpret_cast<volatile unsigned*>(cg::this_cluster().map_shared_rank(&S.exit_flag, tid)) = 1u;
 			break;
 		}
 		++seq;
-		if (SPLIT && leader && tid > 0 && tid < C) *reinterpret_cast<volatile unsigned*>(cg::this_cluster().map_shared_rank(&S.go, tid)) = seq;  // release request `seq`
-		if (tid == 0) {
-			const unsigned opw = v[0].w & 0xffu;
-			if (opw & RT_F_NEW_ARGS) {
-				// pointers changed since the last request: fetch them (one more round trip), else reuse the cached ones
-				S.in = *reinterpret_cast<const float* volatile*>(&ctrl->in);
-				S.out[0] = *reinterpret_cast<float* volatile*>(&ctrl->out[0]);
-				S.out[1] = *reinterpret_cast<float* volatile*>(&ctrl->out[1]);
-				S.out[2] = *reinterpret_cast<float* volatile*>(&ctrl->out[2]);
-				S.which = *reinterpret_cast<volatile int*>(&ctrl->which);
-			}
-			S.op = opw;
-			if (opw & RT_F_STAMPS) {
-				S.stamps[9] = rt_globaltimer();
-				S.stamps[10] = (unsigned long long)clock64();
-			}
-			const bool tagged = (opw & RT_F_TAG_OUT) != 0;
-			S.pk.tag = (seq << 8) | opw;
-			S.em.a[0] = (P.out_flags & 1) ? g_ola_h : nullptr;   // keep the public *_out vectors current (hps.h:195-197)
-			S.em.a[1] = (P.out_flags & 2) ? g_ola_p : nullptr;
-			S.em.a[2] = (P.out_flags & 4) ? g_ola_r : nullptr;
-			S.em.b[0] = ((P.out_flags & 1) && !tagged) ? S.out[0] : nullptr;
-			S.em.b[1] = ((P.out_flags & 2) && !tagged) ? S.out[1] : nullptr;
-			S.em.b[2] = ((P.out_flags & 4) && !tagged) ? S.out[2] : nullptr;
-			S.pk.dst[0] = ((P.out_flags & 1) && tagged) ? stage_out_h : nullptr;
-			S.pk.dst[1] = ((P.out_flags & 2) && tagged) ? stage_out_p : nullptr;
-			S.pk.dst[2] = ((P.out_flags & 4) && tagged) ? stage_out_r : nullptr;
-		}
-		{
-			float* stash = S.hopbuf[prev_idx ^ 1];
-#pragma unroll
-			for (int b = 0; b < PER; ++b) {
-				const int g = tid + b * NT;
-				if (g < NG && (v[b].w & RT_F_PUSH_IN) && (v[b].w & RT_OP_MASK) == RT_OP_PROCESS) {
-					stash[3 * g] = __uint_as_float(v[b].x);
-					if (3 * g + 1 < HOP) stash[3 * g + 1] = __uint_as_float(v[b].y);
-					if (3 * g + 2 < HOP) stash[3 * g + 2] = __uint_as_float(v[b].z);
-				}
-			}
-		}
-		__syncthreads();
-		const unsigned opw = S.op;
-		const unsigned op = opw & RT_OP_MASK;
-		if (SPLIT && !leader && op != RT_OP_PROCESS) {
-			// not speculated on: wait until the leader has released this request (or leaves)
-			if (tid == 0) {
-				volatile unsigned* go = &S.go;
-				volatile unsigned* ex = &S.exit_flag;
-				while (*go != seq && !*ex) {
-				}
-				S.verdict = (*go == seq) ? 1u : 0u;
-			}
-			__syncthreads();
-			if (!S.verdict) {
-				exit_reason = 2u;
-				break;
-			}
-		}
 		if (op == RT_OP_STOP) {
 			exit_reason = 1u;
 			break;
 		}
+		const bool tagged = (opw & RT_F_TAG_OUT) != 0;
 		if (op == RT_OP_PROCESS) {
 			const bool pushed = (opw & RT_F_PUSH_IN) != 0;
-			unsigned long long* stamps = (opw & RT_F_STAMPS) ? S.stamps : nullptr;
+			unsigned long long* stamps = ((opw & RT_F_STAMPS) && leader) ? S.stamps : nullptr;
 			if constexpr (!SPLIT) {
 				hpr_iteration<NFFT, NT, rt_u_for<NFFT>(), true>(P, sm, S.st, iter, S.hopbuf[prev_idx],
 				                                                pushed ? S.hopbuf[prev_idx ^ 1] : S.in, true, false, S.em,
 				                                                pushed ? nullptr : S.hopbuf[prev_idx ^ 1], stamps, nullptr, &S.tb, &S.pk);
-				if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && !(opw & RT_F_TAG_OUT) && S.out[2])
+				if ((P.out_flags & ZEN_OUTPUT_RESIDUAL) && (P.soft || P.sse) && !tagged && S.out[2])
 					for (int n = tid; n < HOP; n += NT)
 						S.out[2][n] = 0.0f;
 			}
@@ -524,36 +552,27 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 						stash[n] = src[n];
 					__syncthreads();
 				}
-				// speculative: nothing below is irreversible before the leader's release (the ring slot written here is
-				// rewritten with the same values when the request is served again after a time-out race)
-				hpr_split_analyse<NFFT, NT, US>(P, sm, S.st, iter, S.hopbuf[prev_idx], S.hopbuf[prev_idx ^ 1], S.tb, S.sp,
-				                                leader ? stamps : nullptr);
-				if (!leader) {
-					if (tid == 0) {
-						volatile unsigned* go = &S.go;
-						volatile unsigned* ex = &S.exit_flag;
-						while (*go != seq && !*ex) {
-						}
-						S.verdict = (*go == seq) ? 1u : 0u;
-					}
-					__syncthreads();
-					if (!S.verdict) {
-						exit_reason = 2u;
-						break;
-					}
-				}
+				// a pushed hop sits in the leader's stash: the other CTAs read it from there and keep a copy as the next `prev`
+				float* stash = S.hopbuf[prev_idx ^ 1];
+				const bool remote = pushed && !leader;
+				const float* cur = remote ? cg::this_cluster().map_shared_rank(stash, 0) : stash;
+				hpr_split_analyse<NFFT, NT, US>(P, sm, S.st, iter, S.hopbuf[prev_idx], cur, remote ? stash : nullptr, S.tb, S.sp,
+				                                reinterpret_cast<float2*>(smem_raw + S.zrecv_off) + 2 * fpad_size(M), (iter & 1) * fpad_size(M), stamps);
 				cg::this_cluster().sync();  // the masked spectra have arrived at their owners
+				// (two receive buffers, by request parity: a CTA may already receive the next hop's spectrum while it
+				// still finishes this one's overlap-add)
+				float2* zrecv = reinterpret_cast<float2*>(smem_raw + S.zrecv_off) + (iter & 1) * fpad_size(M);
+				float2* zpp = reinterpret_cast<float2*>(smem_raw + S.zrecv_off) + 2 * fpad_size(M);
 				if (S.sp.owner[1] == rank)
-					hpr_split_synth<NFFT, NT>(P, reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.st.tail[1], S.em.a[1], S.em.b[1], S.pk.buf, S.pk.dst[1], S.pk.tag, S.tb,
-					                          leader ? stamps : nullptr);
+					hpr_split_synth<NFFT, NT>(P, zrecv, zpp, S.st.tail[1], S.em.a[1], S.em.b[1], S.pk.buf, S.pk.dst[1], S.pk.tag, S.tb, stamps);
 				if (S.sp.owner[0] == rank)
-					hpr_split_synth<NFFT, NT>(P, reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.st.tail[0], S.em.a[0], S.em.b[0], S.pk.buf, S.pk.dst[0], S.pk.tag, S.tb, nullptr);
+					hpr_split_synth<NFFT, NT>(P, zrecv, zpp, S.st.tail[0], S.em.a[0], S.em.b[0], S.pk.buf, S.pk.dst[0], S.pk.tag, S.tb, nullptr);
 				if (S.sp.owner[2] == rank)
-					hpr_split_synth<NFFT, NT>(P, reinterpret_cast<float2*>(smem_raw + S.zrecv_off), S.st.tail[2], S.em.a[2], S.em.b[2], S.pk.buf, S.pk.dst[2], S.pk.tag, S.tb, nullptr);
+					hpr_split_synth<NFFT, NT>(P, zrecv, zpp, S.st.tail[2], S.em.a[2], S.em.b[2], S.pk.buf, S.pk.dst[2], S.pk.tag, S.tb, nullptr);
 			}
 			prev_idx ^= 1;
 			++iter;
-			if (tid == 0 && leader && stamps) {
+			if (tid == 0 && stamps) {
 				S.stamps[11] = (unsigned long long)clock64();
 				S.stamps[12] = rt_globaltimer();
 			}
@@ -564,18 +583,20 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			for (int n = tid; n < HOP; n += NT)
 				dst[n] = __ldcg(src + n);  // written by another CTA in cluster mode: not through this SM's L1
 		}
-		if (SPLIT)
-			cg::this_cluster().sync();  // every CTA is done with this request (and with the receive buffers)
-		else
-			__syncthreads();
-		if (leader) {
-			// Completion flag, needed only when the host is not already watching the tagged output groups.  A release
-			// store: the fence in front of it orders the plain output stores, and - unlike __threadfence_system() -
-			// no L1 invalidation follows it.
-			if (tid == 0 && !(op == RT_OP_PROCESS && (opw & RT_F_TAG_OUT)))
+		// Completion flag, needed only when the host is not already watching the tagged output groups.  A release
+		// store: the fence in front of it orders the plain output stores, and - unlike __threadfence_system() - no L1
+		// invalidation follows it.  (In a cluster the next request's first barrier is what keeps the CTAs in step.)
+		if (!(op == RT_OP_PROCESS && tagged)) {
+			if (SPLIT)
+				cg::this_cluster().sync();  // the owners of the outputs have stored them
+			else
+				__syncthreads();
+			if (leader && tid == 0)
 				asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&ctrl->seq_out), "r"(seq) : "memory");
-			if (tid < 16 && op == RT_OP_PROCESS && (opw & RT_F_STAMPS))
-				ctrl->stamps[tid] = S.stamps[tid];  // diagnostics
+		}
+		if (leader && op == RT_OP_PROCESS && (opw & RT_F_STAMPS)) {
+			__syncthreads();
+			if (tid < 16) ctrl->stamps[tid] = S.stamps[tid];  // diagnostics
 		}
 	}
 
@@ -613,7 +634,6 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	__syncthreads();
 	if (SPLIT) cg::this_cluster().sync();  // nobody touches another CTA's shared memory after this point
 	if (leader && tid == 0) {
-		// (a request the leader never released - time-out race - is not counted: the host publishes it again)
 		ctrl->exit_reason = exit_reason;
 		__threadfence_system();
 		ctrl->seq_out = seq;
@@ -687,7 +707,7 @@ size_t rt_smem_bytes(const HprDev& d, int smem_flags, int cluster)
 	if (smem_flags & 2)
 		b += sizeof(float) * (size_t)rt_table_floats<NFFT>();
 	if (cluster > 1)
-		b += sizeof(float2) * (size_t)fpad_size(M);  // receive buffer of the masked spectrum
+		b += 3 * sizeof(float2) * (size_t)fpad_size(M);  // two receive buffers of the masked spectrum (request parity) + ping-pong partner of the FFTs
 	return b;
 }
 
@@ -717,8 +737,12 @@ int launch_rt_variant(const RtArgs& a)
 template <int NFFT>
 int launch_rt_impl(const RtArgs& a)
 {
-	if (a.cluster > 1)
+	if (a.cluster > 1) {
+		if constexpr (NFFT == 4096) {
+			if (a.alt_nt == 256) return launch_rt_variant<NFFT, 256, true>(a);
+		}
 		return launch_rt_variant<NFFT, nt_rt_split_for<NFFT>(), true>(a);
+	}
 	return launch_rt_variant<NFFT, nt_rt_for<NFFT>(), false>(a);
 }
 
