@@ -323,7 +323,7 @@ int rt_launch(zen_hpr* h)
 		std::memset((void*)h->rt_ctrl, 0, sizeof(RtCtrl));
 		ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->rt_ctrl_dev, (void*)h->rt_ctrl, 0));
 		ZEN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->rt_stream, cudaStreamNonBlocking));
-		ZEN_CUDA_CHECK(cudaMalloc(&h->d_iter, sizeof(int)));
+		ZEN_CUDA_CHECK(cudaMalloc(&h->d_iter, 2 * sizeof(int)));  // frame counter, "the stream's CTAs have left" flag
 		if (const char* e = std::getenv("ZEN_B200_RT_IDLE_MS")) {
 			long ms = std::atol(e);
 			if (ms > 0) h->rt_idle_ns = (unsigned long long)ms * 1000ull * 1000ull;
@@ -362,8 +362,8 @@ int rt_launch(zen_hpr* h)
 			h->rt_stage_in[g].w = h->rt_seq << 8;
 	}
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-	int it = (int)h->iter;
-	ZEN_CUDA_CHECK(cudaMemcpy(h->d_iter, &it, sizeof(int), cudaMemcpyHostToDevice));
+	int it[2] = {(int)h->iter, 0};
+	ZEN_CUDA_CHECK(cudaMemcpy(h->d_iter, it, 2 * sizeof(int), cudaMemcpyHostToDevice));
 	RtArgs a;
 	a.dev = h->plan.dev;
 	a.ctrl = h->rt_ctrl_dev;
@@ -381,6 +381,9 @@ int rt_launch(zen_hpr* h)
 	a.alt_nt = 0;
 	if (const char* e = std::getenv("ZEN_B200_RT_SPLIT_NT"))
 		a.alt_nt = std::atoi(e);
+	a.pad_grid = 0;
+	if (const char* e = std::getenv("ZEN_B200_RT_PAD_GRID"))
+		a.pad_grid = std::atoi(e);
 	h->rt_args_valid = false;
 	h->rt_ctrl->seq_out = h->rt_seq;
 	h->rt_ctrl->exit_reason = 0;
@@ -456,13 +459,15 @@ void rt_publish(zen_hpr* h, unsigned tag, const float* src)
 	}
 }
 
-// all groups of output o carry `tag`: unpack them into dst; false if some group is still old
-bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst)
+// Unpack the groups of output o that already carry `tag` into dst, starting at group g (updated); true when the whole
+// hop is out.  The host calls it while the device is still storing: by the time the last group lands, the others
+// have been copied.
+bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
 {
 	const uint4* st = h->rt_stage_out[o];
 	const int hop = h->hop, groups = h->rt_groups;
 	const int full = hop / 3;  // groups with three samples
-	for (int g = 0; g < full; ++g) {
+	for (; g < full; ++g) {
 		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
 		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
 			return false;
@@ -470,7 +475,7 @@ bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst)
 		_mm_storel_pi(reinterpret_cast<__m64*>(dst + 3 * g), _mm_castsi128_ps(v));
 		_mm_store_ss(dst + 3 * g + 2, _mm_movehl_ps(_mm_castsi128_ps(v), _mm_castsi128_ps(v)));
 	}
-	for (int g = full; g < groups; ++g) {
+	for (; g < groups; ++g) {
 		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
 		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
 			return false;
@@ -545,7 +550,11 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 		std::memset(h->rt_out_host[2], 0, sizeof(float) * (size_t)h->hop);  // the reference's rotate-and-zero (hps.cu:435-449)
 	const auto t0 = std::chrono::steady_clock::now();
 	unsigned spins = 0;
-	// the kernel emits P, H, R in that order (hps.cu:498-579): watch the last group of the last output first
+	// The kernel emits P, H, R in that order (hps.cu:498-579): watch the last group of the last output, then take
+	// everything.  (Unpacking the groups one by one as they land was tried and gave wrong samples now and then: a
+	// 16-byte group is not guaranteed to become visible to the CPU in one piece at the very moment it arrives; by the
+	// time the LAST group is there, the earlier ones have long settled, and every tag is still checked.)
+	int prog[3] = {0, 0, 0};
 	int last_o = -1;
 	if (any_out) last_o = wait_out[2] ? 2 : (wait_out[0] ? 0 : 1);
 	for (;;) {
@@ -553,8 +562,10 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 			if (*reinterpret_cast<volatile unsigned*>(&h->rt_stage_out[last_o][h->rt_groups - 1].w) == tag) {
 				if (h->rt_trace) tr2 = std::chrono::steady_clock::now();
 				bool ok = true;
-				for (int o = 0; o < 3 && ok; ++o)
-					if (wait_out[o]) ok = rt_unpack(h, o, tag, h->rt_out_host[o]);
+				for (int o = 0; o < 3 && ok; ++o) {
+					prog[o] = 0;
+					if (wait_out[o]) ok = rt_unpack(h, o, tag, h->rt_out_host[o], prog[o]);
+				}
 				if (ok) break;
 			}
 		}
@@ -574,6 +585,7 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 						tag = (target << 8) | opw;
 						c->op = opw;
 						rt_publish(h, tag, push_src);
+						prog[0] = prog[1] = prog[2] = 0;
 						rc = rt_launch(h);
 						h->rt_args_valid = true;
 					}

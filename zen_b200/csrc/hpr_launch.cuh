@@ -91,6 +91,7 @@ struct RtArgs {
 	int state_in_smem;     // bit 0: ring + tails + previous hop resident in shared memory; bit 1: window / twiddle tables too
 	int cluster;           // CTAs of the thread-block cluster that serves the stream (1: a single CTA)
 	int alt_nt;            // measurement knob (ZEN_B200_RT_SPLIT_NT): alternative thread count of the split kernel
+	int pad_grid;          // measurement knob (ZEN_B200_RT_PAD_GRID): launch this many CTAs in total, all but the first cluster idle
 	cudaStream_t stream;
 };
 
@@ -301,8 +302,15 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	sm.carve(smem_raw, P.Lp);
 	const int tid = threadIdx.x;
 	// the cluster spans the whole grid: CTA rank == blockIdx.x.  C == 1 is an ordinary launch.
-	const int rank = SPLIT ? blockIdx.x : 0, C = SPLIT ? gridDim.x : 1;
+	const int C = SPLIT ? (int)cg::this_cluster().dim_blocks().x : 1;
+	const int rank = SPLIT ? (int)cg::this_cluster().block_rank() : 0;
 	const bool leader = rank == 0;
+	if ((int)blockIdx.x >= C) {
+		// padding CTAs (measurement knob ZEN_B200_RT_PAD_GRID): they only keep the grid large until the stream's CTAs leave
+		while (*reinterpret_cast<volatile int*>(g_iter + 1) == 0)
+			__nanosleep(20000);
+		return;
+	}
 	const int state_in_smem = smem_flags & 1;
 	const int ring_n = P.W * (M + 1);
 
@@ -492,19 +500,26 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				// them while they window it (rt_microbench: pushing 1026 floats costs ~0.7 us per CTA with 4-byte stores,
 				// pulling them ~0.35 us for all CTAs at once).  The command word doubles as the flag the other CTAs spin
 				// on: no cluster barrier (0.2 us + the leader waiting for it) at the start of a hop.
-				// (thread 0 signals after the barrier, while the other warps already start on the hop)
-				if (tid == 0) {
-					for (int r = 1; r < C && (opw & RT_F_NEW_ARGS); ++r) {
-						RtShared<NFFT>* R = cg::this_cluster().map_shared_rank(&S, r);
-						R->in = S.in;
-						R->out[0] = S.out[0];
-						R->out[1] = S.out[1];
-						R->out[2] = S.out[2];
-						R->which = S.which;
+				// The LAST thread signals, after the barrier, while the other warps already start on the hop.  No
+				// cluster-scope fence on the common path: the stash lives in this CTA's shared memory - one physical
+				// copy, no cache in front of it - and BAR.SYNC has drained the stores into it before the command word
+				// leaves; a reader that has seen the word issues its (remote) loads afterwards.  A fence costs ~0.5 us
+				// of the leader's and of everybody else's hop.  Changed arguments (rare) do travel behind a fence.
+				if (tid == NT - 1) {
+					const unsigned cw = S.op;  // (opw is thread 0's: this thread may not own a tagged group)
+					if (cw & RT_F_NEW_ARGS) {
+						for (int r = 1; r < C; ++r) {
+							RtShared<NFFT>* R = cg::this_cluster().map_shared_rank(&S, r);
+							R->in = S.in;
+							R->out[0] = S.out[0];
+							R->out[1] = S.out[1];
+							R->out[2] = S.out[2];
+							R->which = S.which;
+						}
+						asm volatile("fence.acq_rel.cluster;" ::: "memory");
 					}
-					asm volatile("fence.acq_rel.cluster;" ::: "memory");
 					for (int r = 1; r < C; ++r)
-						*reinterpret_cast<volatile unsigned*>(&cg::this_cluster().map_shared_rank(&S, r)->cmd) = ((seq + 1u) << 8) | opw;
+						*reinterpret_cast<volatile unsigned*>(&cg::this_cluster().map_shared_rank(&S, r)->cmd) = ((seq + 1u) << 8) | cw;
 				}
 			}
 		}
@@ -516,7 +531,10 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				do {
 					c = *cmd;
 				} while (((c ^ ((seq + 1u) << 8)) >> 8) != 0u);
-				asm volatile("fence.acq_rel.cluster;" ::: "memory");
+				if (c & RT_F_NEW_ARGS)
+					asm volatile("fence.acq_rel.cluster;" ::: "memory");
+				else
+					asm volatile("" ::: "memory");
 				fill_request(c & 0xffu, seq + 1u);
 			}
 			__syncthreads();
@@ -630,7 +648,10 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			g_input[HOP + n] = newest;
 		}
 	}
-	if (leader && tid == 0) *g_iter = iter;
+	if (leader && tid == 0) {
+		*g_iter = iter;
+		*reinterpret_cast<volatile int*>(g_iter + 1) = 1;  // releases the padding CTAs, if any
+	}
 	__syncthreads();
 	if (SPLIT) cg::this_cluster().sync();  // nobody touches another CTA's shared memory after this point
 	if (leader && tid == 0) {
@@ -718,7 +739,7 @@ int launch_rt_variant(const RtArgs& a)
 	size_t smem = rt_smem_bytes<NFFT>(a.dev, a.state_in_smem, a.cluster);
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned)a.cluster);
+	cfg.gridDim = dim3((unsigned)(a.pad_grid > a.cluster ? (a.pad_grid / a.cluster) * a.cluster : a.cluster));
 	cfg.blockDim = dim3(NT);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = a.stream;
