@@ -118,17 +118,26 @@ int zen_hpr_copy_residual(zen_hpr* h, float* d_out_hop);
 int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* d_out_h, float* d_out_p, float* d_out_r);
 int zen_hpr_synchronize(zen_hpr* h);
 /* Resident real-time session for a causal stream: a persistent kernel keeps the
- * stream's state in shared memory and serves zen_hpr_process_next_hop /
- * zen_hpr_process_hop_io / zen_hpr_copy_* through a doorbell in mapped memory,
- * so a hop costs neither a kernel launch nor a stream synchronisation.  Calls
- * stay synchronous: on return the outputs are readable by the host.  The kernel
- * leaves by itself after ZEN_B200_RT_IDLE_MS (default 250) without a hop and is
- * brought back transparently by the next call; every other entry point pauses it
- * first.  While it is resident, device-wide synchronisation (cudaDeviceSynchronize)
- * waits for that idle time-out. */
+ * stream's state (|X| ring, overlap-add tails, previous hop, window and twiddle
+ * tables) in shared memory and serves zen_hpr_process_next_hop /
+ * zen_hpr_process_hop_io / zen_hpr_copy_* without a kernel launch, a stream
+ * synchronisation or a system-wide fence per hop.  When the hop pointer and the
+ * output pointers are host-visible (mapped pinned memory, zen_io_alloc) the hop
+ * is PUSHED to the kernel as tagged 16-byte groups {x0, x1, x2, tag} and the
+ * outputs come back the same way; device-memory pointers are read / written by
+ * the kernel itself behind a completion flag.  With the default plan (hard mask,
+ * copy-border) the hop is split over a 4-CTA thread-block cluster
+ * (ZEN_B200_RT_CLUSTER=1|2|4|8).  Calls stay synchronous: on return the outputs
+ * are readable by the host.  The kernel leaves by itself after
+ * ZEN_B200_RT_IDLE_MS (default 250) without a hop and is brought back
+ * transparently by the next call; every other entry point pauses it first.
+ * While it is resident, device-wide synchronisation (cudaDeviceSynchronize)
+ * waits for that idle time-out.  ZEN_B200_RT_PUSH=0 disables the tagged
+ * transfers (the kernel then reads the hop itself: one more PCIe round trip). */
 int zen_hpr_realtime_begin(zen_hpr* h);
 int zen_hpr_realtime_end(zen_hpr* h);
-/* diagnostics: device globaltimer (ns) at the phase boundaries of the last hop the resident kernel served */
+/* diagnostics (ZEN_B200_RT_STAMPS=1): SM cycle counter at the phase boundaries of the last hop the resident kernel
+ * served, [9] / [12] = %globaltimer (ns) at its start / end */
 int zen_hpr_realtime_stamps(zen_hpr* h, unsigned long long* out16);
 /* Make caller-owned device buffers (nwin floats each, 8-byte aligned) the object's
  * streaming state, so that e.g. thrust::device_vector members named like the
@@ -151,7 +160,9 @@ int zen_hpr_materialize(zen_hpr* h, float* d_sliding_stft, float* d_s_mag, float
  * hops of iota data then reset (hps.cu:392-409); then per hop the region the
  * reference times: host copy-in -> process_next_hop -> copy_percussive -> host
  * copy-out.  fused == 1 replaces the two calls by zen_hpr_process_hop_io;
- * fused == 2 additionally serves it from the resident kernel (zen_hpr_realtime_begin).
+ * fused == 2 additionally serves it from the resident kernel (zen_hpr_realtime_begin);
+ * fused == 3 is the resident kernel behind the reference's own two calls (process_next_hop
+ * is then only submitted and copy_percussive unpacks the output on the host).
  * h_us_per_hop (optional) receives the wall time of each hop in microseconds. */
 int zen_fakert_run(float fs, int hop, float beta, int options, const float* h_audio, long n_hops,
                    int warmup_iters, int fused, float* h_perc_out, double* h_us_per_hop);

@@ -463,6 +463,61 @@ def test_resident_realtime_kernel_equals_per_hop_launches(torch, zen, fs, hop, f
     ref_obj.close()
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("hop,flags,cb,soft", [(1024, 2, True, False), (512, 7, True, False), (1024, 7, False, False), (512, 7, True, True)])
+def test_resident_kernel_two_call_sequence(torch, zen, hop, flags, cb, soft):
+    """HPRRealtime's own sequence (process_next_hop, then copy_*; zen/fakert.h:229-230) on a resident session: the hop
+    is only submitted, copy_* waits for the tagged output and unpacks it on the host (host-visible destination) or lets
+    the kernel copy it (device memory).  Bit-identical to the per-launch path, also across an idle time-out and when a
+    copy is skipped or repeated."""
+    import time
+    fs, n_hops = 44100.0, 30
+    audio = synth_audio(n_hops * hop, seed=79)
+
+    def make():
+        h = zen.HPR(fs, hop, 2.5, flags, 0, cb)
+        if soft:
+            h.use_soft_mask()
+        return h
+    ref_obj = make()
+    ref = ref_obj.run(audio)
+    ref_obj.close()
+    h = make()
+    h.realtime_begin()
+    io = zen.IOGPU(hop)
+    houts = [zen.IOGPU(hop) for _ in range(3)]
+    douts = [torch.zeros(hop, dtype=torch.float32, device="cuda") for _ in range(3)]
+    L = zen._lib.lib() if hasattr(zen, "_lib") else None
+    from zen_b200 import _lib
+    L = _lib.lib()
+    copies = [L.zen_hpr_copy_harmonic, L.zen_hpr_copy_percussive, L.zen_hpr_copy_residual]
+    got = [np.zeros(n_hops * hop, np.float32) for _ in range(3)]
+    for i in range(n_hops):
+        sl = slice(i * hop, (i + 1) * hop)
+        if i == 12:
+            time.sleep(0.6)                      # idle time-out between two hops
+        io.host_in[:] = audio[sl]
+        h.process_next_hop(io.device_in)
+        if i == 17:
+            time.sleep(0.6)                      # idle time-out between the submission and the copy
+        for o in range(3):
+            if not flags & (1 << o):
+                continue
+            if i % 5 == 3:                       # device-memory destination: the kernel copies
+                assert copies[o](h._h, douts[o].data_ptr()) == 0
+                torch.cuda.synchronize()
+                got[o][sl] = douts[o].cpu().numpy()
+            else:
+                assert copies[o](h._h, houts[o].device_out) == 0
+                if i % 7 == 2:                   # asking twice gives the same hop
+                    assert copies[o](h._h, houts[o].device_out) == 0
+                got[o][sl] = houts[o].host_out
+    for o in range(3):
+        if flags & (1 << o):
+            assert np.array_equal(got[o], ref[o]), o
+    h.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("hop,flags,mode", [(1024, 7, "device"), (1024, 2, "pull"), (32, 7, "push"), (2048, 3, "device"),
                                             (4096, 2, "mixed")])
 def test_resident_kernel_request_protocols(torch, zen, hop, flags, mode):

@@ -12,19 +12,15 @@ for hop in hops:
     n_h = 3000
     a = synth_audio(n_h * hop, seed=hop)
     ref = None
-    for cluster, push, nt, pad in (("1", "1", "0", "0"), ("4", "1", "0", "0"), ("8", "1", "0", "0"), ("4", "0", "0", "0")):
-        if nt != "0" and hop != 1024:
-            continue
+    for cluster, push, fused in (("1", "1", 2), ("4", "1", 2), ("8", "1", 2), ("4", "0", 2), ("4", "1", 3)):
         os.environ["ZEN_B200_RT_CLUSTER"] = cluster
         os.environ["ZEN_B200_RT_PUSH"] = push
-        os.environ["ZEN_B200_RT_SPLIT_NT"] = nt
-        os.environ["ZEN_B200_RT_PAD_GRID"] = pad
         perc = np.zeros(n_h * hop, np.float32)
         us = np.zeros(n_h, np.float64)
-        rc = L.zen_fakert_run(44100.0, hop, 2.5, 0, a.ctypes.data, n_h, 1000, 2, perc.ctypes.data, us.ctypes.data)
+        rc = L.zen_fakert_run(44100.0, hop, 2.5, 0, a.ctypes.data, n_h, 1000, fused, perc.ctypes.data, us.ctypes.data)
         if ref is None:
             ref = perc.copy()
-        key = "hop%d_cluster%s_%s%s" % (hop, cluster, "push" if push == "1" else "pull", ("_nt256" if nt == "256" else "") + ("_pad148" if pad != "0" else ""))
+        key = "hop%d_cluster%s_%s%s" % (hop, cluster, "push" if push == "1" else "pull", "_two_call" if fused == 3 else "")
         out[key] = {"rc": rc, "p50_us": round(float(np.median(us)), 2), "p99_us": round(float(np.percentile(us, 99)), 2),
                     "min_us": round(float(us.min()), 2), "same_as_cluster1": bool(np.array_equal(perc, ref))}
         print(key, out[key], flush=True)

@@ -259,6 +259,19 @@ struct zen_hpr {
 	bool rt_out_all_host = false;    // every non-null destination of the current call is host memory
 	bool rt_stamps = false;          // ZEN_B200_RT_STAMPS=1: the kernel records its phase boundaries (diagnostics)
 	int rt_cluster = 4;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop
+	// A process_next_hop without destinations is only SUBMITTED (like the reference's, which queues its kernels and lets
+	// copy_* wait, hps.cu:341-363): its outputs land in the tagged staging buffers and the copy_* that follows unpacks them
+	// on the host - the two-call sequence of zen/fakert.h:229-230 costs one round trip to the device, not two.
+	struct RtPending {
+		bool active = false;
+		unsigned op = 0, opw = 0, tag = 0, target = 0;
+		const float* push_src = nullptr;
+		bool tagged[3] = {false, false, false};
+	} rt_pend;
+	unsigned rt_last_tag = 0;                          // tag of the last PROCESS whose outputs sit in the staging buffers
+	bool rt_last_tagged[3] = {false, false, false};
+	const float* rt_copy_ptr[3] = {nullptr, nullptr, nullptr};  // copy_* destination last seen per output and its host alias
+	float* rt_copy_host[3] = {nullptr, nullptr, nullptr};
 	// ZEN_B200_RT_TRACE=1: host-side split of the per-hop time (publish / wait for the device / unpack), printed on destroy
 	bool rt_trace = false;
 	double rt_trace_ns[3] = {0.0, 0.0, 0.0};
@@ -323,7 +336,7 @@ int rt_launch(zen_hpr* h)
 		std::memset((void*)h->rt_ctrl, 0, sizeof(RtCtrl));
 		ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->rt_ctrl_dev, (void*)h->rt_ctrl, 0));
 		ZEN_CUDA_CHECK(cudaStreamCreateWithFlags(&h->rt_stream, cudaStreamNonBlocking));
-		ZEN_CUDA_CHECK(cudaMalloc(&h->d_iter, 2 * sizeof(int)));  // frame counter, "the stream's CTAs have left" flag
+		ZEN_CUDA_CHECK(cudaMalloc(&h->d_iter, sizeof(int)));
 		if (const char* e = std::getenv("ZEN_B200_RT_IDLE_MS")) {
 			long ms = std::atol(e);
 			if (ms > 0) h->rt_idle_ns = (unsigned long long)ms * 1000ull * 1000ull;
@@ -362,8 +375,8 @@ int rt_launch(zen_hpr* h)
 			h->rt_stage_in[g].w = h->rt_seq << 8;
 	}
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-	int it[2] = {(int)h->iter, 0};
-	ZEN_CUDA_CHECK(cudaMemcpy(h->d_iter, it, 2 * sizeof(int), cudaMemcpyHostToDevice));
+	int it = (int)h->iter;
+	ZEN_CUDA_CHECK(cudaMemcpy(h->d_iter, &it, sizeof(int), cudaMemcpyHostToDevice));
 	RtArgs a;
 	a.dev = h->plan.dev;
 	a.ctrl = h->rt_ctrl_dev;
@@ -378,12 +391,6 @@ int rt_launch(zen_hpr* h)
 	a.seq0 = h->rt_seq;
 	a.idle_ns = h->rt_idle_ns;
 	a.stream = h->rt_stream;
-	a.alt_nt = 0;
-	if (const char* e = std::getenv("ZEN_B200_RT_SPLIT_NT"))
-		a.alt_nt = std::atoi(e);
-	a.pad_grid = 0;
-	if (const char* e = std::getenv("ZEN_B200_RT_PAD_GRID"))
-		a.pad_grid = std::atoi(e);
 	h->rt_args_valid = false;
 	h->rt_ctrl->seq_out = h->rt_seq;
 	h->rt_ctrl->exit_reason = 0;
@@ -446,6 +453,18 @@ void rt_publish(zen_hpr* h, unsigned tag, const float* src)
 		const __m128 keep = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
 		const int full = (hop - 1) / 3;  // groups whose 16-byte read stays inside the hop (3g + 3 < hop)
 		int g = 0;
+		// four groups (twelve samples) per step: three loads, four aligned 16-byte stores
+		for (; g + 4 <= full && 3 * g + 12 <= hop; g += 4) {
+			const __m128 s0 = _mm_loadu_ps(src + 3 * g), s1 = _mm_loadu_ps(src + 3 * g + 4), s2 = _mm_loadu_ps(src + 3 * g + 8);
+			const __m128 t1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(0, 0, 3, 3));   // x3 x3 x4 x4
+			const __m128 g1 = _mm_shuffle_ps(t1, s1, _MM_SHUFFLE(3, 1, 2, 0));   // x3 x4 x5 (x7)
+			const __m128 g2 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2));   // x6 x7 x8 (x9)
+			const __m128 g3 = _mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 2, 1));   // x9 x10 x11 (x11)
+			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(s0, keep), tagv));
+			_mm_store_ps(reinterpret_cast<float*>(st + g + 1), _mm_or_ps(_mm_and_ps(g1, keep), tagv));
+			_mm_store_ps(reinterpret_cast<float*>(st + g + 2), _mm_or_ps(_mm_and_ps(g2, keep), tagv));
+			_mm_store_ps(reinterpret_cast<float*>(st + g + 3), _mm_or_ps(_mm_and_ps(g3, keep), tagv));
+		}
 		for (; g < full; ++g)
 			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_loadu_ps(src + 3 * g), keep), tagv));
 		for (; g < groups; ++g) {
@@ -467,6 +486,21 @@ bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
 	const uint4* st = h->rt_stage_out[o];
 	const int hop = h->hop, groups = h->rt_groups;
 	const int full = hop / 3;  // groups with three samples
+	// four groups per step: one tag comparison, three 16-byte stores
+	const __m128i tagv = _mm_set1_epi32((int)tag);
+	for (; g + 4 <= full; g += 4) {
+		const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g)), b = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 1));
+		const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 2)), d = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 3));
+		const __m128i tags = _mm_unpackhi_epi64(_mm_unpackhi_epi32(a, b), _mm_unpackhi_epi32(c, d));  // a3 b3 c3 d3
+		if (_mm_movemask_epi8(_mm_cmpeq_epi32(tags, tagv)) != 0xffff)
+			break;  // the scalar loop below finds the group that is still old
+		const __m128 fa = _mm_castsi128_ps(a), fb = _mm_castsi128_ps(b), fc = _mm_castsi128_ps(c), fd = _mm_castsi128_ps(d);
+		const __m128 t0 = _mm_shuffle_ps(fa, fb, _MM_SHUFFLE(0, 0, 2, 2));   // a2 a2 b0 b0
+		const __m128 t2 = _mm_shuffle_ps(fc, fd, _MM_SHUFFLE(0, 0, 2, 2));   // c2 c2 d0 d0
+		_mm_storeu_ps(dst + 3 * g, _mm_shuffle_ps(fa, t0, _MM_SHUFFLE(2, 0, 1, 0)));      // a0 a1 a2 b0
+		_mm_storeu_ps(dst + 3 * g + 4, _mm_shuffle_ps(fb, fc, _MM_SHUFFLE(1, 0, 2, 1)));  // b1 b2 c0 c1
+		_mm_storeu_ps(dst + 3 * g + 8, _mm_shuffle_ps(t2, fd, _MM_SHUFFLE(2, 1, 2, 0)));  // c2 d0 d1 d2
+	}
 	for (; g < full; ++g) {
 		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
 		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
@@ -487,86 +521,58 @@ bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
 	return true;
 }
 
-int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, float* o2, int which)
+// Wait until request `target` is complete: all tagged outputs in wait_out carry `tag` (they are unpacked into dst[o]
+// where that is not null), or - nothing tagged - the completion flag shows `target`.  Brings the kernel back if it
+// left on its idle time-out before it saw the request.
+// all groups of output o carry `tag`
+bool rt_tags_ready(const zen_hpr* h, int o, unsigned tag)
 {
-	if (h->plan_dirty) {
-		int rc = rt_collect(h);  // cannot be running with a dirty plan, but be safe
-		if (rc == ZEN_OK) rc = rebuild_plan_fwd(h);
-		if (rc != ZEN_OK) return rc;
-	}
-	if (!h->rt_running) {
-		int rc = rt_launch(h);
-		if (rc != ZEN_OK) return rc;
-	}
+	const uint4* st = h->rt_stage_out[o];
+	for (int g = 0; g < h->rt_groups; ++g)
+		if (*reinterpret_cast<volatile const unsigned*>(&st[g].w) != tag)
+			return false;
+	return true;
+}
+
+int rt_wait(zen_hpr* h, unsigned op, unsigned& opw, unsigned& tag, unsigned target, const float* push_src, const bool wait_out[3],
+            float* const dst[3], std::chrono::steady_clock::time_point* t_seen)
+{
 	RtCtrl* c = h->rt_ctrl;
-	const unsigned target = h->rt_seq + 1;
-	// the pointers usually repeat hop after hop (IOGPU buffers): the kernel re-reads them only when told to
-	const bool same = h->rt_args_valid && c->in == in && c->out[0] == o0 && c->out[1] == o1 && c->out[2] == o2 && c->which == which;
-	if (!same) {
-		c->in = in;
-		c->out[0] = o0;
-		c->out[1] = o1;
-		c->out[2] = o2;
-		c->which = which;
-		h->rt_args_valid = true;
-		// which of them can the host itself read / write?  (mapped pinned memory: IOGPU)
-		float* outs[3] = {o0, o1, o2};
-		h->rt_in_host = h->rt_push ? static_cast<const float*>(rt_host_alias(in)) : nullptr;
-		h->rt_out_all_host = h->rt_push;
-		for (int o = 0; o < 3; ++o) {
-			h->rt_out_host[o] = h->rt_push ? static_cast<float*>(rt_host_alias(outs[o])) : nullptr;
-			if (outs[o] && !h->rt_out_host[o]) h->rt_out_all_host = false;
-		}
-	}
-	unsigned opw = op | (same ? 0u : (unsigned)RT_F_NEW_ARGS);
-	// outputs the kernel will emit for this call (hpr_iteration step G)
-	bool wait_out[3] = {false, false, false};
-	bool any_out = false;
-	const float* push_src = nullptr;
-	if (op == RT_OP_PROCESS) {
-		if (h->rt_stamps) opw |= RT_F_STAMPS;
-		if (h->rt_in_host) {
-			opw |= RT_F_PUSH_IN;
-			push_src = h->rt_in_host;
-		}
-		if (h->rt_out_all_host) {
-			const unsigned of = (unsigned)h->plan.dev.out_flags;
-			for (int o = 0; o < 3; ++o) {
-				const bool emitted = (of & (1u << o)) && !(o == 2 && (h->plan.dev.soft || h->plan.dev.sse));
-				wait_out[o] = h->rt_out_host[o] && emitted;
-				any_out = any_out || wait_out[o];
-			}
-			if (any_out) opw |= RT_F_TAG_OUT;
-		}
-	}
-	unsigned tag = (target << 8) | opw;
-	const auto tr0 = std::chrono::steady_clock::now();
-	c->op = opw;
-	_mm_sfence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
-	rt_publish(h, tag, push_src);
-	const auto tr1 = std::chrono::steady_clock::now();
-	auto tr2 = tr1;
-	if (any_out && (h->plan.dev.out_flags & ZEN_OUTPUT_RESIDUAL) && (h->plan.dev.soft || h->plan.dev.sse) && h->rt_out_host[2])
-		std::memset(h->rt_out_host[2], 0, sizeof(float) * (size_t)h->hop);  // the reference's rotate-and-zero (hps.cu:435-449)
+	const bool any_out = wait_out[0] || wait_out[1] || wait_out[2];
 	const auto t0 = std::chrono::steady_clock::now();
 	unsigned spins = 0;
-	// The kernel emits P, H, R in that order (hps.cu:498-579): watch the last group of the last output, then take
-	// everything.  (Unpacking the groups one by one as they land was tried and gave wrong samples now and then: a
-	// 16-byte group is not guaranteed to become visible to the CPU in one piece at the very moment it arrives; by the
-	// time the LAST group is there, the earlier ones have long settled, and every tag is still checked.)
+	// The kernel emits P, H, R in that order (hps.cu:498-579).  The groups are unpacked while they land (that pulls
+	// their cache lines in early: reading 86 freshly DMA-written lines after the fact costs ~0.6 us), but what counts is
+	// the SECOND pass, made once every tag is there: unpacking the groups only at the moment each one arrives was tried
+	// and gave wrong samples now and then - a group is not guaranteed to become visible to the CPU in one piece at the
+	// very moment its tag does.  By the time the last group is in, the earlier ones have long settled; the second pass
+	// checks every tag again and rewrites every sample.
 	int prog[3] = {0, 0, 0};
-	int last_o = -1;
-	if (any_out) last_o = wait_out[2] ? 2 : (wait_out[0] ? 0 : 1);
+	bool seen = false;
 	for (;;) {
 		if (any_out) {
-			if (*reinterpret_cast<volatile unsigned*>(&h->rt_stage_out[last_o][h->rt_groups - 1].w) == tag) {
-				if (h->rt_trace) tr2 = std::chrono::steady_clock::now();
+			bool all = true;
+			for (int oi = 0; oi < 3; ++oi) {
+				const int o = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
+				if (!wait_out[o]) continue;
+				if (dst[o]) {
+					if (prog[o] < h->rt_groups && !rt_unpack(h, o, tag, dst[o], prog[o])) all = false;
+				}
+				else if (!rt_tags_ready(h, o, tag))
+					all = false;
+			}
+			if (t_seen && !seen && (prog[0] | prog[1] | prog[2])) {
+				seen = true;
+				*t_seen = std::chrono::steady_clock::now();
+			}
+			if (all) {
 				bool ok = true;
 				for (int o = 0; o < 3 && ok; ++o) {
-					prog[o] = 0;
-					if (wait_out[o]) ok = rt_unpack(h, o, tag, h->rt_out_host[o], prog[o]);
+					int g = 0;
+					if (wait_out[o] && dst[o]) ok = rt_unpack(h, o, tag, dst[o], g);
 				}
 				if (ok) break;
+				prog[0] = prog[1] = prog[2] = 0;  // (cannot happen: a tag went back) start over
 			}
 		}
 		else if (c->seq_out == target)
@@ -600,6 +606,114 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 		}
 	}
 	h->rt_seq = target;
+	return ZEN_OK;
+}
+
+// complete a submitted-only request (see RtPending)
+int rt_drain(zen_hpr* h)
+{
+	if (!h->rt_pend.active)
+		return ZEN_OK;
+	auto& p = h->rt_pend;
+	float* const none[3] = {nullptr, nullptr, nullptr};
+	int rc = rt_wait(h, p.op, p.opw, p.tag, p.target, p.push_src, p.tagged, none, nullptr);
+	p.active = false;
+	if (rc != ZEN_OK) return rc;
+	h->rt_last_tag = p.tag;
+	for (int o = 0; o < 3; ++o)
+		h->rt_last_tagged[o] = p.tagged[o];
+	return ZEN_OK;
+}
+
+int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, float* o2, int which)
+{
+	{
+		int rc = rt_drain(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	if (h->plan_dirty) {
+		int rc = rt_collect(h);  // cannot be running with a dirty plan, but be safe
+		if (rc == ZEN_OK) rc = rebuild_plan_fwd(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	if (!h->rt_running) {
+		int rc = rt_launch(h);
+		if (rc != ZEN_OK) return rc;
+	}
+	RtCtrl* c = h->rt_ctrl;
+	const unsigned target = h->rt_seq + 1;
+	// the pointers usually repeat hop after hop (IOGPU buffers): the kernel re-reads them only when told to
+	const bool same = h->rt_args_valid && c->in == in && c->out[0] == o0 && c->out[1] == o1 && c->out[2] == o2 && c->which == which;
+	if (!same) {
+		c->in = in;
+		c->out[0] = o0;
+		c->out[1] = o1;
+		c->out[2] = o2;
+		c->which = which;
+		h->rt_args_valid = true;
+		// which of them can the host itself read / write?  (mapped pinned memory: IOGPU)
+		float* outs[3] = {o0, o1, o2};
+		h->rt_in_host = h->rt_push ? static_cast<const float*>(rt_host_alias(in)) : nullptr;
+		h->rt_out_all_host = h->rt_push;
+		for (int o = 0; o < 3; ++o) {
+			h->rt_out_host[o] = h->rt_push ? static_cast<float*>(rt_host_alias(outs[o])) : nullptr;
+			if (outs[o] && !h->rt_out_host[o]) h->rt_out_all_host = false;
+		}
+	}
+	unsigned opw = op | (same ? 0u : (unsigned)RT_F_NEW_ARGS);
+	// outputs the kernel will emit for this call (hpr_iteration step G)
+	bool wait_out[3] = {false, false, false};
+	bool any_out = false;
+	bool defer = false;
+	const float* push_src = nullptr;
+	if (op == RT_OP_PROCESS) {
+		if (h->rt_stamps) opw |= RT_F_STAMPS;
+		if (h->rt_in_host) {
+			opw |= RT_F_PUSH_IN;
+			push_src = h->rt_in_host;
+		}
+		const unsigned of = (unsigned)h->plan.dev.out_flags;
+		const bool no_dst = !o0 && !o1 && !o2;
+		if (h->rt_out_all_host) {
+			for (int o = 0; o < 3; ++o) {
+				const bool emitted = (of & (1u << o)) && !(o == 2 && (h->plan.dev.soft || h->plan.dev.sse));
+				wait_out[o] = emitted && (no_dst || h->rt_out_host[o]);
+				any_out = any_out || wait_out[o];
+			}
+			if (any_out) opw |= RT_F_TAG_OUT;
+			defer = no_dst && any_out;  // process_next_hop: submit only, the outputs stay in the staging buffers
+		}
+		h->rt_last_tagged[0] = h->rt_last_tagged[1] = h->rt_last_tagged[2] = false;  // the staging buffers are about to change
+	}
+	unsigned tag = (target << 8) | opw;
+	const auto tr0 = std::chrono::steady_clock::now();
+	c->op = opw;
+	_mm_sfence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
+	rt_publish(h, tag, push_src);
+	const auto tr1 = std::chrono::steady_clock::now();
+	auto tr2 = tr1;
+	if (defer) {
+		auto& p = h->rt_pend;
+		p.active = true;
+		p.op = op;
+		p.opw = opw;
+		p.tag = tag;
+		p.target = target;
+		p.push_src = push_src;
+		for (int o = 0; o < 3; ++o)
+			p.tagged[o] = wait_out[o];
+		return ZEN_OK;
+	}
+	if (any_out && (h->plan.dev.out_flags & ZEN_OUTPUT_RESIDUAL) && (h->plan.dev.soft || h->plan.dev.sse) && h->rt_out_host[2])
+		std::memset(h->rt_out_host[2], 0, sizeof(float) * (size_t)h->hop);  // the reference's rotate-and-zero (hps.cu:435-449)
+	float* dst[3] = {h->rt_out_host[0], h->rt_out_host[1], h->rt_out_host[2]};
+	int rc = rt_wait(h, op, opw, tag, target, push_src, wait_out, dst, h->rt_trace ? &tr2 : nullptr);
+	if (rc != ZEN_OK) return rc;
+	if (op == RT_OP_PROCESS && any_out) {
+		h->rt_last_tag = tag;
+		for (int o = 0; o < 3; ++o)
+			h->rt_last_tagged[o] = wait_out[o];
+	}
 	if (h->rt_trace && any_out) {
 		const auto tr3 = std::chrono::steady_clock::now();
 		h->rt_trace_ns[0] += std::chrono::duration<double, std::nano>(tr1 - tr0).count();
@@ -610,11 +724,35 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 	return ZEN_OK;
 }
 
+// copy_{harmonic,percussive,residual} of a resident session: when the last hop's output o sits in the tagged staging
+// buffer and the destination is host-visible, the host unpacks it itself; otherwise the kernel copies it
+int rt_copy(zen_hpr* h, int o, float* d_out)
+{
+	int rc = rt_drain(h);
+	if (rc != ZEN_OK) return rc;
+	if (h->rt_push && h->rt_last_tagged[o]) {
+		if (h->rt_copy_ptr[o] != d_out) {
+			h->rt_copy_ptr[o] = d_out;
+			h->rt_copy_host[o] = static_cast<float*>(rt_host_alias(d_out));
+		}
+		if (h->rt_copy_host[o]) {
+			int g = 0;
+			if (rt_unpack(h, o, h->rt_last_tag, h->rt_copy_host[o], g))
+				return ZEN_OK;
+		}
+	}
+	return rt_call(h, RT_OP_COPY, nullptr, d_out, nullptr, nullptr, o);
+}
+
 // leave the resident kernel (state goes back to global memory); rt_mode is kept
 int rt_pause(zen_hpr* h)
 {
 	if (!h->rt_running)
 		return ZEN_OK;
+	{
+		int rc = rt_drain(h);  // a submitted hop is completed first (this brings a timed-out kernel back if need be)
+		if (rc != ZEN_OK) return rc;
+	}
 	if (h->rt_ctrl->alive) {
 		int rc = rt_call(h, RT_OP_STOP, nullptr, nullptr, nullptr, nullptr, 0);
 		if (rc != ZEN_OK) return rc;
@@ -767,7 +905,7 @@ static int copy_out(zen_hpr* h, int o, float* d_out)
 {
 	if (!h || !d_out) return ZEN_ERR_ARG;
 	if (h->rt_mode)
-		return rt_call(h, RT_OP_COPY, nullptr, d_out, nullptr, nullptr, o);
+		return rt_copy(h, o, d_out);
 	int hop = h->hop;
 	copy_hop_kernel<<<(hop + 255) / 256, 256, 0, h->stream>>>(h->d_ola[o], d_out, hop);
 	ZEN_CUDA_CHECK(cudaGetLastError());
@@ -784,7 +922,7 @@ int zen_hpr_synchronize(zen_hpr* h)
 	if (!h) return ZEN_ERR_ARG;
 	// real-time session: every call is served synchronously by the resident kernel and nothing is ever queued on the
 	// object's stream (rt_launch drains it) - a cudaStreamSynchronize here would only add its ~1.5 us to each hop
-	if (h->rt_mode && h->rt_running) return ZEN_OK;
+	if (h->rt_mode && h->rt_running) return rt_drain(h);
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	return ZEN_OK;
 }
@@ -880,7 +1018,8 @@ extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const 
 		zen_hpr_destroy(h);
 		return rc;
 	}
-	if (fused == 2) {
+	const bool two_call = fused == 0 || fused == 3;  // process_next_hop + copy_percussive, as zen/fakert.h:229-230
+	if (fused >= 2) {
 		rc = zen_hpr_realtime_begin(h);  // resident kernel: no launch, no stream synchronisation per hop
 		if (rc != ZEN_OK) {
 			zen_io_free(&io);
@@ -892,7 +1031,7 @@ extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const 
 	for (int i = 0; i < warmup_iters && rc == ZEN_OK; ++i) {
 		for (int j = 0; j < hop; ++j)
 			io.host_in[j] = (float)((long)i * hop + j);
-		rc = fused ? zen_hpr_process_hop_io(h, io.device_in, nullptr, io.device_out, nullptr) : zen_hpr_process_next_hop(h, io.device_in);
+		rc = !two_call ? zen_hpr_process_hop_io(h, io.device_in, nullptr, io.device_out, nullptr) : zen_hpr_process_next_hop(h, io.device_in);
 		if (rc == ZEN_OK) rc = zen_hpr_synchronize(h);
 	}
 	if (rc == ZEN_OK) rc = zen_hpr_reset_buffers(h);
@@ -902,7 +1041,7 @@ extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const 
 		// the destination of this hop's output is cold: ask for its lines while the device works
 		for (int b = 0; b < hop * (int)sizeof(float); b += 64)
 			__builtin_prefetch(reinterpret_cast<const char*>(h_perc_out + (size_t)i * hop) + b, 1, 3);
-		if (fused) {
+		if (!two_call) {
 			rc = zen_hpr_process_hop_io(h, io.device_in, nullptr, io.device_out, nullptr);
 			if (rc == ZEN_OK) rc = zen_hpr_synchronize(h);
 		}

@@ -90,8 +90,6 @@ struct RtArgs {
 	unsigned long long idle_ns;
 	int state_in_smem;     // bit 0: ring + tails + previous hop resident in shared memory; bit 1: window / twiddle tables too
 	int cluster;           // CTAs of the thread-block cluster that serves the stream (1: a single CTA)
-	int alt_nt;            // measurement knob (ZEN_B200_RT_SPLIT_NT): alternative thread count of the split kernel
-	int pad_grid;          // measurement knob (ZEN_B200_RT_PAD_GRID): launch this many CTAs in total, all but the first cluster idle
 	cudaStream_t stream;
 };
 
@@ -305,12 +303,6 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	const int C = SPLIT ? (int)cg::this_cluster().dim_blocks().x : 1;
 	const int rank = SPLIT ? (int)cg::this_cluster().block_rank() : 0;
 	const bool leader = rank == 0;
-	if ((int)blockIdx.x >= C) {
-		// padding CTAs (measurement knob ZEN_B200_RT_PAD_GRID): they only keep the grid large until the stream's CTAs leave
-		while (*reinterpret_cast<volatile int*>(g_iter + 1) == 0)
-			__nanosleep(20000);
-		return;
-	}
 	const int state_in_smem = smem_flags & 1;
 	const int ring_n = P.W * (M + 1);
 
@@ -648,10 +640,7 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			g_input[HOP + n] = newest;
 		}
 	}
-	if (leader && tid == 0) {
-		*g_iter = iter;
-		*reinterpret_cast<volatile int*>(g_iter + 1) = 1;  // releases the padding CTAs, if any
-	}
+	if (leader && tid == 0) *g_iter = iter;
 	__syncthreads();
 	if (SPLIT) cg::this_cluster().sync();  // nobody touches another CTA's shared memory after this point
 	if (leader && tid == 0) {
@@ -739,7 +728,7 @@ int launch_rt_variant(const RtArgs& a)
 	size_t smem = rt_smem_bytes<NFFT>(a.dev, a.state_in_smem, a.cluster);
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned)(a.pad_grid > a.cluster ? (a.pad_grid / a.cluster) * a.cluster : a.cluster));
+	cfg.gridDim = dim3((unsigned)a.cluster);
 	cfg.blockDim = dim3(NT);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = a.stream;
@@ -758,12 +747,8 @@ int launch_rt_variant(const RtArgs& a)
 template <int NFFT>
 int launch_rt_impl(const RtArgs& a)
 {
-	if (a.cluster > 1) {
-		if constexpr (NFFT == 4096) {
-			if (a.alt_nt == 256) return launch_rt_variant<NFFT, 256, true>(a);
-		}
+	if (a.cluster > 1)
 		return launch_rt_variant<NFFT, nt_rt_split_for<NFFT>(), true>(a);
-	}
 	return launch_rt_variant<NFFT, nt_rt_for<NFFT>(), false>(a);
 }
 
