@@ -86,8 +86,7 @@ def test_fakert_cli(tmp_path, oracle, resident):
     wav, out = str(tmp_path / "in.wav"), str(tmp_path / "perc.wav")
     xq = write_wav(wav, x)
     env = dict(os.environ)
-    if resident:
-        env["ZEN_RESIDENT"] = "1"
+    env["ZEN_RESIDENT"] = "1" if resident else "0"
     r = subprocess.run([ZEN, "fakert", "-i", wav, "--hps", "1024", "2.5", "-o", out], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr
     n_chunks = oracle.fakert_n_chunks(xq.size, hop)
