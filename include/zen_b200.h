@@ -136,6 +136,11 @@ int zen_hpr_synchronize(zen_hpr* h);
  * transfers (the kernel then reads the hop itself: one more PCIe round trip). */
 int zen_hpr_realtime_begin(zen_hpr* h);
 int zen_hpr_realtime_end(zen_hpr* h);
+/* host-only test hooks for the tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag} the resident session exchanges with
+ * its kernel (no device involved).  groups: 16-byte aligned, ceil(hop / 3) * 16 bytes.  zen_rt_unpack_groups returns
+ * the number of leading groups that carried `tag` and were unpacked. */
+int zen_rt_pack_groups(const float* src, int hop, unsigned tag, void* groups);
+int zen_rt_unpack_groups(const void* groups, int hop, unsigned tag, float* dst);
 /* diagnostics (ZEN_B200_RT_STAMPS=1): SM cycle counter at the phase boundaries of the last hop the resident kernel
  * served, [9] / [12] = %globaltimer (ns) at its start / end */
 int zen_hpr_realtime_stamps(zen_hpr* h, unsigned long long* out16);

@@ -91,3 +91,46 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not banned.search(txt), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("hop", [32, 64, 128, 256, 512, 1024, 2048, 4096, 1, 2, 3, 4, 5, 11, 12, 13, 1000])
+def test_tagged_group_format_round_trip(hop):
+    """the resident session's staging format {x[3g], x[3g+1], x[3g+2], tag} (hpr_launch.cuh RtCtrl): packing then
+    unpacking is the identity for every hop length (vector body, scalar tail, ragged last group), every group carries
+    the tag, the padding of the last group is zero, and a single stale group stops the unpack exactly there"""
+    import ctypes
+    from zen_b200 import _lib
+    L = _lib.lib()
+    L.zen_rt_pack_groups.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_void_p]
+    L.zen_rt_unpack_groups.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_void_p]
+    rng = np.random.default_rng(hop)
+    x = rng.standard_normal(hop).astype(np.float32)
+    x[rng.integers(0, hop)] = -0.0
+    groups = (hop + 2) // 3
+    raw = np.zeros(groups * 4 + 4, np.uint32)
+    off = (-raw.ctypes.data // 4) % 4                       # 16-byte aligned view
+    g = raw[off:off + groups * 4]
+    assert g.ctypes.data % 16 == 0
+    tag = (123456 << 8) | 0x61
+    assert L.zen_rt_pack_groups(x.ctypes.data, hop, tag, g.ctypes.data) == 0
+    gv = g.reshape(groups, 4)
+    assert np.all(gv[:, 3] == tag)
+    flat = gv[:, :3].reshape(-1)
+    assert np.array_equal(flat[:hop], x.view(np.uint32))    # bit patterns, -0.0 included
+    assert np.all(flat[hop:] == 0)
+    y = np.full(hop + 4, 7.0, np.float32)
+    assert L.zen_rt_unpack_groups(g.ctypes.data, hop, tag, y.ctypes.data) == groups
+    assert np.array_equal(y[:hop].view(np.uint32), x.view(np.uint32))
+    assert np.all(y[hop:] == 7.0)                           # nothing written past the hop
+    # one stale group: the unpack stops there and leaves the rest alone
+    for stale in sorted({0, groups // 2, groups - 1}):
+        buf = np.zeros(groups * 4 + 4, np.uint32)
+        o2 = (-buf.ctypes.data // 4) % 4
+        g2 = buf[o2:o2 + groups * 4]
+        g2[:] = g
+        g2[4 * stale + 3] = tag - 256                       # the previous request's tag
+        y2 = np.full(hop + 4, 7.0, np.float32)
+        assert L.zen_rt_unpack_groups(g2.ctypes.data, hop, tag, y2.ctypes.data) == stale
+        assert np.array_equal(y2[:3 * stale].view(np.uint32), x[:3 * stale].view(np.uint32))
+        assert np.all(y2[3 * stale:] == 7.0)                # nothing of the stale group or behind it was written
+    assert L.zen_rt_pack_groups(x.ctypes.data, hop, tag, g.ctypes.data + 4) != 0   # misaligned staging buffer

@@ -443,48 +443,40 @@ int rt_collect(zen_hpr* h)
 	return ZEN_OK;
 }
 
-// publish one request: tag every group of the staging buffer; with `src` the groups carry the hop
-void rt_publish(zen_hpr* h, unsigned tag, const float* src)
+// ---- tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag} (RtCtrl, hpr_launch.cuh), host side ----------------
+// pack `hop` samples into ceil(hop / 3) groups; one aligned 16-byte store per group
+void rt_pack_groups(const float* src, int hop, unsigned tag, uint4* st)
 {
-	uint4* st = h->rt_stage_in;
-	const int hop = h->hop, groups = h->rt_groups;
-	if (src) {
-		const __m128 tagv = _mm_castsi128_ps(_mm_set_epi32((int)tag, 0, 0, 0));
-		const __m128 keep = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
-		const int full = (hop - 1) / 3;  // groups whose 16-byte read stays inside the hop (3g + 3 < hop)
-		int g = 0;
-		// four groups (twelve samples) per step: three loads, four aligned 16-byte stores
-		for (; g + 4 <= full && 3 * g + 12 <= hop; g += 4) {
-			const __m128 s0 = _mm_loadu_ps(src + 3 * g), s1 = _mm_loadu_ps(src + 3 * g + 4), s2 = _mm_loadu_ps(src + 3 * g + 8);
-			const __m128 t1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(0, 0, 3, 3));   // x3 x3 x4 x4
-			const __m128 g1 = _mm_shuffle_ps(t1, s1, _MM_SHUFFLE(3, 1, 2, 0));   // x3 x4 x5 (x7)
-			const __m128 g2 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2));   // x6 x7 x8 (x9)
-			const __m128 g3 = _mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 2, 1));   // x9 x10 x11 (x11)
-			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(s0, keep), tagv));
-			_mm_store_ps(reinterpret_cast<float*>(st + g + 1), _mm_or_ps(_mm_and_ps(g1, keep), tagv));
-			_mm_store_ps(reinterpret_cast<float*>(st + g + 2), _mm_or_ps(_mm_and_ps(g2, keep), tagv));
-			_mm_store_ps(reinterpret_cast<float*>(st + g + 3), _mm_or_ps(_mm_and_ps(g3, keep), tagv));
-		}
-		for (; g < full; ++g)
-			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_loadu_ps(src + 3 * g), keep), tagv));
-		for (; g < groups; ++g) {
-			float x0 = src[3 * g], x1 = 3 * g + 1 < hop ? src[3 * g + 1] : 0.0f, x2 = 3 * g + 2 < hop ? src[3 * g + 2] : 0.0f;
-			_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_set_ps(0.0f, x2, x1, x0), keep), tagv));
-		}
+	const int groups = (hop + 2) / 3;
+	const __m128 tagv = _mm_castsi128_ps(_mm_set_epi32((int)tag, 0, 0, 0));
+	const __m128 keep = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
+	const int full = (hop - 1) / 3;  // groups whose 16-byte read stays inside the hop (3g + 3 < hop)
+	int g = 0;
+	// four groups (twelve samples) per step: three loads, four aligned 16-byte stores
+	for (; g + 4 <= full && 3 * g + 12 <= hop; g += 4) {
+		const __m128 s0 = _mm_loadu_ps(src + 3 * g), s1 = _mm_loadu_ps(src + 3 * g + 4), s2 = _mm_loadu_ps(src + 3 * g + 8);
+		const __m128 t1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(0, 0, 3, 3));   // x3 x3 x4 x4
+		const __m128 g1 = _mm_shuffle_ps(t1, s1, _MM_SHUFFLE(3, 1, 2, 0));   // x3 x4 x5 (x7)
+		const __m128 g2 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2));   // x6 x7 x8 (x9)
+		const __m128 g3 = _mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 2, 1));   // x9 x10 x11 (x11)
+		_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(s0, keep), tagv));
+		_mm_store_ps(reinterpret_cast<float*>(st + g + 1), _mm_or_ps(_mm_and_ps(g1, keep), tagv));
+		_mm_store_ps(reinterpret_cast<float*>(st + g + 2), _mm_or_ps(_mm_and_ps(g2, keep), tagv));
+		_mm_store_ps(reinterpret_cast<float*>(st + g + 3), _mm_or_ps(_mm_and_ps(g3, keep), tagv));
 	}
-	else {
-		for (int g = 0; g < groups; ++g)
-			*reinterpret_cast<volatile unsigned*>(&st[g].w) = tag;
+	for (; g < full; ++g)
+		_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_loadu_ps(src + 3 * g), keep), tagv));
+	for (; g < groups; ++g) {
+		float x0 = src[3 * g], x1 = 3 * g + 1 < hop ? src[3 * g + 1] : 0.0f, x2 = 3 * g + 2 < hop ? src[3 * g + 2] : 0.0f;
+		_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_set_ps(0.0f, x2, x1, x0), keep), tagv));
 	}
 }
 
-// Unpack the groups of output o that already carry `tag` into dst, starting at group g (updated); true when the whole
-// hop is out.  The host calls it while the device is still storing: by the time the last group lands, the others
-// have been copied.
-bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
+// Unpack the groups that carry `tag` into dst, starting at group g (updated); true when the whole hop is out, false at
+// the first group that is still old.
+bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g)
 {
-	const uint4* st = h->rt_stage_out[o];
-	const int hop = h->hop, groups = h->rt_groups;
+	const int groups = (hop + 2) / 3;
 	const int full = hop / 3;  // groups with three samples
 	// four groups per step: one tag comparison, three 16-byte stores
 	const __m128i tagv = _mm_set1_epi32((int)tag);
@@ -521,9 +513,22 @@ bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
 	return true;
 }
 
-// Wait until request `target` is complete: all tagged outputs in wait_out carry `tag` (they are unpacked into dst[o]
-// where that is not null), or - nothing tagged - the completion flag shows `target`.  Brings the kernel back if it
-// left on its idle time-out before it saw the request.
+// publish one request: tag every group of the staging buffer; with `src` the groups carry the hop
+void rt_publish(zen_hpr* h, unsigned tag, const float* src)
+{
+	uint4* st = h->rt_stage_in;
+	if (src)
+		rt_pack_groups(src, h->hop, tag, st);
+	else
+		for (int g = 0; g < h->rt_groups; ++g)
+			*reinterpret_cast<volatile unsigned*>(&st[g].w) = tag;
+}
+
+bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
+{
+	return rt_unpack_groups(h->rt_stage_out[o], h->hop, tag, dst, g);
+}
+
 // all groups of output o carry `tag`
 bool rt_tags_ready(const zen_hpr* h, int o, unsigned tag)
 {
@@ -992,6 +997,24 @@ float* zen_hpr_state_ptr(zen_hpr* h, int which)
 // process_next_hop + copy_percussive pair.
 
 #include <chrono>
+
+// Host-only test hooks for the tagged-group format of the resident kernel's staging buffers (no device involved).
+// groups: 16-byte aligned, ceil(hop / 3) * 16 bytes.
+extern "C" int zen_rt_pack_groups(const float* src, int hop, unsigned tag, void* groups)
+{
+	if (!src || !groups || hop < 1 || ((uintptr_t)groups & 15)) return ZEN_ERR_ARG;
+	rt_pack_groups(src, hop, tag, static_cast<uint4*>(groups));
+	return ZEN_OK;
+}
+
+/* returns the number of groups unpacked (== ceil(hop / 3) when every group carries `tag`), negative on bad arguments */
+extern "C" int zen_rt_unpack_groups(const void* groups, int hop, unsigned tag, float* dst)
+{
+	if (!dst || !groups || hop < 1 || ((uintptr_t)groups & 15)) return ZEN_ERR_ARG;
+	int g = 0;
+	rt_unpack_groups(static_cast<const uint4*>(groups), hop, tag, dst, g);
+	return g;
+}
 
 extern "C" int zen_fakert_run(float fs, int hop, float beta, int options, const float* h_audio, long n_hops,
                               int warmup_iters, int fused, float* h_perc_out, double* h_us_per_hop)
