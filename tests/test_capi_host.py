@@ -97,7 +97,8 @@ def test_product_never_imports_the_oracle():
 def test_tagged_group_format_round_trip(hop):
     """the resident session's staging format {x[3g], x[3g+1], x[3g+2], tag} (hpr_launch.cuh RtCtrl): packing then
     unpacking is the identity for every hop length (vector body, scalar tail, ragged last group), every group carries
-    the tag, the padding of the last group is zero, and a single stale group stops the unpack exactly there"""
+    the tag (stored XOR a hash of its samples), the padding of the last group is zero, and a single stale or
+    half-written group stops the unpack exactly there"""
     import ctypes
     from zen_b200 import _lib
     L = _lib.lib()
@@ -114,7 +115,11 @@ def test_tagged_group_format_round_trip(hop):
     tag = (123456 << 8) | 0x61
     assert L.zen_rt_pack_groups(x.ctypes.data, hop, tag, g.ctypes.data) == 0
     gv = g.reshape(groups, 4)
-    assert np.all(gv[:, 3] == tag)
+
+    def rotl(v, n):
+        return ((v << np.uint32(n)) | (v >> np.uint32(32 - n))).astype(np.uint32)
+    # the tag word is stored XOR zen_group_hash(x0, x1, x2) (hpr_core.cuh): a group validates itself
+    assert np.all((gv[:, 3] ^ gv[:, 0] ^ rotl(gv[:, 1], 11) ^ rotl(gv[:, 2], 22)) == tag)
     flat = gv[:, :3].reshape(-1)
     assert np.array_equal(flat[:hop], x.view(np.uint32))    # bit patterns, -0.0 included
     assert np.all(flat[hop:] == 0)
@@ -128,7 +133,10 @@ def test_tagged_group_format_round_trip(hop):
         o2 = (-buf.ctypes.data // 4) % 4
         g2 = buf[o2:o2 + groups * 4]
         g2[:] = g
-        g2[4 * stale + 3] = tag - 256                       # the previous request's tag
+        if stale % 2 == 0:
+            g2[4 * stale + 3] ^= np.uint32((tag - 256) ^ tag)  # the previous request's tag on the same samples
+        else:
+            g2[4 * stale + 1] ^= np.uint32(1 << 7)          # a group caught half-written: a sample that does not belong to the tag word
         y2 = np.full(hop + 4, 7.0, np.float32)
         assert L.zen_rt_unpack_groups(g2.ctypes.data, hop, tag, y2.ctypes.data) == stale
         assert np.array_equal(y2[:3 * stale].view(np.uint32), x[:3 * stale].view(np.uint32))

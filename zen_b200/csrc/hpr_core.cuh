@@ -69,8 +69,15 @@ struct HprTables {
 };
 
 // Tagged emission of the resident real-time kernel: the emitted hop is also written to mapped host memory as
-// 16-byte groups {x[3g], x[3g+1], x[3g+2], tag}.  One group is one aligned 16-byte store, so the host sees a
-// group either old or complete and needs no completion flag behind a system-wide fence (rt_call, hpr_kernels.cu).
+// 16-byte groups {x[3g], x[3g+1], x[3g+2], tag ^ zen_group_hash(x)}.  One group is one aligned 16-byte store and
+// validates ITSELF: a reader that catches it half-way (new tag word, old samples, or the reverse - observed on the
+// host about once in a million groups when it reads a group the moment it lands) computes a tag that is not the one
+// it waits for and simply looks again.  No completion flag behind a system-wide fence is needed (rt_call, hpr_kernels.cu).
+__host__ __device__ __forceinline__ unsigned zen_group_hash(unsigned x0, unsigned x1, unsigned x2)
+{
+	return x0 ^ ((x1 << 11) | (x1 >> 21)) ^ ((x2 << 22) | (x2 >> 10));
+}
+
 struct HprPack {
 	float* buf;     // hop floats of shared memory
 	uint4* dst[3];  // per output (H, P, R) or null
@@ -310,7 +317,7 @@ __device__ __forceinline__ void hpr_ola_emit(const HprDev& P, const float2* zb, 
 			v.x = __float_as_uint(pbuf[3 * g]);
 			v.y = 3 * g + 1 < HOP ? __float_as_uint(pbuf[3 * g + 1]) : 0u;
 			v.z = 3 * g + 2 < HOP ? __float_as_uint(pbuf[3 * g + 2]) : 0u;
-			v.w = ptag;
+			v.w = ptag ^ zen_group_hash(v.x, v.y, v.z);
 			asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pdst + g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
 			             : "memory");
 		}

@@ -372,7 +372,7 @@ int rt_launch(zen_hpr* h)
 		h->rt_groups = groups;
 		// tags of the sequence number already served, so that a fresh kernel does not take stale groups for a request
 		for (int g = 0; g < groups; ++g)
-			h->rt_stage_in[g].w = h->rt_seq << 8;
+			h->rt_stage_in[g].w = h->rt_seq << 8;  // (samples zero: hash zero)
 	}
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	int it = (int)h->iter;
@@ -443,49 +443,84 @@ int rt_collect(zen_hpr* h)
 	return ZEN_OK;
 }
 
-// ---- tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag} (RtCtrl, hpr_launch.cuh), host side ----------------
-// pack `hop` samples into ceil(hop / 3) groups; one aligned 16-byte store per group
+// ---- tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag ^ zen_group_hash(x)} (RtCtrl, hpr_launch.cuh), host side ----
+inline __m128i rotl32(__m128i v, int n) { return _mm_or_si128(_mm_slli_epi32(v, n), _mm_srli_epi32(v, 32 - n)); }
+
+// zen_group_hash of the three sample lanes of one group, in every lane
+inline __m128i group_hash(__m128i g)
+{
+	return _mm_xor_si128(_mm_shuffle_epi32(g, _MM_SHUFFLE(0, 0, 0, 0)),
+	                     _mm_xor_si128(_mm_shuffle_epi32(rotl32(g, 11), _MM_SHUFFLE(1, 1, 1, 1)), _mm_shuffle_epi32(rotl32(g, 22), _MM_SHUFFLE(2, 2, 2, 2))));
+}
+
+// one group: the three samples of `x` (lane 3 ignored) and the hashed tag, one aligned 16-byte store
+inline void store_group(uint4* dst, __m128 x, __m128i tag_all)
+{
+	const __m128i keep = _mm_set_epi32(0, -1, -1, -1);
+	const __m128i g = _mm_and_si128(_mm_castps_si128(x), keep);
+	const __m128i w = _mm_andnot_si128(keep, _mm_xor_si128(group_hash(g), tag_all));
+	_mm_store_si128(reinterpret_cast<__m128i*>(dst), _mm_or_si128(g, w));
+}
+
+// the plain tag of a group as read (lane 3 XOR the hash of lanes 0-2); a half-written group gives neither the old nor the new tag
+inline unsigned group_tag(__m128i g)
+{
+	return (unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(_mm_xor_si128(g, group_hash(g)), 0xFF));
+}
+
+// pack `hop` samples into ceil(hop / 3) groups
 void rt_pack_groups(const float* src, int hop, unsigned tag, uint4* st)
 {
 	const int groups = (hop + 2) / 3;
-	const __m128 tagv = _mm_castsi128_ps(_mm_set_epi32((int)tag, 0, 0, 0));
-	const __m128 keep = _mm_castsi128_ps(_mm_set_epi32(0, -1, -1, -1));
+	const __m128i tagv = _mm_set1_epi32((int)tag);
 	const int full = (hop - 1) / 3;  // groups whose 16-byte read stays inside the hop (3g + 3 < hop)
 	int g = 0;
 	// four groups (twelve samples) per step: three loads, four aligned 16-byte stores
 	for (; g + 4 <= full && 3 * g + 12 <= hop; g += 4) {
 		const __m128 s0 = _mm_loadu_ps(src + 3 * g), s1 = _mm_loadu_ps(src + 3 * g + 4), s2 = _mm_loadu_ps(src + 3 * g + 8);
+		// the four hashes at once: gather the first / second / third samples of the four groups
+		const __m128 a0 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(2, 2, 3, 0));                             // x0 x3 x6 x6
+		const __m128 X0 = _mm_shuffle_ps(a0, _mm_shuffle_ps(a0, s2, _MM_SHUFFLE(1, 1, 2, 2)), _MM_SHUFFLE(2, 0, 1, 0));  // x0 x3 x6 x9
+		const __m128 a1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(3, 0, 1, 1));                             // x1 x1 x4 x7
+		const __m128 X1 = _mm_shuffle_ps(a1, _mm_shuffle_ps(a1, s2, _MM_SHUFFLE(2, 2, 3, 3)), _MM_SHUFFLE(2, 0, 2, 0));  // x1 x4 x7 x10
+		const __m128 X2 = _mm_shuffle_ps(_mm_shuffle_ps(s0, s1, _MM_SHUFFLE(1, 1, 2, 2)), _mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 0, 0)),
+		                                 _MM_SHUFFLE(2, 0, 2, 0));                                     // x2 x5 x8 x11
+		const __m128 W = _mm_castsi128_ps(_mm_xor_si128(_mm_xor_si128(tagv, _mm_castps_si128(X0)),
+		                                                _mm_xor_si128(rotl32(_mm_castps_si128(X1), 11), rotl32(_mm_castps_si128(X2), 22))));
+		// {a b c ?} + tag word k of W -> {a b c w}
+		auto with_tag = [&](__m128 grp, __m128 wk) { return _mm_shuffle_ps(grp, _mm_shuffle_ps(grp, wk, _MM_SHUFFLE(0, 0, 2, 2)), _MM_SHUFFLE(2, 0, 1, 0)); };
 		const __m128 t1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(0, 0, 3, 3));   // x3 x3 x4 x4
-		const __m128 g1 = _mm_shuffle_ps(t1, s1, _MM_SHUFFLE(3, 1, 2, 0));   // x3 x4 x5 (x7)
-		const __m128 g2 = _mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2));   // x6 x7 x8 (x9)
-		const __m128 g3 = _mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 2, 1));   // x9 x10 x11 (x11)
-		_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(s0, keep), tagv));
-		_mm_store_ps(reinterpret_cast<float*>(st + g + 1), _mm_or_ps(_mm_and_ps(g1, keep), tagv));
-		_mm_store_ps(reinterpret_cast<float*>(st + g + 2), _mm_or_ps(_mm_and_ps(g2, keep), tagv));
-		_mm_store_ps(reinterpret_cast<float*>(st + g + 3), _mm_or_ps(_mm_and_ps(g3, keep), tagv));
+		_mm_store_ps(reinterpret_cast<float*>(st + g), with_tag(s0, _mm_shuffle_ps(W, W, _MM_SHUFFLE(0, 0, 0, 0))));
+		_mm_store_ps(reinterpret_cast<float*>(st + g + 1), with_tag(_mm_shuffle_ps(t1, s1, _MM_SHUFFLE(3, 1, 2, 0)), _mm_shuffle_ps(W, W, _MM_SHUFFLE(1, 1, 1, 1))));
+		_mm_store_ps(reinterpret_cast<float*>(st + g + 2), with_tag(_mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2)), _mm_shuffle_ps(W, W, _MM_SHUFFLE(2, 2, 2, 2))));
+		_mm_store_ps(reinterpret_cast<float*>(st + g + 3), with_tag(_mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 2, 1)), _mm_shuffle_ps(W, W, _MM_SHUFFLE(3, 3, 3, 3))));
 	}
 	for (; g < full; ++g)
-		_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_loadu_ps(src + 3 * g), keep), tagv));
+		store_group(st + g, _mm_loadu_ps(src + 3 * g), tagv);
 	for (; g < groups; ++g) {
 		float x0 = src[3 * g], x1 = 3 * g + 1 < hop ? src[3 * g + 1] : 0.0f, x2 = 3 * g + 2 < hop ? src[3 * g + 2] : 0.0f;
-		_mm_store_ps(reinterpret_cast<float*>(st + g), _mm_or_ps(_mm_and_ps(_mm_set_ps(0.0f, x2, x1, x0), keep), tagv));
+		store_group(st + g, _mm_set_ps(0.0f, x2, x1, x0), tagv);
 	}
 }
 
 // Unpack the groups that carry `tag` into dst, starting at group g (updated); true when the whole hop is out, false at
-// the first group that is still old.
+// the first group that is still old (or caught half-written).
 bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g)
 {
 	const int groups = (hop + 2) / 3;
 	const int full = hop / 3;  // groups with three samples
-	// four groups per step: one tag comparison, three 16-byte stores
+	// four groups per step: transpose, one hash + tag comparison for the four, three 16-byte stores
 	const __m128i tagv = _mm_set1_epi32((int)tag);
 	for (; g + 4 <= full; g += 4) {
 		const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g)), b = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 1));
 		const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 2)), d = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 3));
-		const __m128i tags = _mm_unpackhi_epi64(_mm_unpackhi_epi32(a, b), _mm_unpackhi_epi32(c, d));  // a3 b3 c3 d3
+		const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);   // a0 b0 a1 b1 | a2 b2 a3 b3
+		const __m128i cd_lo = _mm_unpacklo_epi32(c, d), cd_hi = _mm_unpackhi_epi32(c, d);
+		const __m128i x0 = _mm_unpacklo_epi64(ab_lo, cd_lo), x1 = _mm_unpackhi_epi64(ab_lo, cd_lo);   // a0 b0 c0 d0 | a1 b1 c1 d1
+		const __m128i x2 = _mm_unpacklo_epi64(ab_hi, cd_hi), w = _mm_unpackhi_epi64(ab_hi, cd_hi);    // a2 b2 c2 d2 | a3 b3 c3 d3
+		const __m128i tags = _mm_xor_si128(_mm_xor_si128(w, x0), _mm_xor_si128(rotl32(x1, 11), rotl32(x2, 22)));
 		if (_mm_movemask_epi8(_mm_cmpeq_epi32(tags, tagv)) != 0xffff)
-			break;  // the scalar loop below finds the group that is still old
+			break;  // the scalar loop below finds the group that is not there yet
 		const __m128 fa = _mm_castsi128_ps(a), fb = _mm_castsi128_ps(b), fc = _mm_castsi128_ps(c), fd = _mm_castsi128_ps(d);
 		const __m128 t0 = _mm_shuffle_ps(fa, fb, _MM_SHUFFLE(0, 0, 2, 2));   // a2 a2 b0 b0
 		const __m128 t2 = _mm_shuffle_ps(fc, fd, _MM_SHUFFLE(0, 0, 2, 2));   // c2 c2 d0 d0
@@ -495,7 +530,7 @@ bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g
 	}
 	for (; g < full; ++g) {
 		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
-		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
+		if (group_tag(v) != tag)
 			return false;
 		// three floats; the fourth lane would spill into the next group's slot of dst, so store 8 + 4 bytes
 		_mm_storel_pi(reinterpret_cast<__m64*>(dst + 3 * g), _mm_castsi128_ps(v));
@@ -503,7 +538,7 @@ bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g
 	}
 	for (; g < groups; ++g) {
 		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
-		if ((unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(v, 0xFF)) != tag)
+		if (group_tag(v) != tag)
 			return false;
 		alignas(16) float t[4];
 		_mm_store_ps(t, _mm_castsi128_ps(v));
@@ -520,8 +555,8 @@ void rt_publish(zen_hpr* h, unsigned tag, const float* src)
 	if (src)
 		rt_pack_groups(src, h->hop, tag, st);
 	else
-		for (int g = 0; g < h->rt_groups; ++g)
-			*reinterpret_cast<volatile unsigned*>(&st[g].w) = tag;
+		for (int g = 0; g < h->rt_groups; ++g)  // no samples: {0, 0, 0, tag} (the hash of zeros is zero)
+			_mm_store_si128(reinterpret_cast<__m128i*>(st + g), _mm_set_epi32((int)tag, 0, 0, 0));
 }
 
 bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
@@ -534,7 +569,7 @@ bool rt_tags_ready(const zen_hpr* h, int o, unsigned tag)
 {
 	const uint4* st = h->rt_stage_out[o];
 	for (int g = 0; g < h->rt_groups; ++g)
-		if (*reinterpret_cast<volatile const unsigned*>(&st[g].w) != tag)
+		if (group_tag(_mm_load_si128(reinterpret_cast<const __m128i*>(st + g))) != tag)
 			return false;
 	return true;
 }
@@ -544,7 +579,7 @@ int rt_wait(zen_hpr* h, unsigned op, unsigned& opw, unsigned& tag, unsigned targ
 {
 	RtCtrl* c = h->rt_ctrl;
 	const bool any_out = wait_out[0] || wait_out[1] || wait_out[2];
-	const auto t0 = std::chrono::steady_clock::now();
+	std::chrono::steady_clock::time_point t0;  // taken at the first check-point (a hop is over long before)
 	unsigned spins = 0;
 	// The kernel emits P, H, R in that order (hps.cu:498-579): watch the last group of the last output, then take
 	// everything.  Two alternatives were measured and dropped: unpacking each group the moment its tag shows up gave
@@ -556,18 +591,14 @@ int rt_wait(zen_hpr* h, unsigned op, unsigned& opw, unsigned& tag, unsigned targ
 	int last_o = -1;
 	if (any_out) last_o = wait_out[2] ? 2 : (wait_out[0] ? 0 : 1);
 	for (;;) {
+		asm volatile("" ::: "memory");  // the staging buffers change under us: reload them every time round
 		if (any_out) {
-			if (*reinterpret_cast<volatile unsigned*>(&h->rt_stage_out[last_o][h->rt_groups - 1].w) == tag) {
+			if (group_tag(_mm_load_si128(reinterpret_cast<const __m128i*>(&h->rt_stage_out[last_o][h->rt_groups - 1]))) == tag) {
 				if (t_seen) *t_seen = std::chrono::steady_clock::now();
 				bool ok = true;
 				for (int o = 0; o < 3 && ok; ++o) {
 					prog[o] = 0;
 					if (wait_out[o]) ok = dst[o] ? rt_unpack(h, o, tag, dst[o], prog[o]) : rt_tags_ready(h, o, tag);
-				}
-				// the groups that arrived last are read once more, half a microsecond after their tags were first seen
-				for (int o = 0; o < 3 && ok; ++o) {
-					prog[o] = h->rt_groups > 16 ? h->rt_groups - 16 : 0;
-					if (wait_out[o] && dst[o]) ok = rt_unpack(h, o, tag, dst[o], prog[o]);
 				}
 				if (ok) break;
 			}
@@ -596,6 +627,7 @@ int rt_wait(zen_hpr* h, unsigned op, unsigned& opw, unsigned& tag, unsigned targ
 					if (op == RT_OP_STOP) break;
 				}
 			}
+			if (spins == 1024u) t0 = std::chrono::steady_clock::now();
 			if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
 				std::fprintf(stderr, "zen_b200: the resident real-time kernel did not answer within 5 s\n");
 				return ZEN_ERR_CUDA;
@@ -683,12 +715,12 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 		h->rt_last_tagged[0] = h->rt_last_tagged[1] = h->rt_last_tagged[2] = false;  // the staging buffers are about to change
 	}
 	unsigned tag = (target << 8) | opw;
-	const auto tr0 = std::chrono::steady_clock::now();
+	std::chrono::steady_clock::time_point tr0, tr1, tr2;
+	if (h->rt_trace) tr0 = std::chrono::steady_clock::now();
 	c->op = opw;
 	_mm_sfence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
 	rt_publish(h, tag, push_src);
-	const auto tr1 = std::chrono::steady_clock::now();
-	auto tr2 = tr1;
+	if (h->rt_trace) tr2 = tr1 = std::chrono::steady_clock::now();
 	if (defer) {
 		auto& p = h->rt_pend;
 		p.active = true;

@@ -55,7 +55,7 @@ struct HopArgs {
 // Control block of the persistent real-time kernel, in mapped pinned host memory.
 //
 // Host -> device.  A request is published by TAGGING the staging buffer `stage_in`: ceil(hop/3) groups of
-// 16 bytes {x[3g], x[3g+1], x[3g+2], tag}, tag = (sequence number << 8) | op bits.  The CTA's threads poll
+// 16 bytes {x[3g], x[3g+1], x[3g+2], tag ^ zen_group_hash(x)}, tag = (sequence number << 8) | op bits.  The CTA's threads poll
 // their own groups, so with RT_F_PUSH_IN the doorbell and the samples arrive in the SAME PCIe round trip
 // (a doorbell word followed by a read of the hop costs two).  A group is written with one aligned 16-byte
 // store and read with one 16-byte load, so it is seen either old or complete.  Arguments that changed since
@@ -436,7 +436,12 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 						             : "=r"(v[b].x), "=r"(v[b].y), "=r"(v[b].z), "=r"(v[b].w)
 						             : "l"(stage_in + tid + b * NT)
 						             : "memory");
-						if ((v[b].w ^ want) <= 0xffu) pending &= ~(1u << b);
+						// the tag word is stored XOR a hash of the samples: a group caught half-written does not match
+						const unsigned t = v[b].w ^ zen_group_hash(v[b].x, v[b].y, v[b].z);
+						if ((t ^ want) <= 0xffu) {
+							pending &= ~(1u << b);
+							v[b].w = t;
+						}
 					}
 				}
 				got = pending == 0u;
