@@ -118,8 +118,19 @@ def test_tagged_group_format_round_trip(hop):
 
     def rotl(v, n):
         return ((v << np.uint32(n)) | (v >> np.uint32(32 - n))).astype(np.uint32)
-    # the tag word is stored XOR zen_group_hash(x0, x1, x2) (hpr_core.cuh): a group validates itself
-    assert np.all((gv[:, 3] ^ gv[:, 0] ^ rotl(gv[:, 1], 11) ^ rotl(gv[:, 2], 22)) == tag)
+    # The tag words are stored XOR a hash of the samples (zen_group_key, hpr_core.cuh): the four groups of a whole
+    # 64-byte line share the line hash V[l] = y[l] ^ rotl(y[4+l], 11) ^ rotl(y[8+l], 22) of their twelve samples, the
+    # groups behind the last whole line use zen_group_hash(x0, x1, x2).  Either way a group validates itself.
+    xu = np.zeros(groups * 3, np.uint32)
+    xu[:hop] = x.view(np.uint32)
+    lg = 4 * (hop // 12)
+    key = np.zeros(groups, np.uint32)
+    for b in range(lg // 4):
+        y = xu[12 * b:12 * b + 12]
+        key[4 * b:4 * b + 4] = y[0:4] ^ rotl(y[4:8], 11) ^ rotl(y[8:12], 22)
+    t = xu[3 * lg:].reshape(-1, 3)
+    key[lg:] = t[:, 0] ^ rotl(t[:, 1], 11) ^ rotl(t[:, 2], 22)
+    assert np.all((gv[:, 3] ^ key) == tag)
     flat = gv[:, :3].reshape(-1)
     assert np.array_equal(flat[:hop], x.view(np.uint32))    # bit patterns, -0.0 included
     assert np.all(flat[hop:] == 0)
@@ -138,7 +149,8 @@ def test_tagged_group_format_round_trip(hop):
         else:
             g2[4 * stale + 1] ^= np.uint32(1 << 7)          # a group caught half-written: a sample that does not belong to the tag word
         y2 = np.full(hop + 4, 7.0, np.float32)
-        assert L.zen_rt_unpack_groups(g2.ctypes.data, hop, tag, y2.ctypes.data) == stale
-        assert np.array_equal(y2[:3 * stale].view(np.uint32), x[:3 * stale].view(np.uint32))
-        assert np.all(y2[3 * stale:] == 7.0)                # nothing of the stale group or behind it was written
+        stop = 4 * (stale // 4) if stale < lg else stale     # a whole line is taken or left
+        assert L.zen_rt_unpack_groups(g2.ctypes.data, hop, tag, y2.ctypes.data) == stop
+        assert np.array_equal(y2[:3 * stop].view(np.uint32), x[:3 * stop].view(np.uint32))
+        assert np.all(y2[3 * stop:] == 7.0)                 # nothing of the stale line / group or behind it was written
     assert L.zen_rt_pack_groups(x.ctypes.data, hop, tag, g.ctypes.data + 4) != 0   # misaligned staging buffer

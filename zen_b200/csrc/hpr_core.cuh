@@ -77,6 +77,50 @@ __host__ __device__ __forceinline__ unsigned zen_group_hash(unsigned x0, unsigne
 {
 	return x0 ^ ((x1 << 11) | (x1 >> 21)) ^ ((x2 << 22) | (x2 >> 10));
 }
+// What a group's tag word is XORed with.  The four groups of a whole 64-byte line (twelve samples y0..y11, all inside
+// the hop: groups below n_line_groups = 4 * (hop / 12)) share one LINE hash, V[l] = y[l] ^ rotl(y[4+l], 11) ^
+// rotl(y[8+l], 22), and group q carries tag ^ V[q]: on the host that is three vertical vector operations on the twelve
+// samples as they lie in memory (the per-group hash needs a transpose, and the shuffle port is what bounds the host's
+// pack / unpack loops).  Every sample of the line is in exactly one V[l], so the line is good when its four tag words
+// are.  The few groups behind the last whole line use zen_group_hash.  Must be called by all 32 lanes of the warp; the
+// four groups of a line sit in four consecutive lanes.
+__device__ __forceinline__ unsigned zen_group_key(unsigned x0, unsigned x1, unsigned x2, int g, int n_line_groups)
+{
+	auto r11 = [](unsigned v) { return (v << 11) | (v >> 21); };
+	auto r22 = [](unsigned v) { return (v << 22) | (v >> 10); };
+	const int q = g & 3;
+	// this group holds y[3q], y[3q+1], y[3q+2]: their contributions to V[0..3]
+	unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+	if (q == 0) {
+		c0 = x0;
+		c1 = x1;
+		c2 = x2;
+	}
+	else if (q == 1) {
+		c3 = x0;
+		c0 = r11(x1);
+		c1 = r11(x2);
+	}
+	else if (q == 2) {
+		c2 = r11(x0);
+		c3 = r11(x1);
+		c0 = r22(x2);
+	}
+	else {
+		c1 = r22(x0);
+		c2 = r22(x1);
+		c3 = r22(x2);
+	}
+#pragma unroll
+	for (int m = 1; m <= 2; m <<= 1) {
+		c0 ^= __shfl_xor_sync(0xffffffffu, c0, m);
+		c1 ^= __shfl_xor_sync(0xffffffffu, c1, m);
+		c2 ^= __shfl_xor_sync(0xffffffffu, c2, m);
+		c3 ^= __shfl_xor_sync(0xffffffffu, c3, m);
+	}
+	const unsigned vq = q == 0 ? c0 : (q == 1 ? c1 : (q == 2 ? c2 : c3));
+	return g < n_line_groups ? vq : zen_group_hash(x0, x1, x2);
+}
 
 struct HprPack {
 	float* buf;     // hop floats of shared memory
@@ -312,14 +356,19 @@ __device__ __forceinline__ void hpr_ola_emit(const HprDev& P, const float2* zb, 
 	}
 	__syncthreads();
 	if (pdst) {
-		for (int g = tid; 3 * g < HOP; g += NT) {
-			uint4 v;
-			v.x = __float_as_uint(pbuf[3 * g]);
-			v.y = 3 * g + 1 < HOP ? __float_as_uint(pbuf[3 * g + 1]) : 0u;
-			v.z = 3 * g + 2 < HOP ? __float_as_uint(pbuf[3 * g + 2]) : 0u;
-			v.w = ptag ^ zen_group_hash(v.x, v.y, v.z);
-			asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pdst + g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-			             : "memory");
+		constexpr int NG = (HOP + 2) / 3, NLG = 4 * (HOP / 12);
+		for (int g0 = 0; g0 < NG; g0 += NT) {  // (every thread makes every trip: zen_group_key shuffles)
+			const int g = g0 + tid;
+			uint4 v = make_uint4(0u, 0u, 0u, 0u);
+			if (g < NG) {
+				v.x = __float_as_uint(pbuf[3 * g]);
+				v.y = 3 * g + 1 < HOP ? __float_as_uint(pbuf[3 * g + 1]) : 0u;
+				v.z = 3 * g + 2 < HOP ? __float_as_uint(pbuf[3 * g + 2]) : 0u;
+			}
+			v.w = ptag ^ zen_group_key(v.x, v.y, v.z, g, NLG);
+			if (g < NG)
+				asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pdst + g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+				             : "memory");
 		}
 	}
 	for (int n = HOP / 2 + tid; n < HOP; n += NT) {

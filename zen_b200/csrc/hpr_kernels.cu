@@ -468,25 +468,23 @@ inline unsigned group_tag(__m128i g)
 	return (unsigned)_mm_cvtsi128_si32(_mm_shuffle_epi32(_mm_xor_si128(g, group_hash(g)), 0xFF));
 }
 
+// the line hash of twelve samples as they lie in memory (zen_group_key, hpr_core.cuh): V[l] = y[l] ^ rotl(y[4+l], 11) ^ rotl(y[8+l], 22)
+inline __m128i line_hash(__m128 s0, __m128 s1, __m128 s2)
+{
+	return _mm_xor_si128(_mm_castps_si128(s0), _mm_xor_si128(rotl32(_mm_castps_si128(s1), 11), rotl32(_mm_castps_si128(s2), 22)));
+}
+
 // pack `hop` samples into ceil(hop / 3) groups
 void rt_pack_groups(const float* src, int hop, unsigned tag, uint4* st)
 {
 	const int groups = (hop + 2) / 3;
+	const int line_groups = 4 * (hop / 12);  // groups of whole 64-byte lines: tag words XOR the line hash
 	const __m128i tagv = _mm_set1_epi32((int)tag);
-	const int full = (hop - 1) / 3;  // groups whose 16-byte read stays inside the hop (3g + 3 < hop)
 	int g = 0;
-	// four groups (twelve samples) per step: three loads, four aligned 16-byte stores
-	for (; g + 4 <= full && 3 * g + 12 <= hop; g += 4) {
+	// a line (four groups, twelve samples) per step: three loads, four aligned 16-byte stores
+	for (; g < line_groups; g += 4) {
 		const __m128 s0 = _mm_loadu_ps(src + 3 * g), s1 = _mm_loadu_ps(src + 3 * g + 4), s2 = _mm_loadu_ps(src + 3 * g + 8);
-		// the four hashes at once: gather the first / second / third samples of the four groups
-		const __m128 a0 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(2, 2, 3, 0));                             // x0 x3 x6 x6
-		const __m128 X0 = _mm_shuffle_ps(a0, _mm_shuffle_ps(a0, s2, _MM_SHUFFLE(1, 1, 2, 2)), _MM_SHUFFLE(2, 0, 1, 0));  // x0 x3 x6 x9
-		const __m128 a1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(3, 0, 1, 1));                             // x1 x1 x4 x7
-		const __m128 X1 = _mm_shuffle_ps(a1, _mm_shuffle_ps(a1, s2, _MM_SHUFFLE(2, 2, 3, 3)), _MM_SHUFFLE(2, 0, 2, 0));  // x1 x4 x7 x10
-		const __m128 X2 = _mm_shuffle_ps(_mm_shuffle_ps(s0, s1, _MM_SHUFFLE(1, 1, 2, 2)), _mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 0, 0)),
-		                                 _MM_SHUFFLE(2, 0, 2, 0));                                     // x2 x5 x8 x11
-		const __m128 W = _mm_castsi128_ps(_mm_xor_si128(_mm_xor_si128(tagv, _mm_castps_si128(X0)),
-		                                                _mm_xor_si128(rotl32(_mm_castps_si128(X1), 11), rotl32(_mm_castps_si128(X2), 22))));
+		const __m128 W = _mm_castsi128_ps(_mm_xor_si128(tagv, line_hash(s0, s1, s2)));
 		// {a b c ?} + tag word k of W -> {a b c w}
 		auto with_tag = [&](__m128 grp, __m128 wk) { return _mm_shuffle_ps(grp, _mm_shuffle_ps(grp, wk, _MM_SHUFFLE(0, 0, 2, 2)), _MM_SHUFFLE(2, 0, 1, 0)); };
 		const __m128 t1 = _mm_shuffle_ps(s0, s1, _MM_SHUFFLE(0, 0, 3, 3));   // x3 x3 x4 x4
@@ -495,46 +493,35 @@ void rt_pack_groups(const float* src, int hop, unsigned tag, uint4* st)
 		_mm_store_ps(reinterpret_cast<float*>(st + g + 2), with_tag(_mm_shuffle_ps(s1, s2, _MM_SHUFFLE(1, 0, 3, 2)), _mm_shuffle_ps(W, W, _MM_SHUFFLE(2, 2, 2, 2))));
 		_mm_store_ps(reinterpret_cast<float*>(st + g + 3), with_tag(_mm_shuffle_ps(s2, s2, _MM_SHUFFLE(3, 3, 2, 1)), _mm_shuffle_ps(W, W, _MM_SHUFFLE(3, 3, 3, 3))));
 	}
-	for (; g < full; ++g)
-		store_group(st + g, _mm_loadu_ps(src + 3 * g), tagv);
+	// behind the last whole line: per-group hash
 	for (; g < groups; ++g) {
 		float x0 = src[3 * g], x1 = 3 * g + 1 < hop ? src[3 * g + 1] : 0.0f, x2 = 3 * g + 2 < hop ? src[3 * g + 2] : 0.0f;
 		store_group(st + g, _mm_set_ps(0.0f, x2, x1, x0), tagv);
 	}
 }
 
-// Unpack the groups that carry `tag` into dst, starting at group g (updated); true when the whole hop is out, false at
-// the first group that is still old (or caught half-written).
+// Unpack the groups that carry `tag` into dst, starting at group g (a multiple of four inside the whole lines;
+// updated); true when the whole hop is out, false at the first line / group that is still old or caught half-written.
 bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g)
 {
 	const int groups = (hop + 2) / 3;
-	const int full = hop / 3;  // groups with three samples
-	// four groups per step: transpose, one hash + tag comparison for the four, three 16-byte stores
+	const int line_groups = 4 * (hop / 12);
 	const __m128i tagv = _mm_set1_epi32((int)tag);
-	for (; g + 4 <= full; g += 4) {
+	for (; g < line_groups; g += 4) {
 		const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g)), b = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 1));
 		const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 2)), d = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g + 3));
-		const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);   // a0 b0 a1 b1 | a2 b2 a3 b3
-		const __m128i cd_lo = _mm_unpacklo_epi32(c, d), cd_hi = _mm_unpackhi_epi32(c, d);
-		const __m128i x0 = _mm_unpacklo_epi64(ab_lo, cd_lo), x1 = _mm_unpackhi_epi64(ab_lo, cd_lo);   // a0 b0 c0 d0 | a1 b1 c1 d1
-		const __m128i x2 = _mm_unpacklo_epi64(ab_hi, cd_hi), w = _mm_unpackhi_epi64(ab_hi, cd_hi);    // a2 b2 c2 d2 | a3 b3 c3 d3
-		const __m128i tags = _mm_xor_si128(_mm_xor_si128(w, x0), _mm_xor_si128(rotl32(x1, 11), rotl32(x2, 22)));
-		if (_mm_movemask_epi8(_mm_cmpeq_epi32(tags, tagv)) != 0xffff)
-			break;  // the scalar loop below finds the group that is not there yet
 		const __m128 fa = _mm_castsi128_ps(a), fb = _mm_castsi128_ps(b), fc = _mm_castsi128_ps(c), fd = _mm_castsi128_ps(d);
 		const __m128 t0 = _mm_shuffle_ps(fa, fb, _MM_SHUFFLE(0, 0, 2, 2));   // a2 a2 b0 b0
 		const __m128 t2 = _mm_shuffle_ps(fc, fd, _MM_SHUFFLE(0, 0, 2, 2));   // c2 c2 d0 d0
-		_mm_storeu_ps(dst + 3 * g, _mm_shuffle_ps(fa, t0, _MM_SHUFFLE(2, 0, 1, 0)));      // a0 a1 a2 b0
-		_mm_storeu_ps(dst + 3 * g + 4, _mm_shuffle_ps(fb, fc, _MM_SHUFFLE(1, 0, 2, 1)));  // b1 b2 c0 c1
-		_mm_storeu_ps(dst + 3 * g + 8, _mm_shuffle_ps(t2, fd, _MM_SHUFFLE(2, 1, 2, 0)));  // c2 d0 d1 d2
-	}
-	for (; g < full; ++g) {
-		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
-		if (group_tag(v) != tag)
-			return false;
-		// three floats; the fourth lane would spill into the next group's slot of dst, so store 8 + 4 bytes
-		_mm_storel_pi(reinterpret_cast<__m64*>(dst + 3 * g), _mm_castsi128_ps(v));
-		_mm_store_ss(dst + 3 * g + 2, _mm_movehl_ps(_mm_castsi128_ps(v), _mm_castsi128_ps(v)));
+		const __m128 s0 = _mm_shuffle_ps(fa, t0, _MM_SHUFFLE(2, 0, 1, 0));   // a0 a1 a2 b0
+		const __m128 s1 = _mm_shuffle_ps(fb, fc, _MM_SHUFFLE(1, 0, 2, 1));   // b1 b2 c0 c1
+		const __m128 s2 = _mm_shuffle_ps(t2, fd, _MM_SHUFFLE(2, 1, 2, 0));   // c2 d0 d1 d2
+		const __m128i w = _mm_unpackhi_epi64(_mm_unpackhi_epi32(a, b), _mm_unpackhi_epi32(c, d));  // a3 b3 c3 d3
+		if (_mm_movemask_epi8(_mm_cmpeq_epi32(_mm_xor_si128(w, line_hash(s0, s1, s2)), tagv)) != 0xffff)
+			return false;  // the line is taken as a whole or not at all
+		_mm_storeu_ps(dst + 3 * g, s0);
+		_mm_storeu_ps(dst + 3 * g + 4, s1);
+		_mm_storeu_ps(dst + 3 * g + 8, s2);
 	}
 	for (; g < groups; ++g) {
 		const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(st + g));
@@ -542,10 +529,23 @@ bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g
 			return false;
 		alignas(16) float t[4];
 		_mm_store_ps(t, _mm_castsi128_ps(v));
-		for (int j = 0; 3 * g + j < hop; ++j)
+		for (int j = 0; j < 3 && 3 * g + j < hop; ++j)
 			dst[3 * g + j] = t[j];
 	}
 	return true;
+}
+
+// the last group of the hop carries `tag` (validated with its line when it belongs to one)
+bool rt_last_group_ready(const uint4* st, int hop, unsigned tag)
+{
+	const int groups = (hop + 2) / 3, line_groups = 4 * (hop / 12);
+	if (groups > line_groups)
+		return group_tag(_mm_load_si128(reinterpret_cast<const __m128i*>(st + groups - 1))) == tag;
+	alignas(16) float scratch[12];
+	int g = groups - 4;
+	const uint4* line = st + g;
+	int g0 = 0;
+	return rt_unpack_groups(line, 12, tag, scratch, g0);
 }
 
 // publish one request: tag every group of the staging buffer; with `src` the groups carry the hop
@@ -567,11 +567,10 @@ bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
 // all groups of output o carry `tag`
 bool rt_tags_ready(const zen_hpr* h, int o, unsigned tag)
 {
-	const uint4* st = h->rt_stage_out[o];
-	for (int g = 0; g < h->rt_groups; ++g)
-		if (group_tag(_mm_load_si128(reinterpret_cast<const __m128i*>(st + g))) != tag)
-			return false;
-	return true;
+	static thread_local std::vector<float> scratch;
+	if ((int)scratch.size() < h->hop) scratch.resize((size_t)h->hop);
+	int g = 0;
+	return rt_unpack_groups(h->rt_stage_out[o], h->hop, tag, scratch.data(), g);
 }
 
 int rt_wait(zen_hpr* h, unsigned op, unsigned& opw, unsigned& tag, unsigned target, const float* push_src, const bool wait_out[3],
@@ -593,7 +592,7 @@ int rt_wait(zen_hpr* h, unsigned op, unsigned& opw, unsigned& tag, unsigned targ
 	for (;;) {
 		asm volatile("" ::: "memory");  // the staging buffers change under us: reload them every time round
 		if (any_out) {
-			if (group_tag(_mm_load_si128(reinterpret_cast<const __m128i*>(&h->rt_stage_out[last_o][h->rt_groups - 1]))) == tag) {
+			if (rt_last_group_ready(h->rt_stage_out[last_o], h->hop, tag)) {
 				if (t_seen) *t_seen = std::chrono::steady_clock::now();
 				bool ok = true;
 				for (int o = 0; o < 3 && ok; ++o) {

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	constexpr int M = NFFT / 2, HOP = M / 2;
 	constexpr int NG = (HOP + 2) / 3;        // tagged groups per hop
 	constexpr int PER = (NG + NT - 1) / NT;  // groups polled by one thread
+	constexpr int NLG = 4 * (HOP / 12);      // groups that belong to a whole 64-byte line (zen_group_key)
 	constexpr int US = rt_us_for<NFFT, NT>();
 	(void)US;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -417,10 +418,12 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			// hop and the command to the other CTAs through distributed shared memory.
 			const unsigned want = (seq + 1u) << 8;
 			uint4 v[PER];
+			unsigned w_raw[PER];
 			unsigned pending = 0u;
 #pragma unroll
 			for (int b = 0; b < PER; ++b) {
 				v[b] = make_uint4(0u, 0u, 0u, ~want);
+				w_raw[b] = ~want;
 				if (tid + b * NT < NG) pending |= 1u << b;
 			}
 			bool got = pending == 0u;
@@ -431,17 +434,30 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			for (;;) {
 #pragma unroll
 				for (int b = 0; b < PER; ++b) {
-					if (pending & (1u << b)) {
+					if (pending & (1u << b))
 						asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-						             : "=r"(v[b].x), "=r"(v[b].y), "=r"(v[b].z), "=r"(v[b].w)
+						             : "=r"(v[b].x), "=r"(v[b].y), "=r"(v[b].z), "=r"(w_raw[b])
 						             : "l"(stage_in + tid + b * NT)
 						             : "memory");
-						// the tag word is stored XOR a hash of the samples: a group caught half-written does not match
-						const unsigned t = v[b].w ^ zen_group_hash(v[b].x, v[b].y, v[b].z);
-						if ((t ^ want) <= 0xffu) {
-							pending &= ~(1u << b);
-							v[b].w = t;
-						}
+				}
+#pragma unroll
+				for (int b = 0; b < PER; ++b) {
+					// The tag word is stored XOR a hash of the samples (zen_group_key: per 64-byte line, per group behind
+					// the last whole line): a group caught half-written does not match.  A line is taken as a whole.
+					const int g = tid + b * NT;
+					const unsigned t = w_raw[b] ^ zen_group_key(v[b].x, v[b].y, v[b].z, g, NLG);
+					unsigned ok = ((t ^ want) <= 0xffu) ? 1u : 0u;
+					if (g < NLG) {
+						ok &= __shfl_xor_sync(0xffffffffu, ok, 1);
+						ok &= __shfl_xor_sync(0xffffffffu, ok, 2);
+					}
+					else {
+						(void)__shfl_xor_sync(0xffffffffu, ok, 1);
+						(void)__shfl_xor_sync(0xffffffffu, ok, 2);
+					}
+					if ((pending & (1u << b)) && ok) {
+						pending &= ~(1u << b);
+						v[b].w = t;
 					}
 				}
 				got = pending == 0u;
