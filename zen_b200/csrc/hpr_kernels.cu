@@ -411,6 +411,12 @@ int rt_launch(zen_hpr* h)
 		a.cluster = (can_split && rt_smem_bytes<N>(a.dev, 3, h->rt_cluster) <= limit) ? h->rt_cluster : 1; \
 		a.state_in_smem = rt_smem_bytes<N>(a.dev, 3, a.cluster) <= limit ? 3 : (rt_smem_bytes<N>(a.dev, 1, 1) <= limit ? 1 : (rt_smem_bytes<N>(a.dev, 2, 1) <= limit ? 2 : 0)); \
 		rc = launch_rt_impl<N>(a);                                                \
+		if (rc != ZEN_OK && a.cluster > 1) { /* no room for a cluster (partitioned GPU, SMs taken): one CTA serves the stream */ \
+			cudaGetLastError();                                                   \
+			a.cluster = 1;                                                        \
+			a.state_in_smem = rt_smem_bytes<N>(a.dev, 3, 1) <= limit ? 3 : (rt_smem_bytes<N>(a.dev, 1, 1) <= limit ? 1 : (rt_smem_bytes<N>(a.dev, 2, 1) <= limit ? 2 : 0)); \
+			rc = launch_rt_impl<N>(a);                                            \
+		}                                                                         \
 		break;
 	switch (h->plan.nfft) {
 		ZEN_RT_CASE(128)

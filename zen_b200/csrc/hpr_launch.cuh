@@ -58,12 +58,14 @@ struct HopArgs {
 // 16 bytes {x[3g], x[3g+1], x[3g+2], tag ^ zen_group_hash(x)}, tag = (sequence number << 8) | op bits.  The CTA's threads poll
 // their own groups, so with RT_F_PUSH_IN the doorbell and the samples arrive in the SAME PCIe round trip
 // (a doorbell word followed by a read of the hop costs two).  A group is written with one aligned 16-byte
-// store and read with one 16-byte load, so it is seen either old or complete.  Arguments that changed since
+// store and read with one 16-byte load, and it validates itself: its tag word carries a hash of its samples
+// (zen_group_key), so a group caught half-written is never taken for a new one.  Arguments that changed since
 // the previous request (RT_F_NEW_ARGS) are written to this block BEFORE the tags.
 // Device -> host.  With RT_F_TAG_OUT every emitted hop is written as tagged groups to stage_out[o] and the
-// host unpacks it as soon as all tags match; seq_out (behind a system-wide fence) completes everything else.
+// host unpacks it once the last group is in and every group checks out; seq_out (a release store) completes
+// everything else.
 struct RtCtrl {
-	volatile unsigned seq_in;      // unused by the tagged protocol (kept for diagnostics)
+	volatile unsigned seq_in;      // unused (the tags are the doorbell)
 	volatile unsigned op;
 	const float* in;               // device-visible pointer to the incoming hop (when it is not pushed)
 	float* out[3];                 // device-visible destinations of the emitted hop (H, P, R) or null (when not tagged)
