@@ -20,6 +20,7 @@
 #define ZEN_B200_H
 
 #include <stddef.h>
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -136,6 +137,15 @@ int zen_hpr_synchronize(zen_hpr* h);
  * transfers (the kernel then reads the hop itself: one more PCIe round trip). */
 int zen_hpr_realtime_begin(zen_hpr* h);
 int zen_hpr_realtime_end(zen_hpr* h);
+/* The on-disk format either side of the path, batched on the device (device pointers; rows = independent streams).
+ * zen_pcm16_decode_mono: PCM16 mono or interleaved stereo -> float32 mono exactly as libnyquist decodes it for
+ * zen offline / fakert: (float)s / 32767.f (vendor/libnyquist/include/libnyquist/Common.h:296-302), stereo folded
+ * with (l + r) / 2.0f (Common.h:669-675; zen/offline.h:104-117, zen/fakert.h:117-130).  Strides in elements.
+ * zen_pcm16_encode_normalized: what the command line writes: x / max(-min, max) (zen/offline.h:180-192,
+ * zen/fakert.h:259-268), then (int16_t)lroundf(x * 32767.f), no dither (vendor/libnyquist/src/Common.cpp:332-337);
+ * d_peaks[n_streams] receives the peaks.  A silent stream (peak 0, where the reference divides by zero) stays silent. */
+int zen_pcm16_decode_mono(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out, long out_stride);
+int zen_pcm16_encode_normalized(const float* d_in, long in_stride, int n_streams, long n, int16_t* d_out, long out_stride, float* d_peaks);
 /* host-only test hooks for the tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag} the resident session exchanges with
  * its kernel (no device involved).  groups: 16-byte aligned, ceil(hop / 3) * 16 bytes.  zen_rt_unpack_groups returns
  * the number of leading groups that carried `tag` and were unpacked. */

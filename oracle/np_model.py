@@ -131,3 +131,35 @@ def hpr_geometry(fs: float, hop: int, causal: bool):
     l_perc = int(np.floor(np.float32(500.0) / np.float32(fs32 / np.float32(nfft)) + np.float32(0.5)))
     lag = 1 if causal else l_harm
     return dict(nwin=nwin, nfft=nfft, l_harm=l_harm, l_perc=l_perc, lag=lag, stft_width=2 * l_harm)
+
+
+# ---- the on-disk format either side of the path ------------------------------
+# /root/reference/vendor/libnyquist/include/libnyquist/Common.h:296-302 (int16_to_float32, float32_to_int16),
+# Common.h:669-675 (StereoToMono), vendor/libnyquist/src/Common.cpp:332-337 (lroundf, no dither),
+# /root/reference/zen/offline.h:104-117, 180-192 and zen/fakert.h:117-130, 259-268 (mono fold, peak normalisation).
+
+def pcm16_decode_mono(pcm, channels):
+    """int16 [n_frames * channels] (interleaved) -> float32 [n_frames]: (float)s / 32767.f, stereo as (l + r) / 2.0f"""
+    f = pcm.astype(np.float32) / np.float32(32767.0)
+    if channels == 2:
+        f = (f[0::2] + f[1::2]) / np.float32(2.0)
+    return f.astype(np.float32)
+
+
+def lroundf(v):
+    """C lroundf on float32 values: nearest integer, halfway cases away from zero"""
+    v64 = v.astype(np.float64)
+    return np.trunc(v64 + np.copysign(0.5, v64)).astype(np.int64)
+
+
+def pcm16_encode_normalized(x):
+    """float32 [n] -> (int16 [n], peak): x / max(-min, max), then (int16_t)lroundf(x * 32767.f).
+    A silent signal (peak 0: the reference divides by zero) stays silent - the one deliberate difference."""
+    x = x.astype(np.float32)
+    if x.size == 0:
+        return np.zeros(0, np.int16), np.float32(0.0)
+    peak = np.float32(max(-x.min(), x.max()))
+    if not peak > 0:
+        return np.zeros(x.size, np.int16), np.float32(0.0)
+    y = (x / peak).astype(np.float32) * np.float32(32767.0)
+    return lroundf(y.astype(np.float32)).astype(np.int16), peak

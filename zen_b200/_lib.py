@@ -43,7 +43,7 @@ EXPORTS = [
     "zen_hpr_batch_create", "zen_hpr_batch_destroy", "zen_hpr_batch_process", "zen_hpr_batch_process_host",
     "zen_hpr_batch_last_launches", "zen_hpr_batch_last_kernel_ms", "zen_offline_process",
     "zen_offline_process_device", "zen_copy_to_host", "zen_copy_to_device", "zen_fakert_run", "zen_host_alloc", "zen_host_free", "zen_hpr_bind_state", "zen_hpr_realtime_begin", "zen_hpr_realtime_end", "zen_hpr_realtime_stamps",
-    "zen_rt_pack_groups", "zen_rt_unpack_groups",
+    "zen_rt_pack_groups", "zen_rt_unpack_groups", "zen_pcm16_decode_mono", "zen_pcm16_encode_normalized",
 ]
 
 _lib = None
@@ -64,6 +64,8 @@ def lib():
     L.zen_io_alloc.argtypes = [ctypes.POINTER(ZenIO), ctypes.c_size_t]
     L.zen_io_free.argtypes = [ctypes.POINTER(ZenIO)]
     L.zen_io_free.restype = None
+    L.zen_pcm16_decode_mono.argtypes = [vp, cl, ci, ci, cl, vp, cl]
+    L.zen_pcm16_encode_normalized.argtypes = [vp, cl, ci, cl, vp, cl, vp]
     L.zen_median_filter.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp]
     L.zen_box_filter.argtypes = [ci, ci, ci, ci, vp, vp, vp]
     L.zen_fft_c2c.argtypes = [ci, vp, ci, vp]

@@ -364,3 +364,27 @@ class HPRBatch:
     @property
     def last_launches(self):
         return int(_lib.lib().zen_hpr_batch_last_launches(self._b))
+
+
+def pcm16_decode_mono(pcm, channels=1):
+    """batched libnyquist decode (Common.h:296-302, 669-675): int16 CUDA tensor [n_streams, n_frames * channels]
+    (interleaved) -> float32 CUDA tensor [n_streams, n_frames]"""
+    torch = _torch()
+    assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.dim() == 2 and pcm.stride(1) == 1
+    n_streams, n_frames = pcm.shape[0], pcm.shape[1] // channels
+    out = torch.empty((n_streams, n_frames), dtype=torch.float32, device=pcm.device)
+    check(_lib.lib().zen_pcm16_decode_mono(pcm.data_ptr(), pcm.stride(0), channels, n_streams, n_frames, out.data_ptr(), max(1, out.stride(0))),
+          "zen_pcm16_decode_mono")
+    return out
+
+
+def pcm16_encode_normalized(x):
+    """batched peak normalisation + PCM16 encode as the zen command line writes its outputs (zen/offline.h:180-192,
+    libnyquist Common.cpp:332-337): float32 CUDA tensor [n_streams, n] -> (int16 [n_streams, n], float32 peaks [n_streams])"""
+    torch = _torch()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    peaks = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    check(_lib.lib().zen_pcm16_encode_normalized(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), max(1, out.stride(0)),
+                                                 peaks.data_ptr()), "zen_pcm16_encode_normalized")
+    return out, peaks
