@@ -373,6 +373,8 @@ def pcm16_decode_mono(pcm, channels=1):
     assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.dim() == 2 and pcm.stride(1) == 1
     n_streams, n_frames = pcm.shape[0], pcm.shape[1] // channels
     out = torch.empty((n_streams, n_frames), dtype=torch.float32, device=pcm.device)
+    if n_frames == 0:
+        return out
     check(_lib.lib().zen_pcm16_decode_mono(pcm.data_ptr(), pcm.stride(0), channels, n_streams, n_frames, out.data_ptr(), max(1, out.stride(0))),
           "zen_pcm16_decode_mono")
     return out
@@ -384,7 +386,9 @@ def pcm16_encode_normalized(x):
     torch = _torch()
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
-    peaks = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    peaks = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
+    if x.shape[1] == 0:
+        return out, peaks
     check(_lib.lib().zen_pcm16_encode_normalized(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), max(1, out.stride(0)),
                                                  peaks.data_ptr()), "zen_pcm16_encode_normalized")
     return out, peaks
