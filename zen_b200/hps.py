@@ -370,7 +370,7 @@ def pcm16_decode_mono(pcm, channels=1):
     """batched libnyquist decode (Common.h:296-302, 669-675): int16 CUDA tensor [n_streams, n_frames * channels]
     (interleaved) -> float32 CUDA tensor [n_streams, n_frames]"""
     torch = _torch()
-    assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.dim() == 2 and pcm.stride(1) == 1
+    assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.dim() == 2 and (pcm.shape[1] == 0 or pcm.stride(1) == 1)
     n_streams, n_frames = pcm.shape[0], pcm.shape[1] // channels
     out = torch.empty((n_streams, n_frames), dtype=torch.float32, device=pcm.device)
     if n_frames == 0:
@@ -384,7 +384,7 @@ def pcm16_encode_normalized(x):
     """batched peak normalisation + PCM16 encode as the zen command line writes its outputs (zen/offline.h:180-192,
     libnyquist Common.cpp:332-337): float32 CUDA tensor [n_streams, n] -> (int16 [n_streams, n], float32 peaks [n_streams])"""
     torch = _torch()
-    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and (x.shape[1] == 0 or x.stride(1) == 1)
     out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
     peaks = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
     if x.shape[1] == 0:
