@@ -146,6 +146,9 @@ int zen_hpr_realtime_end(zen_hpr* h);
  * d_peaks[n_streams] receives the peaks.  A silent stream (peak 0, where the reference divides by zero) stays silent. */
 int zen_pcm16_decode_mono(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out, long out_stride);
 int zen_pcm16_encode_normalized(const float* d_in, long in_stride, int n_streams, long n, int16_t* d_out, long out_stride, float* d_peaks);
+/* host-only test hook: which half-spectrum bins CTA `rank` of a `cluster`-CTA resident kernel owns
+ * (out6 = {k0, k1, a0, a1, b0, b1}: bin pairs (k, nfft/2 - k) for k in [k0, k1), i.e. bins [a0, a1) and [b0, b1)) */
+int zen_rt_split_ranges(int nfft, int rank, int cluster, int* out6);
 /* host-only test hooks for the tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag} the resident session exchanges with
  * its kernel (no device involved).  groups: 16-byte aligned, ceil(hop / 3) * 16 bytes.  zen_rt_unpack_groups returns
  * the number of leading groups that carried `tag` and were unpacked. */

@@ -154,3 +154,32 @@ def test_tagged_group_format_round_trip(hop):
         assert np.array_equal(y2[:3 * stop].view(np.uint32), x[:3 * stop].view(np.uint32))
         assert np.all(y2[3 * stop:] == 7.0)                 # nothing of the stale line / group or behind it was written
     assert L.zen_rt_pack_groups(x.ctypes.data, hop, tag, g.ctypes.data + 4) != 0   # misaligned staging buffer
+
+
+@pytest.mark.parametrize("nfft", [128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_cluster_split_owns_every_bin_exactly_once(nfft, cluster):
+    """hpr_split_ranges (hpr_core.cuh): the CTAs of the resident cluster kernel divide the nfft/2 + 1 half-spectrum bins
+    by pairs (k, M - k); every bin must have exactly one owner, a CTA's two ranges must not overlap, the pair ranges
+    must tile [0, M/2], and the ranges must be the mirror images of the pairs"""
+    import ctypes
+    from zen_b200 import _lib
+    L = _lib.lib()
+    M = nfft // 2
+    owners = np.zeros(M + 1, np.int32)
+    next_k = 0
+    for rank in range(cluster):
+        r = (ctypes.c_int * 6)()
+        assert L.zen_rt_split_ranges(nfft, rank, cluster, r) == 0
+        k0, k1, a0, a1, b0, b1 = list(r)
+        assert k0 == next_k and k0 <= k1 <= M // 2 + 1
+        next_k = k1
+        assert (a0, a1) == (k0, k1) or k0 == k1
+        assert a1 <= b0 or k0 == k1                            # the two ranges of one CTA do not overlap
+        owners[a0:a1] += 1
+        owners[b0:b1] += 1
+        own = set(range(a0, a1)) | set(range(b0, b1))
+        assert own == {k for k in range(k0, k1)} | {M - k for k in range(k0, k1)}
+    assert next_k == M // 2 + 1
+    assert np.all(owners == 1)
+    assert L.zen_rt_split_ranges(nfft, cluster, cluster, (ctypes.c_int * 6)()) != 0

@@ -44,6 +44,7 @@ EXPORTS = [
     "zen_hpr_batch_last_launches", "zen_hpr_batch_last_kernel_ms", "zen_offline_process",
     "zen_offline_process_device", "zen_copy_to_host", "zen_copy_to_device", "zen_fakert_run", "zen_host_alloc", "zen_host_free", "zen_hpr_bind_state", "zen_hpr_realtime_begin", "zen_hpr_realtime_end", "zen_hpr_realtime_stamps",
     "zen_rt_pack_groups", "zen_rt_unpack_groups", "zen_pcm16_decode_mono", "zen_pcm16_encode_normalized",
+    "zen_rt_split_ranges",
 ]
 
 _lib = None

@@ -1035,6 +1035,15 @@ float* zen_hpr_state_ptr(zen_hpr* h, int which)
 
 #include <chrono>
 
+// Host-only test hook: the bin ownership of the cluster-split hop (hpr_split_ranges, hpr_core.cuh).
+// out6 = {k0, k1, a0, a1, b0, b1}: own pairs [k0, k1), own bins [a0, a1) and [b0, b1) of CTA `rank` out of `cluster`.
+extern "C" int zen_rt_split_ranges(int nfft, int rank, int cluster, int* out6)
+{
+	if (!out6 || nfft < 8 || (nfft & (nfft - 1)) || cluster < 1 || rank < 0 || rank >= cluster) return ZEN_ERR_ARG;
+	hpr_split_ranges(nfft / 2, rank, cluster, out6[0], out6[1], out6[2], out6[3], out6[4], out6[5]);
+	return ZEN_OK;
+}
+
 // Host-only test hooks for the tagged-group format of the resident kernel's staging buffers (no device involved).
 // groups: 16-byte aligned, ceil(hop / 3) * 16 bytes.
 extern "C" int zen_rt_pack_groups(const float* src, int hop, unsigned tag, void* groups)
