@@ -5,11 +5,14 @@
     python bench.py --gpus N --steps K --warmup W            # our arm
     python bench.py --impl reference --gpus N --steps K ...  # reference CPU path on the host cores
 
-Workload (BASELINE.json configs[4]): a batch of 4096 independent synthetic 60 s
-mono 44.1 kHz streams per GPU, real-time HPR (HPRRealtime<GPU> semantics: causal,
+Workload (BASELINE.json configs[4]): ONE batch of 4096 independent synthetic 60 s
+mono 44.1 kHz streams, real-time HPR (HPRRealtime<GPU> semantics: causal,
 copy-border, percussive output, hard mask) at hop 1024, beta 2.5.  One step = one
-pass of the hot path over the whole batch.  Under torchrun every rank owns one
-GPU and its own 4096 streams (no collective on the data path; weak scaling).
+pass of the hot path over the whole batch.  Under torchrun the batch is sharded
+4096/N streams per rank (one rank per GPU, no collective on the data path): strong
+scaling, the configuration as named.  The other variant (every GPU owns 4096
+streams) is measured in the same run and reported under "weak"; --scaling weak
+makes it the headline instead.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md for the definition of every field.
 """
@@ -183,8 +186,8 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "HPR audio-sec/sec batched", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, N_STREAMS, SECONDS),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.streams, args.seconds, world, args.scaling == "strong"),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind,
                          "sample": cpu_sample_text(kind, cores, n_hops) + " per step"},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,16 +196,58 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, n_streams, seconds):
-    return {"workload": "BASELINE.json configs[4]: %d independent synthetic %d s mono 44.1 kHz streams per GPU, real-time HPR "
-                        "(causal, copy-border, percussive out, hard mask), hop %d, beta %.1f" % (n_streams, seconds, HOP, BETA),
-            "streams_per_gpu": n_streams, "hops_per_stream": fakert_hops(seconds * FS, HOP), "hop": HOP, "nfft": 4 * HOP,
-            "fs": FS, "l2": ("inputs exceed L2 (%.1f GB in + %.1f GB out per GPU per step)" % (2 * (n_streams * seconds * FS * 4 / 1e9,))
-                             if n_streams * seconds * FS * 4 >= (512 << 20) else "small run: L2 flushed between steps"),
+def workload_config(args, n_streams, seconds, world=1, strong=True):
+    per_gpu = -(-n_streams // world) if strong else n_streams
+    return {"workload": "BASELINE.json configs[4]: %d independent synthetic %d s mono 44.1 kHz streams %s, real-time HPR "
+                        "(causal, copy-border, percussive out, hard mask), hop %d, beta %.1f"
+                        % (n_streams, seconds, "in total, sharded over the GPUs" if strong else "per GPU", HOP, BETA),
+            "streams_total": n_streams if strong else n_streams * world, "streams_per_gpu": per_gpu,
+            "hops_per_stream": fakert_hops(seconds * FS, HOP), "hop": HOP, "nfft": 4 * HOP,
+            "fs": FS, "l2": ("inputs exceed L2 (%.1f GB in + %.1f GB out per GPU per step)" % (2 * (per_gpu * seconds * FS * 4 / 1e9,))
+                             if per_gpu * seconds * FS * 4 >= (512 << 20) else "small run: L2 flushed between steps"),
             "parallelism": "streams sharded over GPUs, no collective"}
 
 
 # ----------------------------------------------------------------------- our arm ---
+
+def parity_sample(torch, hps, x, out_p, rows, n_hops):
+    """CHECKER (not on the measured path): full-length streams of the batch against the oracle, hop by hop, with the
+    hard-mask threshold flips counted (tests/util.py:flip_aware_compare), and the batched kernel's output of the same
+    streams required to equal the checked per-hop path bit for bit."""
+    from oracle import oraclebind as ob
+    from tests.util import flip_aware_compare
+    res = {"streams": [], "hops": 0, "flips": 0, "flip_hops": 0, "worst_margin": 0.0, "max_abs_err": 0.0, "min_snr_db": float("inf"),
+           "batched_equals_checked_path": True, "oracle": "oracle/hpr_oracle.c (GPU geometry), pinned by tests/test_oracle_golden.py",
+           "tolerance": "max-abs <= 1e-4 and SNR >= 80 dB after peak normalisation on every hop without a flipped bin"}
+    for r in rows:
+        a = x[r, : n_hops * HOP].cpu().numpy()
+        o = ob.OracleHPR(ob.GEOM_GPU, float(FS), HOP, BETA, 2, ob.CAUSAL, True)
+        h = hps.HPR(float(FS), HOP, BETA, 2, 0, True)
+        c = flip_aware_compare(h, o, a, HOP, 2, hard_mask=True)
+        h.close()
+        o.close()
+        res["streams"].append(int(r))
+        res["hops"] += n_hops
+        res["flips"] += int(c["flips"].sum())
+        res["flip_hops"] += int(np.count_nonzero(c["flips"]))
+        res["worst_margin"] = max(res["worst_margin"], float(c["worst_margin"]))
+        res["max_abs_err"] = max(res["max_abs_err"], float(c["err"][1]))
+        res["min_snr_db"] = min(res["min_snr_db"], float(c["snr"][1]))
+        same = bool(np.array_equal(out_p[r, : n_hops * HOP].cpu().numpy(), c["got"][1]))
+        res["batched_equals_checked_path"] = res["batched_equals_checked_path"] and same
+    res["ok"] = bool(res["batched_equals_checked_path"] and res["max_abs_err"] <= 1e-4 and res["min_snr_db"] >= 80.0
+                     and res["worst_margin"] <= 2e-5)
+    return res
+
+
+def quantize_to_pinned(torch, _lib, x, h_pcm, rows_per_chunk=256):
+    """PCM16 image of the device batch (libnyquist's float32_to_int16 convention, x * 32767 rounded) in pinned host memory"""
+    n = x.shape[1]
+    for s0 in range(0, x.shape[0], rows_per_chunk):
+        q = (x[s0:s0 + rows_per_chunk] * 32767.0).round_().clamp_(-32768, 32767).to(torch.int16).contiguous()
+        _lib.check(_lib.lib().zen_copy_to_host(h_pcm.ptr + s0 * n * 2, q.data_ptr(), q.numel() * 2), "zen_copy_to_host")
+        del q
+
 
 def run_ours(args, rank, world, local_rank):
     import torch
@@ -213,103 +258,146 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; zen_b200 has no CPU fallback")
     _lib.lib()  # fail loudly if the CUDA library is missing
     torch.cuda.set_device(local_rank)
+    numa = shard.bind_to_gpu_numa(local_rank)  # before any pinned allocation
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ddist = dist if world > 1 else None
 
-    n_streams, seconds = args.streams, args.seconds
+    strong = args.scaling == "strong"
+    seconds = args.seconds
     n_hops = fakert_hops(seconds * FS, HOP)
     n = n_hops * HOP
-    x = synth_batch_device(torch, n_streams, n, dev, seed0=shard.stream_seed(1000, rank, n_streams, 0))
-    out_p = torch.empty_like(x)
-    b = hps.HPRBatch(float(FS), HOP, BETA, hps.OUTPUT_PERCUSSIVE)
-    small = n_streams * n * 4 < (512 << 20)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+    if strong:   # BASELINE.json configs[4] as named: ONE batch of args.streams streams, sharded over the GPUs
+        lo, hi = shard.shard_range(args.streams, rank, world)
+        n_local, seed0 = hi - lo, 1000 + lo
+    else:        # every GPU owns args.streams streams
+        n_local, seed0 = args.streams, shard.stream_seed(1000, rank, args.streams, 0)
 
-    def step():
-        if flush is not None:
-            flush.zero_()
-        b.process(x, [None, out_p, None])
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    assert bool(torch.isfinite(out_p[:4]).all()) and float(out_p[:4].abs().max()) > 0, "kernel produced no output"
-    # full-size sanity: a few streams of the batch must equal, bit for bit, the same stream fed hop by hop through
-    # HPRRealtime-style per-hop launches (the path the parity tests pin against the oracle)
-    verified = []
-    for sidx in sorted(set([0, n_streams // 2, n_streams - 1])):
-        hh = hps.HPR(float(FS), HOP, BETA, hps.OUTPUT_PERCUSSIVE, 0, True)
-        n_chk = min(n_hops, 400)
-        ref_p = hh.run(x[sidx, : n_chk * HOP].cpu().numpy(), n_chk)[1]
-        hh.close()
-        assert np.array_equal(out_p[sidx, : n_chk * HOP].cpu().numpy(), ref_p), "batched kernel != per-hop path on stream %d" % sidx
-        verified.append(int(sidx))
-
-    sampler = ClockSampler(local_rank)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.zero_()
-        ev[2 * k].record()
-        b.process(x, [None, out_p, None])
-        ev[2 * k + 1].record()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    kern_ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[-1]) if flush is None else sum(kern_ms)
-    launches = args.steps * b.last_launches
-    if world > 1:
-        dist.barrier()
-    total_ms_max = shard.max_over_ranks(dist if world > 1 else None, total_ms, dev)
-    audio_per_step = n_streams * n / FS
-    value = shard.aggregate_throughput(audio_per_step * args.steps, world, total_ms_max * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
-    e2e = None
-    try:
-        # pinned host buffers for the whole batch when the host has room for them (2 x 43 GB per rank at full size);
-        # otherwise the largest prefix of the streams that fits, and the dict says so
-        e2e_streams = n_streams
-        try:
-            import psutil
-            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-            budget = 0.6 * psutil.virtual_memory().available / max(1, local_world)
-            e2e_streams = int(max(1, min(n_streams, budget // (2 * n * 4))))
-        except Exception:  # noqa: BLE001
-            pass
-        h_in = hps.PinnedArray(e2e_streams, n)
-        h_out = hps.PinnedArray(e2e_streams, n)
-        _lib.check(_lib.lib().zen_copy_to_host(h_in.ptr, x.data_ptr(), h_in.nbytes), "zen_copy_to_host")
+    def timed_batch(x, out_p, steps, warmup):
+        b = hps.HPRBatch(float(FS), HOP, BETA, hps.OUTPUT_PERCUSSIVE)
+        small = x.numel() * 4 < (512 << 20)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+        for _ in range(warmup):
+            if flush is not None:
+                flush.zero_()
+            b.process(x, [None, out_p, None])
         torch.cuda.synchronize()
-        del out_p
-        audio_per_e2e_step = e2e_streams * n / FS
-        e2e_steps = max(1, min(args.steps, 3))
-        b.process_host(h_in.array, [None, h_out.array, None])  # warm-up (allocates the staging buffers)
-        if world > 1:
-            dist.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]
+        if ddist:
+            ddist.barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            b.process_host(h_in.array, [None, h_out.array, None])
+        for k in range(steps):
+            if flush is not None:
+                flush.zero_()
+            ev[2 * k].record()
+            b.process(x, [None, out_p, None])
+            ev[2 * k + 1].record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        kern_ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(steps)]
+        total_ms = ev[0].elapsed_time(ev[-1]) if flush is None else sum(kern_ms)
+        if ddist:
+            ddist.barrier()
+        total_ms_max = shard.max_over_ranks(ddist, total_ms, dev)
+        launches = steps * b.last_launches
+        b.close()
+        return total_ms_max, kern_ms, launches, wall
+
+    x = synth_batch_device(torch, n_local, n, dev, seed0=seed0)
+    out_p = torch.empty_like(x)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms_max, kern_ms, launches, t_wall = timed_batch(x, out_p, args.steps, args.warmup)
+    clocks = sampler.stop()
+    assert bool(torch.isfinite(out_p[:4]).all()) and float(out_p[:4].abs().max()) > 0, "kernel produced no output"
+    streams_all = args.streams if strong else args.streams * world
+    value = streams_all * n / FS * args.steps / (total_ms_max * 1e-3)
+
+    # ---- parity of what was just timed, against the oracle (rank 0; checker only)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            rows = sorted(set([0, n_local - 1]))[: max(1, args.parity_streams)]
+            parity = parity_sample(torch, hps, x, out_p, rows, min(n_hops, args.parity_hops))
+        except Exception as exc:  # noqa: BLE001
+            parity = {"ok": False, "error": repr(exc)[:300]}
+
+    # ---- end to end through the C ABI with HOST buffers, H2D + D2H inside the timed region.
+    # Headline: the command line's own sample format on both sides (zen_hpr_batch_process_host_pcm16: PCM16 in,
+    # peak-normalised PCM16 out, zen/offline.h:88-117, 180-223); secondary: float32 both ways on a prefix of the streams.
+    def e2e_run(fn_name, dtype, e2e_streams, steps):
+        h_in = hps.PinnedArray(e2e_streams, n, dtype)
+        h_out = hps.PinnedArray(e2e_streams, n, dtype)
+        if dtype == np.int16:
+            quantize_to_pinned(torch, _lib, x[:e2e_streams], h_in)
+        else:
+            _lib.check(_lib.lib().zen_copy_to_host(h_in.ptr, x.data_ptr(), h_in.nbytes), "zen_copy_to_host")
+        torch.cuda.synchronize()
+        b = hps.HPRBatch(float(FS), HOP, BETA, hps.OUTPUT_PERCUSSIVE)
+        fn = getattr(b, fn_name)
+        fn(h_in.array, [None, h_out.array, None])  # warm-up (allocates the staging buffers)
+        if ddist:
+            ddist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn(h_in.array, [None, h_out.array, None])
         dt = time.perf_counter() - t0
-        launches_e2e = e2e_steps * b.last_launches
-        dt_max = shard.max_over_ranks(dist if world > 1 else None, dt, dev)
-        e2e = {"value": shard.aggregate_throughput(audio_per_e2e_step * e2e_steps, world, dt_max), "unit": "audio-s/s",
-               "h2d_bytes_per_step": int(e2e_streams) * n * 4, "d2h_bytes_per_step": int(e2e_streams) * n * 4,
-               "streams_per_gpu": int(e2e_streams),
-               "steps": e2e_steps, "kernel_launches_per_step": launches_e2e // e2e_steps,
-               "api": "zen_hpr_batch_process_host (pinned host buffers in and out)"}
-        assert bool(np.isfinite(h_out.array[:2]).all()) and float(np.abs(h_out.array[:2]).max()) > 0
+        launches_e2e = b.last_launches
+        dt_max = shard.max_over_ranks(ddist, dt, dev)
+        ok = bool(np.isfinite(h_out.array[:2].astype(np.float32)).all()) and float(np.abs(h_out.array[:2].astype(np.float32)).max()) > 0
+        head = h_out.array[0, : 64 * HOP].copy()
+        b.close()
         h_in.close()
         h_out.close()
+        return dt_max, launches_e2e, ok, head
+
+    e2e = None
+    e2e_f32 = None
+    try:
+        import psutil
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        budget = 0.6 * psutil.virtual_memory().available / max(1, local_world)
+        e2e_steps = max(1, min(args.steps, 3))
+        es = int(max(1, min(n_local, budget // (2 * n * 2))))
+        es_min = int(shard.max_over_ranks(ddist, -es, dev) * -1)   # every rank runs the same share of its shard
+        frac = es_min / n_local
+        dt_max, le, ok, head = e2e_run("process_host_pcm16", np.int16, es_min, e2e_steps)
+        streams_e2e_all = streams_all * frac
+        e2e = {"value": streams_e2e_all * n / FS * e2e_steps / dt_max, "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(es_min) * n * 2, "d2h_bytes_per_step": int(es_min) * n * 2,
+               "streams_per_gpu": int(es_min), "steps": e2e_steps, "kernel_launches_per_step": int(le), "output_checked": ok,
+               "sample_format": "PCM16 mono in, peak-normalised PCM16 out (what zen offline / fakert read and write)",
+               "api": "zen_hpr_batch_process_host_pcm16 (pinned host buffers in and out; decode, HPR, peak + encode on the device)"}
+        e2e["output_peak_int16_first_64_hops"] = int(np.abs(head.astype(np.int32)).max())
+        if not args.no_e2e_f32:
+            es32 = int(max(1, min(es_min, args.e2e_f32_streams, budget // (2 * n * 4))))
+            dt32, le32, ok32, _ = e2e_run("process_host", np.float32, es32, max(1, min(e2e_steps, 2)))
+            e2e_f32 = {"value": streams_all * (es32 / n_local) * n / FS * max(1, min(e2e_steps, 2)) / dt32, "unit": "audio-s/s",
+                       "h2d_bytes_per_step": es32 * n * 4, "d2h_bytes_per_step": es32 * n * 4, "streams_per_gpu": es32,
+                       "output_checked": ok32, "api": "zen_hpr_batch_process_host (float32 both ways)"}
     except Exception as exc:  # noqa: BLE001
-        e2e = {"value": None, "unit": "audio-s/s", "error": repr(exc)[:200]}
+        if e2e is None:
+            e2e = {"value": None, "unit": "audio-s/s", "error": repr(exc)[:200]}
+        else:
+            e2e_f32 = {"value": None, "error": repr(exc)[:200]}
+
+    # ---- the other scaling variant (N > 1): every GPU owns the whole 4096-stream batch
+    weak = None
+    if world > 1 and strong and not args.no_weak:
+        try:
+            del x, out_p
+            torch.cuda.empty_cache()
+            xw = synth_batch_device(torch, args.streams, n, dev, seed0=shard.stream_seed(1000, rank, args.streams, 0))
+            ow = torch.empty_like(xw)
+            w_steps = max(1, min(args.steps, 3))
+            w_ms, _, _, _ = timed_batch(xw, ow, w_steps, 3)
+            weak = {"scaling": "weak", "streams_per_gpu": args.streams, "ms_per_step": w_ms / w_steps, "steps": w_steps,
+                    "value": world * args.streams * n / FS * w_steps / (w_ms * 1e-3), "unit": "audio-s/s"}
+            del xw, ow
+        except Exception as exc:  # noqa: BLE001
+            weak = {"error": repr(exc)[:200]}
 
     if rank != 0:
         if world > 1:
@@ -318,29 +406,36 @@ def run_ours(args, rank, world, local_rank):
 
     peak, peak_src = measured_peak_gbs()
     kern_avg_ms = float(np.mean(kern_ms))
-    achieved = n_streams * n_hops * BYTES_PER_HOP / (kern_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    achieved = n_local * n_hops * BYTES_PER_HOP / (kern_avg_ms * 1e-3) / 1e9
+    roof = {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "kernel": "hpr_tile_kernel<4096,256>", "kernel_ms": kern_avg_ms,
+            "algorithmic_bytes_per_launch": n_local * n_hops * BYTES_PER_HOP,
+            "note": "achieved / peak / frac are the compulsory-byte HBM figures the contract asks for; the fused kernel is bound by "
+                    "instruction issue (mask decision + FFT), not by HBM - issue_frac / alu_pipe_frac / fma_pipe_frac are ncu's "
+                    "smsp__issue_active, sm__inst_executed_pipe_alu / _fma (pct of peak) of the capture named in `ncu`"}
+    tp = os.path.join(ROOT, "profiles", "tile_kernel_ncu.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            # measured on the full 4096 x 2583-hop launch; scaled to this run's launch size
-            traffic = tj.get("dram_bytes_per_launch") * (n_streams * n_hops * BYTES_PER_HOP) / tj.get("algorithmic_bytes_per_launch")
+            # measured on one full-size launch; scaled to this run's launch size
+            roof["traffic"] = tj["dram_bytes_per_launch"] * (n_local * n_hops * BYTES_PER_HOP) / tj["algorithmic_bytes_per_launch"]
+            for k in ("issue_frac", "alu_pipe_frac", "fma_pipe_frac", "warp_instr_per_hop", "ncu"):
+                if k in tj:
+                    roof[k] = tj[k]
         except Exception:  # noqa: BLE001
-            traffic = None
+            pass
 
     line = {
         "metric": "HPR audio-sec/sec batched", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_streams, seconds),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "kernel": "hpr_tile_kernel<4096,256>", "kernel_ms": kern_avg_ms,
-                     "algorithmic_bytes_per_launch": n_streams * n_hops * BYTES_PER_HOP,
-                     "note": "the fused kernel is ALU/issue-bound on the median selection, not HBM-bound (DESIGN.md)"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall,
-        "verified_streams_bit_exact_vs_per_hop_path": verified,
+        "config": workload_config(args, args.streams, seconds, world, strong),
+        "roofline": roof, "e2e": e2e, "e2e_f32": e2e_f32, "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall,
+        "parity": parity, "numa": numa,
     }
+    if weak is not None:
+        line["weak"] = weak
 
     # ---- per-hop latency of one real-time stream (BASELINE.json configs[1])
     if not args.no_latency:
@@ -410,6 +505,14 @@ def main():
     ap.add_argument("--cpu-hops", type=int, default=600, help="hops per core of the cpu_baseline sample")
     ap.add_argument("--ref-hops", type=int, default=1500, help="hops per core and step of the reference arm")
     ap.add_argument("--latency-hops", type=int, default=2000)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --streams is the whole batch, sharded over the GPUs (configs[4] as named); weak: --streams per GPU")
+    ap.add_argument("--parity-streams", type=int, default=2, help="full-length streams checked against the oracle")
+    ap.add_argument("--parity-hops", type=int, default=1 << 30)
+    ap.add_argument("--e2e-f32-streams", type=int, default=1024)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-e2e-f32", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()

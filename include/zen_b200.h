@@ -118,6 +118,10 @@ int zen_hpr_copy_residual(zen_hpr* h, float* d_out_hop);
  * skipped.  This is the latency path (zen fakert's timed region). */
 int zen_hpr_process_hop_io(zen_hpr* h, const float* d_in_hop, float* d_out_h, float* d_out_p, float* d_out_r);
 int zen_hpr_synchronize(zen_hpr* h);
+/* Returns once the hop passed to the last zen_hpr_process_next_hop has been read, i.e. the caller may refill the
+ * buffer (the reference's process_next_hop has copied in_hop when it returns, hps.cu:452-453).  Free for a resident
+ * session fed from mapped host memory (the hop was copied at submission); a stream synchronisation otherwise. */
+int zen_hpr_wait_input_consumed(zen_hpr* h);
 /* Resident real-time session for a causal stream: a persistent kernel keeps the
  * stream's state (|X| ring, overlap-add tails, previous hop, window and twiddle
  * tables) in shared memory and serves zen_hpr_process_next_hop /
@@ -146,6 +150,17 @@ int zen_hpr_realtime_end(zen_hpr* h);
  * d_peaks[n_streams] receives the peaks.  A silent stream (peak 0, where the reference divides by zero) stays silent. */
 int zen_pcm16_decode_mono(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out, long out_stride);
 int zen_pcm16_encode_normalized(const float* d_in, long in_stride, int n_streams, long n, int16_t* d_out, long out_stride, float* d_peaks);
+/* The same on a CUDA stream, without waiting (the two entry points above run on the legacy default stream and
+ * synchronise).  zen_pcm16_peaks_async: d_peaks[s] = max |x| of row s; zen_pcm16_encode_with_peaks_async: the encode
+ * pass alone, given the peaks; zen_pcm16_encode_normalized_async = both.  Rows whose pointers and strides are 16-byte
+ * aligned take the vector path (8 samples per thread and access). */
+int zen_pcm16_decode_mono_async(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out,
+                                long out_stride, void* cuda_stream);
+int zen_pcm16_peaks_async(const float* d_in, long in_stride, int n_streams, long n, float* d_peaks, void* cuda_stream);
+int zen_pcm16_encode_with_peaks_async(const float* d_in, long in_stride, int n_streams, long n, const float* d_peaks, int16_t* d_out,
+                                      long out_stride, void* cuda_stream);
+int zen_pcm16_encode_normalized_async(const float* d_in, long in_stride, int n_streams, long n, int16_t* d_out, long out_stride,
+                                      float* d_peaks, void* cuda_stream);
 /* host-only test hook: which half-spectrum bins CTA `rank` of a `cluster`-CTA resident kernel owns
  * (out6 = {k0, k1, a0, a1, b0, b1}: bin pairs (k, nfft/2 - k) for k in [k0, k1), i.e. bins [a0, a1) and [b0, b1)) */
 int zen_rt_split_ranges(int nfft, int rank, int cluster, int* out6);
@@ -204,6 +219,16 @@ int zen_hpr_batch_process(zen_hpr_batch* b, const float* d_in, long in_stride, i
  * copied in, processed and copied out on alternating CUDA streams */
 int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stride, int n_streams, long n_hops,
                                float* h_out_h, float* h_out_p, float* h_out_r, long out_stride);
+/* The same with the command line's on-disk sample format on both sides of the PCIe link (zen/offline.h:88-117,
+ * 180-223; zen/fakert.h:101-130, 259-287): h_in holds mono PCM16 rows, decoded on the device exactly as libnyquist
+ * does ((float)s / 32767.f, vendor/libnyquist/include/libnyquist/Common.h:296-302); every requested output comes
+ * back peak-normalised per stream (x / max|x|) and converted with (int16_t)lroundf(x * 32767.f)
+ * (vendor/libnyquist/src/Common.cpp:332-337) - what `zen offline|fakert` write to their wav files.  2 bytes per
+ * sample cross the link in each direction instead of 4.  h_peaks_* (optional, n_streams floats each) receive the
+ * peaks the outputs were divided by.  A silent stream stays silent (the reference divides by zero there). */
+int zen_hpr_batch_process_host_pcm16(zen_hpr_batch* b, const int16_t* h_in, long in_stride, int n_streams, long n_hops,
+                                     int16_t* h_out_h, int16_t* h_out_p, int16_t* h_out_r, long out_stride,
+                                     float* h_peaks_h, float* h_peaks_p, float* h_peaks_r);
 /* number of kernels launched by the last zen_hpr_batch_process* call */
 long zen_hpr_batch_last_launches(const zen_hpr_batch* b);
 /* device time of the fused kernel(s) of the last zen_hpr_batch_process call, ms (CUDA events) */

@@ -44,7 +44,8 @@ EXPORTS = [
     "zen_hpr_batch_last_launches", "zen_hpr_batch_last_kernel_ms", "zen_offline_process",
     "zen_offline_process_device", "zen_copy_to_host", "zen_copy_to_device", "zen_fakert_run", "zen_host_alloc", "zen_host_free", "zen_hpr_bind_state", "zen_hpr_realtime_begin", "zen_hpr_realtime_end", "zen_hpr_realtime_stamps",
     "zen_rt_pack_groups", "zen_rt_unpack_groups", "zen_pcm16_decode_mono", "zen_pcm16_encode_normalized",
-    "zen_rt_split_ranges",
+    "zen_rt_split_ranges", "zen_pcm16_decode_mono_async", "zen_pcm16_peaks_async", "zen_pcm16_encode_with_peaks_async",
+    "zen_pcm16_encode_normalized_async", "zen_hpr_batch_process_host_pcm16", "zen_hpr_wait_input_consumed",
 ]
 
 _lib = None
@@ -67,13 +68,18 @@ def lib():
     L.zen_io_free.restype = None
     L.zen_pcm16_decode_mono.argtypes = [vp, cl, ci, ci, cl, vp, cl]
     L.zen_pcm16_encode_normalized.argtypes = [vp, cl, ci, cl, vp, cl, vp]
+    L.zen_pcm16_decode_mono_async.argtypes = [vp, cl, ci, ci, cl, vp, cl, vp]
+    L.zen_pcm16_peaks_async.argtypes = [vp, cl, ci, cl, vp, vp]
+    L.zen_pcm16_encode_with_peaks_async.argtypes = [vp, cl, ci, cl, vp, vp, cl, vp]
+    L.zen_pcm16_encode_normalized_async.argtypes = [vp, cl, ci, cl, vp, cl, vp, vp]
+    L.zen_hpr_batch_process_host_pcm16.argtypes = [vp, vp, cl, ci, cl, vp, vp, vp, cl, vp, vp, vp]
     L.zen_median_filter.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp]
     L.zen_box_filter.argtypes = [ci, ci, ci, ci, vp, vp, vp]
     L.zen_fft_c2c.argtypes = [ci, vp, ci, vp]
     L.zen_hpr_create.argtypes = [ctypes.POINTER(vp), cf, ci, cf, cu, ci, ci]
     L.zen_hpr_destroy.argtypes = [vp]
     L.zen_hpr_destroy.restype = None
-    for n in ("zen_hpr_use_sse_filter", "zen_hpr_use_soft_mask", "zen_hpr_reset_buffers", "zen_hpr_synchronize"):
+    for n in ("zen_hpr_use_sse_filter", "zen_hpr_use_soft_mask", "zen_hpr_reset_buffers", "zen_hpr_synchronize", "zen_hpr_wait_input_consumed"):
         getattr(L, n).argtypes = [vp]
     L.zen_hpr_get_geometry.argtypes = [vp, ctypes.POINTER(ZenGeometry)]
     L.zen_hpr_process_next_hop.argtypes = [vp, vp]

@@ -63,6 +63,8 @@ int zen_hpr_geometry(float fs, int hop, int causal, zen_geometry* g)
 
 // IOGPU, libzen/libzen/io.h:24-70: mapped + portable pinned buffers (input also
 // write-combined) and their device aliases.
+void zen_io_free(zen_io* io);
+
 int zen_io_alloc(zen_io* io, size_t size)
 {
 	if (!io || size == 0)
@@ -73,10 +75,15 @@ int zen_io_alloc(zen_io* io, size_t size)
 	// The reference allocates host_in write-combined (libzen/libzen/io.h:30-34).  Ours is ordinary cached pinned memory:
 	// the resident real-time kernel's host side re-reads the hop to push it in tagged groups (rt_publish), and reading
 	// write-combined memory back on the host is uncached.
-	ZEN_CUDA_CHECK(cudaHostAlloc((void**)&io->host_in, size * sizeof(float), flags));
-	ZEN_CUDA_CHECK(cudaHostAlloc((void**)&io->host_out, size * sizeof(float), flags));
-	ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&io->device_in, io->host_in, 0));
-	ZEN_CUDA_CHECK(cudaHostGetDevicePointer((void**)&io->device_out, io->host_out, 0));
+	cudaError_t e = cudaHostAlloc((void**)&io->host_in, size * sizeof(float), flags);
+	if (e == cudaSuccess) e = cudaHostAlloc((void**)&io->host_out, size * sizeof(float), flags);
+	if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&io->device_in, io->host_in, 0);
+	if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&io->device_out, io->host_out, 0);
+	if (e != cudaSuccess) {
+		std::fprintf(stderr, "zen_b200: zen_io_alloc failed: %s\n", cudaGetErrorString(e));
+		zen_io_free(io);  // nothing leaks on a partial failure
+		return ZEN_ERR_CUDA;
+	}
 	std::memset(io->host_in, 0, size * sizeof(float));
 	std::memset(io->host_out, 0, size * sizeof(float));
 	return ZEN_OK;

@@ -848,8 +848,13 @@ int zen_hpr_create(zen_hpr** out, float fs, int hop, float beta, unsigned flags,
 		zen_hpr_destroy(h);
 		return ZEN_ERR_CUDA;
 	}
+	rc = zen_hpr_reset_buffers(h);
+	if (rc != ZEN_OK) {
+		zen_hpr_destroy(h);
+		return rc;
+	}
 	*out = h;
-	return zen_hpr_reset_buffers(h);
+	return ZEN_OK;
 }
 
 void zen_hpr_destroy(zen_hpr* h)
@@ -957,6 +962,20 @@ int zen_hpr_synchronize(zen_hpr* h)
 	// real-time session: every call is served synchronously by the resident kernel and nothing is ever queued on the
 	// object's stream (rt_launch drains it) - a cudaStreamSynchronize here would only add its ~1.5 us to each hop
 	if (h->rt_mode && h->rt_running) return rt_drain(h);
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+	return ZEN_OK;
+}
+
+// After this returns the caller may overwrite the hop it passed to the last zen_hpr_process_next_hop (in the
+// reference the copy of in_hop has completed when process_next_hop returns, hps.cu:452-453).
+int zen_hpr_wait_input_consumed(zen_hpr* h)
+{
+	if (!h) return ZEN_ERR_ARG;
+	if (h->rt_mode && h->rt_running) {
+		// a pushed hop was copied into the tagged staging buffer at submission
+		if (!h->rt_pend.active || h->rt_pend.push_src) return ZEN_OK;
+		return rt_drain(h);
+	}
 	ZEN_CUDA_CHECK(cudaStreamSynchronize(h->stream));
 	return ZEN_OK;
 }
@@ -1278,11 +1297,20 @@ struct zen_hpr_batch {
 	long last_launches = 0;
 	float last_kernel_ms = 0.0f;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	// host pipeline
+	// host pipeline: per slot a float staging buffer for the input and one per requested output, and (PCM16 entry
+	// point) the int16 images of both plus the per-stream peaks.  Capacities are tracked in ELEMENTS per buffer, so
+	// a later call with longer rows, more streams per chunk or another set of outputs regrows exactly what it lacks.
 	cudaStream_t streams[ZEN_PIPE_SLOTS] = {};
 	float* d_stage_in[ZEN_PIPE_SLOTS] = {};
+	size_t cap_in[ZEN_PIPE_SLOTS] = {};
 	float* d_stage_out[ZEN_PIPE_SLOTS][3] = {};
-	int stage_streams = 0;
+	size_t cap_out[ZEN_PIPE_SLOTS][3] = {};
+	int16_t* d_pcm_in[ZEN_PIPE_SLOTS] = {};
+	size_t cap_pcm_in[ZEN_PIPE_SLOTS] = {};
+	int16_t* d_pcm_out[ZEN_PIPE_SLOTS][3] = {};
+	size_t cap_pcm_out[ZEN_PIPE_SLOTS][3] = {};
+	float* d_peaks[ZEN_PIPE_SLOTS][3] = {};
+	size_t cap_peaks[ZEN_PIPE_SLOTS][3] = {};
 };
 
 namespace {
@@ -1356,8 +1384,12 @@ void zen_hpr_batch_destroy(zen_hpr_batch* b)
 	cudaFree(b->d_counters);
 	for (int s = 0; s < ZEN_PIPE_SLOTS; ++s) {
 		cudaFree(b->d_stage_in[s]);
-		for (int o = 0; o < 3; ++o)
+		cudaFree(b->d_pcm_in[s]);
+		for (int o = 0; o < 3; ++o) {
 			cudaFree(b->d_stage_out[s][o]);
+			cudaFree(b->d_pcm_out[s][o]);
+			cudaFree(b->d_peaks[s][o]);
+		}
 		if (b->streams[s]) cudaStreamDestroy(b->streams[s]);
 	}
 	if (b->ev0) cudaEventDestroy(b->ev0);
@@ -1370,7 +1402,8 @@ int zen_hpr_batch_process(zen_hpr_batch* b, const float* d_in, long in_stride, i
 {
 	if (!b || !d_in || n_streams < 1 || n_hops < 1)
 		return ZEN_ERR_ARG;
-	if ((in_stride & 1) || (out_stride & 1) || ((uintptr_t)d_in & 7))
+	if ((in_stride & 1) || (out_stride & 1) || ((uintptr_t)d_in & 7) || ((uintptr_t)d_out_h & 7) || ((uintptr_t)d_out_p & 7)
+	    || ((uintptr_t)d_out_r & 7) || in_stride < n_hops * b->plan.dev.hop || out_stride < n_hops * b->plan.dev.hop)
 		return ZEN_ERR_ARG;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
 	int rc = ensure_scratch(b);
@@ -1379,6 +1412,11 @@ int zen_hpr_batch_process(zen_hpr_batch* b, const float* d_in, long in_stride, i
 	int tile = choose_tile_hops(b->plan, n_streams, n_hops, b->resident);
 	b->tile_hops = tile;
 	const unsigned f = b->plan.dev.out_flags;
+	// the soft-mask / SSE variants never write the residual: the reference's residual_out is only rotated and
+	// zero-filled (hps.cu:435-449, 562), so N process_next_hop calls emit zeros
+	if ((f & 4) && d_out_r && (b->plan.dev.soft || b->plan.dev.sse))
+		ZEN_CUDA_CHECK(cudaMemset2DAsync(d_out_r, (size_t)out_stride * sizeof(float), 0, (size_t)n_hops * b->plan.dev.hop * sizeof(float),
+		                                 (size_t)n_streams, s));
 	cudaEventRecord(b->ev0, s);
 	rc = dispatch_tile(b->plan, d_in, in_stride, (f & 1) ? d_out_h : nullptr, (f & 2) ? d_out_p : nullptr,
 	                   (f & 4) ? d_out_r : nullptr, out_stride, n_streams, n_hops, tile, b->d_scratch, b->d_counters, b->resident, s);
@@ -1399,36 +1437,67 @@ float zen_hpr_batch_last_kernel_ms(const zen_hpr_batch* b)
 	return ms;
 }
 
-int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stride, int n_streams, long n_hops,
-                               float* h_out_h, float* h_out_p, float* h_out_r, long out_stride)
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+int grow(T*& p, size_t& cap, size_t need)
 {
-	if (!b || !h_in || n_streams < 1 || n_hops < 1)
-		return ZEN_ERR_ARG;
-	const int hop = b->plan.dev.hop;
-	const size_t row = (size_t)n_hops * hop;
-	const unsigned f = b->plan.dev.out_flags;
-	float* h_out[3] = {(f & 1) ? h_out_h : nullptr, (f & 2) ? h_out_p : nullptr, (f & 4) ? h_out_r : nullptr};
-	// chunk so that one chunk's input is ~128 MB
+	if (cap >= need && p)
+		return ZEN_OK;
+	cudaFree(p);
+	p = nullptr;
+	cap = 0;
+	ZEN_CUDA_CHECK(cudaMalloc(&p, need * sizeof(T)));
+	cap = need;
+	return ZEN_OK;
+}
+
+// streams per chunk so that one chunk's float input is ~chunk_mb
+int host_chunk_streams(size_t row, int n_streams)
+{
 	size_t chunk_mb = 128;
 	if (const char* e = std::getenv("ZEN_B200_CHUNK_MB")) {
 		long v = std::atol(e);
 		if (v > 0) chunk_mb = (size_t)v;
 	}
-	int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, (chunk_mb << 20) / (row * sizeof(float)) + 1));
-	if (chunk > b->stage_streams) {
-		for (int s = 0; s < ZEN_PIPE_SLOTS; ++s) {
-			cudaFree(b->d_stage_in[s]);
-			b->d_stage_in[s] = nullptr;
-			for (int o = 0; o < 3; ++o) {
-				cudaFree(b->d_stage_out[s][o]);
-				b->d_stage_out[s][o] = nullptr;
-			}
-			if (!b->streams[s]) ZEN_CUDA_CHECK(cudaStreamCreateWithFlags(&b->streams[s], cudaStreamNonBlocking));
-			ZEN_CUDA_CHECK(cudaMalloc(&b->d_stage_in[s], row * sizeof(float) * chunk));
-			for (int o = 0; o < 3; ++o)
-				if (h_out[o]) ZEN_CUDA_CHECK(cudaMalloc(&b->d_stage_out[s][o], row * sizeof(float) * chunk));
+	return (int)std::max<size_t>(1, std::min<size_t>((size_t)n_streams, (chunk_mb << 20) / (row * sizeof(float)) + 1));
+}
+
+// The host pipeline shared by the float and the PCM16 entry points.  Streams are cut into chunks; chunk c runs on
+// CUDA stream c mod ZEN_PIPE_SLOTS: copy in, (decode,) fused HPR kernel, (peak + encode,) copy out, so the H2D copy of
+// one chunk, the kernel of the previous one and the D2H copy of the one before overlap.
+template <typename T>
+int batch_process_host_impl(zen_hpr_batch* b, const T* h_in, long in_stride, int n_streams, long n_hops, T* h_out_h, T* h_out_p,
+                            T* h_out_r, long out_stride, float* h_peaks_h, float* h_peaks_p, float* h_peaks_r)
+{
+	constexpr bool PCM = sizeof(T) == 2;
+	if (!b || !h_in || n_streams < 1 || n_hops < 1)
+		return ZEN_ERR_ARG;
+	const int hop = b->plan.dev.hop;
+	const size_t row = (size_t)n_hops * hop;
+	if ((size_t)in_stride < row || (size_t)out_stride < row)
+		return ZEN_ERR_ARG;
+	const unsigned f = b->plan.dev.out_flags;
+	T* h_out[3] = {(f & 1) ? h_out_h : nullptr, (f & 2) ? h_out_p : nullptr, (f & 4) ? h_out_r : nullptr};
+	float* h_peaks[3] = {h_peaks_h, h_peaks_p, h_peaks_r};
+	const bool zero_r = (f & 4) && (b->plan.dev.soft || b->plan.dev.sse);  // hps.cu:562: residual never written
+	const int chunk = host_chunk_streams(row, n_streams);
+	// device rows are padded to a multiple of 8 elements so that the 16-byte paths of the PCM kernels apply
+	const size_t drow = (row + 7) & ~(size_t)7;
+	for (int s = 0; s < ZEN_PIPE_SLOTS; ++s) {
+		if (!b->streams[s]) ZEN_CUDA_CHECK(cudaStreamCreateWithFlags(&b->streams[s], cudaStreamNonBlocking));
+		int rc = grow(b->d_stage_in[s], b->cap_in[s], drow * chunk);
+		if (rc == ZEN_OK && PCM) rc = grow(b->d_pcm_in[s], b->cap_pcm_in[s], drow * chunk);
+		for (int o = 0; o < 3 && rc == ZEN_OK; ++o) {
+			if (!h_out[o]) continue;
+			rc = grow(b->d_stage_out[s][o], b->cap_out[s][o], drow * chunk);
+			if (rc == ZEN_OK && PCM) rc = grow(b->d_pcm_out[s][o], b->cap_pcm_out[s][o], drow * chunk);
+			if (rc == ZEN_OK && PCM) rc = grow(b->d_peaks[s][o], b->cap_peaks[s][o], (size_t)chunk);
 		}
-		b->stage_streams = chunk;
+		if (rc != ZEN_OK)
+			return rc;
 	}
 	int rc = ensure_scratch(b);
 	if (rc != ZEN_OK)
@@ -1442,26 +1511,71 @@ int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stri
 	for (int s0 = 0; s0 < n_streams; s0 += chunk, slot = (slot + 1) % ZEN_PIPE_SLOTS) {
 		const int ns = std::min(chunk, n_streams - s0);
 		cudaStream_t st = b->streams[slot];
-		ZEN_CUDA_CHECK(cudaMemcpy2DAsync(b->d_stage_in[slot], row * sizeof(float), h_in + (size_t)s0 * in_stride,
-		                                 (size_t)in_stride * sizeof(float), row * sizeof(float), ns,
-		                                 cudaMemcpyHostToDevice, st));
-		rc = dispatch_tile(b->plan, b->d_stage_in[slot], (long)row, b->d_stage_out[slot][0], b->d_stage_out[slot][1],
-		                   b->d_stage_out[slot][2], (long)row, ns, n_hops, tile, b->d_scratch + slot * scratch_half,
-		                   b->d_counters + slot, b->resident, st);
+		if (PCM) {
+			ZEN_CUDA_CHECK(cudaMemcpy2DAsync(b->d_pcm_in[slot], drow * sizeof(T), h_in + (size_t)s0 * in_stride,
+			                                 (size_t)in_stride * sizeof(T), row * sizeof(T), ns, cudaMemcpyHostToDevice, st));
+			rc = zen_pcm16_decode_mono_async(reinterpret_cast<const int16_t*>(b->d_pcm_in[slot]), (long)drow, 1, ns, (long)row,
+			                                 b->d_stage_in[slot], (long)drow, st);
+			if (rc != ZEN_OK)
+				return rc;
+			++launches;
+		}
+		else {
+			ZEN_CUDA_CHECK(cudaMemcpy2DAsync(b->d_stage_in[slot], drow * sizeof(float), h_in + (size_t)s0 * in_stride,
+			                                 (size_t)in_stride * sizeof(T), row * sizeof(T), ns, cudaMemcpyHostToDevice, st));
+		}
+		if (zero_r && h_out[2])
+			ZEN_CUDA_CHECK(cudaMemsetAsync(b->d_stage_out[slot][2], 0, drow * sizeof(float) * ns, st));
+		rc = dispatch_tile(b->plan, b->d_stage_in[slot], (long)drow, h_out[0] ? b->d_stage_out[slot][0] : nullptr,
+		                   h_out[1] ? b->d_stage_out[slot][1] : nullptr, h_out[2] ? b->d_stage_out[slot][2] : nullptr, (long)drow, ns,
+		                   n_hops, tile, b->d_scratch + slot * scratch_half, b->d_counters + slot, b->resident, st);
 		if (rc != ZEN_OK)
 			return rc;
 		++launches;
-		for (int o = 0; o < 3; ++o)
-			if (h_out[o])
-				ZEN_CUDA_CHECK(cudaMemcpy2DAsync(h_out[o] + (size_t)s0 * out_stride, (size_t)out_stride * sizeof(float),
-				                                 b->d_stage_out[slot][o], row * sizeof(float), row * sizeof(float), ns,
-				                                 cudaMemcpyDeviceToHost, st));
+		for (int o = 0; o < 3; ++o) {
+			if (!h_out[o]) continue;
+			if (PCM) {
+				// what the command line does with every output: x / max|x|, then PCM16 (zen/offline.h:180-223)
+				rc = zen_pcm16_encode_normalized_async(b->d_stage_out[slot][o], (long)drow, ns, (long)row,
+				                                       reinterpret_cast<int16_t*>(b->d_pcm_out[slot][o]), (long)drow, b->d_peaks[slot][o], st);
+				if (rc != ZEN_OK)
+					return rc;
+				launches += 2;
+				ZEN_CUDA_CHECK(cudaMemcpy2DAsync(h_out[o] + (size_t)s0 * out_stride, (size_t)out_stride * sizeof(T), b->d_pcm_out[slot][o],
+				                                 drow * sizeof(T), row * sizeof(T), ns, cudaMemcpyDeviceToHost, st));
+				if (h_peaks[o])
+					ZEN_CUDA_CHECK(cudaMemcpyAsync(h_peaks[o] + s0, b->d_peaks[slot][o], sizeof(float) * ns, cudaMemcpyDeviceToHost, st));
+			}
+			else {
+				ZEN_CUDA_CHECK(cudaMemcpy2DAsync(h_out[o] + (size_t)s0 * out_stride, (size_t)out_stride * sizeof(T), b->d_stage_out[slot][o],
+				                                 drow * sizeof(float), row * sizeof(T), ns, cudaMemcpyDeviceToHost, st));
+			}
+		}
 	}
 	for (int s = 0; s < ZEN_PIPE_SLOTS; ++s)
 		ZEN_CUDA_CHECK(cudaStreamSynchronize(b->streams[s]));
 	b->last_launches = launches;
 	return ZEN_OK;
 }
+
+}  // namespace
+
+extern "C" int zen_hpr_batch_process_host(zen_hpr_batch* b, const float* h_in, long in_stride, int n_streams, long n_hops,
+                                          float* h_out_h, float* h_out_p, float* h_out_r, long out_stride)
+{
+	return batch_process_host_impl<float>(b, h_in, in_stride, n_streams, n_hops, h_out_h, h_out_p, h_out_r, out_stride, nullptr,
+	                                      nullptr, nullptr);
+}
+
+extern "C" int zen_hpr_batch_process_host_pcm16(zen_hpr_batch* b, const int16_t* h_in, long in_stride, int n_streams, long n_hops,
+                                                int16_t* h_out_h, int16_t* h_out_p, int16_t* h_out_r, long out_stride,
+                                                float* h_peaks_h, float* h_peaks_p, float* h_peaks_r)
+{
+	return batch_process_host_impl<int16_t>(b, h_in, in_stride, n_streams, n_hops, h_out_h, h_out_p, h_out_r, out_stride, h_peaks_h,
+	                                        h_peaks_p, h_peaks_r);
+}
+
+extern "C" {
 
 // ---------------------------------------------------------------- offline ---
 

@@ -5,111 +5,254 @@
 //   float32 -> peak-normalised PCM16, as the command line writes its outputs
 //     (zen/offline.h:180-192 / zen/fakert.h:259-268: x /= max(-min, max);
 //      vendor/libnyquist/src/Common.cpp:332-337: (int16_t)lroundf(x * 32767.f), no dither).
-// Every stream (row) of a batch is independent.  Pure streaming kernels: 2-4 B in + 4 B out per frame for the decode,
-// 4 B in (peak pass) + 4 B in + 2 B out for the encode; IEEE division / multiplication as the reference's host code.
+// Every stream (row) of a batch is independent.  Pure streaming kernels, bound by HBM: 2-4 B in + 4 B out per
+// frame for the decode, 4 B in (peak pass) + 4 B in + 2 B out for the encode.  Each thread moves 16 bytes per
+// access (8 samples of PCM16, 4 floats); rows are folded into the x dimension of the grid, so any number of
+// streams fits one launch.  The results are the reference's bit for bit:
+//   * s / 32767.f is evaluated as q = s*r, q' = fma(fma(-q, 32767, s), r, q) with r = RN(1/32767): correctly
+//     rounded for every int16 s (checked exhaustively, tests/test_pcm.py::test_div32767_exact), three FMA-pipe
+//     instructions instead of the IEEE division's slow path;
+//   * x / peak keeps the IEEE division (the divisor is arbitrary).
 #include <cstdint>
 
 #include "zen_common.cuh"
 
 namespace {
 
-__global__ void pcm16_decode_kernel(const int16_t* __restrict__ pcm, long pcm_stride, int channels, float* __restrict__ out,
-                                    long out_stride, long n_frames)
+__device__ __forceinline__ float pcm_to_float(int s)
 {
-	const int16_t* src = pcm + (size_t)blockIdx.y * pcm_stride;
-	float* dst = out + (size_t)blockIdx.y * out_stride;
-	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames; i += (long)gridDim.x * blockDim.x) {
-		float v;
-		if (channels == 2) {
-			const float l = __fdiv_rn((float)src[2 * i], 32767.0f), r = __fdiv_rn((float)src[2 * i + 1], 32767.0f);
-			v = __fdiv_rn(__fadd_rn(l, r), 2.0f);
+	const float r = 1.0f / 32767.0f;  // RN(1/32767), folded at compile time
+	const float x = (float)s;
+	const float q = __fmul_rn(x, r);
+	const float e = __fmaf_rn(-q, 32767.0f, x);
+	return __fmaf_rn(e, r, q);
+}
+
+__device__ __forceinline__ float stereo_fold(int l, int r)
+{
+	return __fmul_rn(__fadd_rn(pcm_to_float(l), pcm_to_float(r)), 0.5f);  // (l + r) / 2.0f, exact halving
+}
+
+// one work item = 8 consecutive output frames of one row
+template <int CH, bool VEC>
+__global__ void __launch_bounds__(256) pcm16_decode_kernel(const int16_t* __restrict__ pcm, long pcm_stride, float* __restrict__ out,
+                                                          long out_stride, long n_frames, long items_per_row, long total_items)
+{
+	for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < total_items; it += (long)gridDim.x * blockDim.x) {
+		const long row = it / items_per_row;
+		const long i0 = (it - row * items_per_row) * 8;
+		const int16_t* src = pcm + (size_t)row * pcm_stride + (size_t)i0 * CH;
+		float* dst = out + (size_t)row * out_stride + i0;
+		if (VEC && i0 + 8 <= n_frames) {
+			float v[8];
+			if (CH == 1) {
+				const int4 p = __ldcs(reinterpret_cast<const int4*>(src));
+				const int w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					v[2 * j] = pcm_to_float((int)(short)(w[j] & 0xffff));
+					v[2 * j + 1] = pcm_to_float(w[j] >> 16);
+				}
+			}
+			else {
+				const int4 p0 = __ldcs(reinterpret_cast<const int4*>(src)), p1 = __ldcs(reinterpret_cast<const int4*>(src) + 1);
+				const int w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+					v[j] = stereo_fold((int)(short)(w[j] & 0xffff), w[j] >> 16);
+			}
+			reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+			reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
 		}
 		else {
-			v = __fdiv_rn((float)src[i], 32767.0f);
+			for (long i = 0; i < 8 && i0 + i < n_frames; ++i)
+				dst[i] = CH == 1 ? pcm_to_float(src[i]) : stereo_fold(src[2 * i], src[2 * i + 1]);
 		}
-		dst[i] = v;
 	}
 }
 
-// max(-min, max) of a row == max |x| ; non-negative floats order like their bit patterns
-__global__ void peak_kernel(const float* __restrict__ in, long in_stride, long n, unsigned* __restrict__ peak_bits)
+// max(-min, max) of a row == max |x| ; non-negative floats order like their bit patterns.
+// One work item = 8 consecutive samples; a warp's 32 items never straddle more than two rows, so the warp
+// reduces per row segment before its atomics.
+template <bool VEC>
+__global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ in, long in_stride, long n, long items_per_row,
+                                                  long total_items, unsigned* __restrict__ peak_bits)
 {
-	const float* src = in + (size_t)blockIdx.y * in_stride;
-	float m = 0.0f;
-	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-		m = fmaxf(m, fabsf(src[i]));
-	for (int s = 16; s > 0; s >>= 1)
-		m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-	__shared__ float wm[32];
-	if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		m = threadIdx.x < (blockDim.x + 31) / 32 ? wm[threadIdx.x] : 0.0f;
-		for (int s = 16; s > 0; s >>= 1)
-			m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-		if (threadIdx.x == 0) atomicMax(peak_bits + blockIdx.y, __float_as_uint(m));
+	for (long it0 = (long)blockIdx.x * blockDim.x; it0 < total_items; it0 += (long)gridDim.x * blockDim.x) {
+		const long it = it0 + threadIdx.x;
+		float m = 0.0f;
+		long row = -1;
+		if (it < total_items) {
+			row = it / items_per_row;
+			const long i0 = (it - row * items_per_row) * 8;
+			const float* src = in + (size_t)row * in_stride + i0;
+			if (VEC && i0 + 8 <= n) {
+				const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+				m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+				          fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+			}
+			else {
+				for (long i = 0; i < 8 && i0 + i < n; ++i)
+					m = fmaxf(m, fabsf(src[i]));
+			}
+		}
+		// segmented warp reduction: lanes of the same row combine
+		const long row0 = __shfl_sync(0xffffffffu, row, 0);
+		const bool uniform = __all_sync(0xffffffffu, row == row0);
+		if (uniform) {
+			for (int s = 16; s > 0; s >>= 1)
+				m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+			if ((threadIdx.x & 31) == 0 && row >= 0 && m > 0.0f) atomicMax(peak_bits + row, __float_as_uint(m));
+		}
+		else if (row >= 0 && m > 0.0f) {
+			atomicMax(peak_bits + row, __float_as_uint(m));
+		}
 	}
 }
 
-__global__ void pcm16_encode_kernel(const float* __restrict__ in, long in_stride, long n, const unsigned* __restrict__ peak_bits,
-                                    int16_t* __restrict__ out, long out_stride)
+__device__ __forceinline__ int pcm_from_float(float v, float peak)
 {
-	const float* src = in + (size_t)blockIdx.y * in_stride;
-	int16_t* dst = out + (size_t)blockIdx.y * out_stride;
-	const float peak = __uint_as_float(peak_bits[blockIdx.y]);
-	for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-		// a silent stream has no peak to divide by (the reference would write lroundf(NaN)): it stays silent
-		const float x = peak > 0.0f ? __fdiv_rn(src[i], peak) : 0.0f;
-		dst[i] = (int16_t)lroundf(__fmul_rn(x, 32767.0f));
+	// a silent stream has no peak to divide by (the reference would write lroundf(NaN)): it stays silent
+	const float x = peak > 0.0f ? __fdiv_rn(v, peak) : 0.0f;
+	return (int)(int16_t)lroundf(__fmul_rn(x, 32767.0f));
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) pcm16_encode_kernel(const float* __restrict__ in, long in_stride, long n,
+                                                          const unsigned* __restrict__ peak_bits, int16_t* __restrict__ out,
+                                                          long out_stride, long items_per_row, long total_items)
+{
+	for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < total_items; it += (long)gridDim.x * blockDim.x) {
+		const long row = it / items_per_row;
+		const long i0 = (it - row * items_per_row) * 8;
+		const float* src = in + (size_t)row * in_stride + i0;
+		int16_t* dst = out + (size_t)row * out_stride + i0;
+		const float peak = __uint_as_float(__ldg(peak_bits + row));
+		if (VEC && i0 + 8 <= n) {
+			const float4 a = __ldcs(reinterpret_cast<const float4*>(src)), b = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+			const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+			int w[4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				w[j] = (pcm_from_float(v[2 * j], peak) & 0xffff) | (pcm_from_float(v[2 * j + 1], peak) << 16);
+			__stcs(reinterpret_cast<int4*>(dst), make_int4(w[0], w[1], w[2], w[3]));
+		}
+		else {
+			for (long i = 0; i < 8 && i0 + i < n; ++i)
+				dst[i] = (int16_t)pcm_from_float(src[i], peak);
+		}
 	}
 }
 
-int grid_x_for(long n, int n_streams)
+int grid_for(long total_items)
 {
 	int sms = 148, dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	// about eight 256-thread CTAs per SM over the whole batch, at least one per row, no more than the row needs
-	long per_row = ((long)sms * 8 + n_streams - 1) / n_streams;
-	long need = (n + 255) / 256;
-	long gx = per_row < need ? per_row : need;
-	return (int)(gx < 1 ? 1 : gx);
+	long need = (total_items + 255) / 256;
+	long cap = (long)sms * 8;  // eight 256-thread CTAs per SM, grid-stride beyond that
+	long g = need < cap ? need : cap;
+	return (int)(g < 1 ? 1 : g);
 }
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
 
 extern "C" {
 
-int zen_pcm16_decode_mono(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out, long out_stride)
+int zen_pcm16_decode_mono_async(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out,
+                                long out_stride, void* cuda_stream)
 {
 	if (!d_pcm || !d_out || (channels != 1 && channels != 2) || n_streams < 1 || n_frames < 0 || pcm_stride < n_frames * channels
-	    || out_stride < n_frames || n_streams > 65535)
+	    || out_stride < n_frames)
 		return ZEN_ERR_ARG;
 	if (zen_device_count() <= 0)
 		return ZEN_ERR_CUDA;
 	if (n_frames == 0)
 		return ZEN_OK;
-	dim3 grid(grid_x_for(n_frames, n_streams), n_streams);
-	pcm16_decode_kernel<<<grid, 256>>>(d_pcm, pcm_stride, channels, d_out, out_stride, n_frames);
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	const long ipr = (n_frames + 7) / 8, total = ipr * n_streams;
+	const bool vec = aligned16(d_pcm) && aligned16(d_out) && (pcm_stride % 8) == 0 && (out_stride % 4) == 0;
+	const int g = grid_for(total);
+	if (channels == 1) {
+		if (vec) pcm16_decode_kernel<1, true><<<g, 256, 0, s>>>(d_pcm, pcm_stride, d_out, out_stride, n_frames, ipr, total);
+		else pcm16_decode_kernel<1, false><<<g, 256, 0, s>>>(d_pcm, pcm_stride, d_out, out_stride, n_frames, ipr, total);
+	}
+	else {
+		if (vec) pcm16_decode_kernel<2, true><<<g, 256, 0, s>>>(d_pcm, pcm_stride, d_out, out_stride, n_frames, ipr, total);
+		else pcm16_decode_kernel<2, false><<<g, 256, 0, s>>>(d_pcm, pcm_stride, d_out, out_stride, n_frames, ipr, total);
+	}
 	ZEN_CUDA_CHECK(cudaGetLastError());
-	ZEN_CUDA_CHECK(cudaDeviceSynchronize());
+	return ZEN_OK;
+}
+
+int zen_pcm16_peaks_async(const float* d_in, long in_stride, int n_streams, long n, float* d_peaks, void* cuda_stream)
+{
+	if (!d_in || !d_peaks || n_streams < 1 || n < 0 || in_stride < n)
+		return ZEN_ERR_ARG;
+	if (zen_device_count() <= 0)
+		return ZEN_ERR_CUDA;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	ZEN_CUDA_CHECK(cudaMemsetAsync(d_peaks, 0, sizeof(float) * (size_t)n_streams, s));
+	if (n == 0)
+		return ZEN_OK;
+	const long ipr = (n + 7) / 8, total = ipr * n_streams;
+	const bool vec = aligned16(d_in) && (in_stride % 4) == 0;
+	const int g = grid_for(total);
+	if (vec) peak_kernel<true><<<g, 256, 0, s>>>(d_in, in_stride, n, ipr, total, reinterpret_cast<unsigned*>(d_peaks));
+	else peak_kernel<false><<<g, 256, 0, s>>>(d_in, in_stride, n, ipr, total, reinterpret_cast<unsigned*>(d_peaks));
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	return ZEN_OK;
+}
+
+int zen_pcm16_encode_with_peaks_async(const float* d_in, long in_stride, int n_streams, long n, const float* d_peaks, int16_t* d_out,
+                                      long out_stride, void* cuda_stream)
+{
+	if (!d_in || !d_out || !d_peaks || n_streams < 1 || n < 0 || in_stride < n || out_stride < n)
+		return ZEN_ERR_ARG;
+	if (zen_device_count() <= 0)
+		return ZEN_ERR_CUDA;
+	if (n == 0)
+		return ZEN_OK;
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	const long ipr = (n + 7) / 8, total = ipr * n_streams;
+	const bool vec = aligned16(d_in) && aligned16(d_out) && (in_stride % 4) == 0 && (out_stride % 8) == 0;
+	const int g = grid_for(total);
+	if (vec)
+		pcm16_encode_kernel<true><<<g, 256, 0, s>>>(d_in, in_stride, n, reinterpret_cast<const unsigned*>(d_peaks), d_out, out_stride, ipr, total);
+	else
+		pcm16_encode_kernel<false><<<g, 256, 0, s>>>(d_in, in_stride, n, reinterpret_cast<const unsigned*>(d_peaks), d_out, out_stride, ipr, total);
+	ZEN_CUDA_CHECK(cudaGetLastError());
+	return ZEN_OK;
+}
+
+int zen_pcm16_encode_normalized_async(const float* d_in, long in_stride, int n_streams, long n, int16_t* d_out, long out_stride,
+                                      float* d_peaks, void* cuda_stream)
+{
+	if (!d_out)
+		return ZEN_ERR_ARG;
+	int rc = zen_pcm16_peaks_async(d_in, in_stride, n_streams, n, d_peaks, cuda_stream);
+	if (rc != ZEN_OK)
+		return rc;
+	return zen_pcm16_encode_with_peaks_async(d_in, in_stride, n_streams, n, d_peaks, d_out, out_stride, cuda_stream);
+}
+
+// the round-1 entry points: legacy default stream, synchronous
+int zen_pcm16_decode_mono(const int16_t* d_pcm, long pcm_stride, int channels, int n_streams, long n_frames, float* d_out, long out_stride)
+{
+	int rc = zen_pcm16_decode_mono_async(d_pcm, pcm_stride, channels, n_streams, n_frames, d_out, out_stride, nullptr);
+	if (rc != ZEN_OK)
+		return rc;
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(nullptr));
 	return ZEN_OK;
 }
 
 int zen_pcm16_encode_normalized(const float* d_in, long in_stride, int n_streams, long n, int16_t* d_out, long out_stride, float* d_peaks)
 {
-	if (!d_in || !d_out || !d_peaks || n_streams < 1 || n < 0 || in_stride < n || out_stride < n || n_streams > 65535)
-		return ZEN_ERR_ARG;
-	if (zen_device_count() <= 0)
-		return ZEN_ERR_CUDA;
-	ZEN_CUDA_CHECK(cudaMemset(d_peaks, 0, sizeof(float) * (size_t)n_streams));
-	if (n == 0)
-		return ZEN_OK;
-	dim3 grid(grid_x_for(n, n_streams), n_streams);
-	peak_kernel<<<grid, 256>>>(d_in, in_stride, n, reinterpret_cast<unsigned*>(d_peaks));
-	ZEN_CUDA_CHECK(cudaGetLastError());
-	pcm16_encode_kernel<<<grid, 256>>>(d_in, in_stride, n, reinterpret_cast<const unsigned*>(d_peaks), d_out, out_stride);
-	ZEN_CUDA_CHECK(cudaGetLastError());
-	ZEN_CUDA_CHECK(cudaDeviceSynchronize());
+	int rc = zen_pcm16_encode_normalized_async(d_in, in_stride, n_streams, n, d_out, out_stride, d_peaks, nullptr);
+	if (rc != ZEN_OK)
+		return rc;
+	ZEN_CUDA_CHECK(cudaStreamSynchronize(nullptr));
 	return ZEN_OK;
 }
 

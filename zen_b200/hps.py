@@ -71,14 +71,16 @@ class IOGPU:
 
 
 class PinnedArray:
-    """float32 [rows, cols] array in page-locked host memory (zen_host_alloc)."""
+    """[rows, cols] array (float32, or int16 for PCM16 payloads) in page-locked host memory (zen_host_alloc)."""
 
-    def __init__(self, rows, cols):
-        self.nbytes = rows * cols * 4
+    def __init__(self, rows, cols, dtype=np.float32):
+        dt = np.dtype(dtype)
+        ct = {np.dtype(np.float32): ctypes.c_float, np.dtype(np.int16): ctypes.c_int16}[dt]
+        self.nbytes = rows * cols * dt.itemsize
         self.ptr = _lib.lib().zen_host_alloc(self.nbytes)
         if not self.ptr:
             raise MemoryError("zen_host_alloc(%d bytes) failed" % self.nbytes)
-        self.array = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ctypes.c_float)), (rows, cols))
+        self.array = np.ctypeslib.as_array(ctypes.cast(self.ptr, ctypes.POINTER(ct)), (rows, cols))
 
     def close(self):
         if self.ptr:
@@ -276,7 +278,9 @@ class HPRRealtime:
         for i in range(test_iters):
             io.host_in[:hop] = np.arange(i * hop, (i + 1) * hop, dtype=np.float32)
             self.p_impl.process_next_hop(io.device_in)
-        self.p_impl.synchronize()
+            # process_next_hop only enqueues the hop kernel, which reads the mapped host_in later: wait for it before
+            # host_in is refilled (in the reference the copy of in_hop has completed when the call returns)
+            self.p_impl.synchronize()
         self.p_impl.reset_buffers()
 
 
@@ -337,25 +341,72 @@ class HPRBatch:
             pass
 
     def process(self, x, outs=None):
-        """x: [n_streams, n_hops*hop] float32 CUDA tensor. Returns (H, P, R) tensors (None where disabled)."""
+        """x: [n_streams, n_hops*hop] float32 CUDA tensor (rows contiguous, any even row stride).  Returns (H, P, R)
+        tensors (None where disabled).  Equivalent to n_hops process_next_hop calls per stream: the residual of the
+        soft-mask / SSE variants is all zeros (libzen/hps.cu:435-449, 562)."""
         torch = _torch()
+        if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda or (x.shape[1] > 1 and x.stride(1) != 1):
+            raise ValueError("HPRBatch.process: x must be a 2-D float32 CUDA tensor with contiguous rows")
         n_streams, n = x.shape
+        if n % self.hop != 0 or n == 0:
+            raise ValueError("HPRBatch.process: the row length must be a positive multiple of hop")
         n_hops = n // self.hop
         if outs is None:
-            outs = [torch.empty_like(x) if self.flags & (1 << o) else None for o in range(3)]
+            outs = [torch.empty((n_streams, n), dtype=torch.float32, device=x.device) if self.flags & (1 << o) else None for o in range(3)]
+        strides = set()
+        for o in outs:
+            if o is None:
+                continue
+            if o.shape != x.shape or o.dtype != torch.float32 or o.device != x.device or (n > 1 and o.stride(1) != 1):
+                raise ValueError("HPRBatch.process: outputs must match x in shape / dtype / device and have contiguous rows")
+            strides.add(o.stride(0) if n_streams > 1 else n)
+        if len(strides) > 1:
+            raise ValueError("HPRBatch.process: all outputs must share one row stride")
+        out_stride = strides.pop() if strides else n
+        in_stride = x.stride(0) if n_streams > 1 else n
         ptr = [o.data_ptr() if o is not None else None for o in outs]
-        check(_lib.lib().zen_hpr_batch_process(self._b, x.data_ptr(), x.stride(0), n_streams, n_hops, ptr[0], ptr[1], ptr[2],
-                                               x.stride(0), torch.cuda.current_stream().cuda_stream), "zen_hpr_batch_process")
+        check(_lib.lib().zen_hpr_batch_process(self._b, x.data_ptr(), in_stride, n_streams, n_hops, ptr[0], ptr[1], ptr[2],
+                                               out_stride, torch.cuda.current_stream().cuda_stream), "zen_hpr_batch_process")
         return outs
+
+    @staticmethod
+    def _host_rows(a, name, itemsize):
+        """(address, row stride in elements) of a 2-D host array with contiguous rows"""
+        if isinstance(a, np.ndarray):
+            if a.ndim != 2 or a.itemsize != itemsize or (a.shape[1] > 1 and a.strides[1] != itemsize) or a.strides[0] % itemsize:
+                raise ValueError("HPRBatch: %s must be 2-D with contiguous rows" % name)
+            return a.ctypes.data, (a.strides[0] // itemsize if a.shape[0] > 1 else a.shape[1])
+        if a.dim() != 2 or a.element_size() != itemsize or (a.shape[1] > 1 and a.stride(1) != 1):
+            raise ValueError("HPRBatch: %s must be 2-D with contiguous rows" % name)
+        return a.data_ptr(), (a.stride(0) if a.shape[0] > 1 else a.shape[1])
+
+    def _process_host(self, fn, what, x, outs, itemsize, extra=()):
+        n_streams, n = x.shape
+        if n % self.hop != 0 or n == 0:
+            raise ValueError("HPRBatch.%s: the row length must be a positive multiple of hop" % what)
+        xa, xs = self._host_rows(x, "x", itemsize)
+        oa, os_ = [None, None, None], set()
+        for i, o in enumerate(outs):
+            if o is None:
+                continue
+            if tuple(o.shape) != tuple(x.shape):
+                raise ValueError("HPRBatch.%s: outputs must have the shape of x" % what)
+            oa[i], st = self._host_rows(o, "outs[%d]" % i, itemsize)
+            os_.add(st)
+        if len(os_) > 1:
+            raise ValueError("HPRBatch.%s: all outputs must share one row stride" % what)
+        check(fn(self._b, xa, xs, n_streams, n // self.hop, oa[0], oa[1], oa[2], os_.pop() if os_ else n, *extra), what)
 
     def process_host(self, x, outs):
         """x, outs[*]: [n_streams, n_hops*hop] float32 host arrays (numpy or pinned torch tensors)."""
-        def addr(a):
-            return None if a is None else (a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
-        n_streams, n = x.shape
-        n_hops = n // self.hop
-        check(_lib.lib().zen_hpr_batch_process_host(self._b, addr(x), n, n_streams, n_hops, addr(outs[0]), addr(outs[1]),
-                                                    addr(outs[2]), n), "zen_hpr_batch_process_host")
+        self._process_host(_lib.lib().zen_hpr_batch_process_host, "zen_hpr_batch_process_host", x, outs, 4)
+
+    def process_host_pcm16(self, x, outs, peaks=(None, None, None)):
+        """The command line's sample format on both sides of the link (zen/offline.h:88-117, 180-223): x and outs[*] are
+        [n_streams, n_hops*hop] int16 host arrays; every output comes back peak-normalised per stream and converted as
+        libnyquist does.  peaks[*]: optional float32 arrays [n_streams] receiving the divisors."""
+        pk = [None if p is None else p.ctypes.data for p in peaks]
+        self._process_host(_lib.lib().zen_hpr_batch_process_host_pcm16, "zen_hpr_batch_process_host_pcm16", x, outs, 2, extra=pk)
 
     @property
     def last_kernel_ms(self):

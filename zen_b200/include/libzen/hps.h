@@ -155,8 +155,10 @@ namespace hps {
 	template <zen::Backend B>
 	void HPRRealtime<B>::process_next_hop(thrust::device_ptr<float> in)
 	{
-		// asynchronous: the copy_* call that follows (zen/fakert.h:229-230) waits for it
+		// the hop has been read when this returns, as in the reference (hps.cu:452-453): callers refill `in` right away
+		// (zen/fakert.h:225-229).  The outputs are waited for by the copy_* call that follows.
 		zen::b200_detail::check(zen_hpr_process_next_hop(p_impl->handle(), thrust::raw_pointer_cast(in)), "process_next_hop");
+		zen::b200_detail::check(zen_hpr_wait_input_consumed(p_impl->handle()), "process_next_hop");
 	}
 
 	template <zen::Backend B>
