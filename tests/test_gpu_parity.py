@@ -417,6 +417,34 @@ def test_decision_path_equals_median_path(torch, zen, fs, hop, flags, causal, cb
             assert np.abs(a).max() > 0
 
 
+@pytest.mark.parametrize("fs,hop,flags", [(44100.0, 1024, 2), (44100.0, 1024, 7), (44100.0, 1024, 4), (44100.0, 1024, 5), (44100.0, 512, 2),
+                                          (44100.0, 512, 3), (44100.0, 2048, 7), (44100.0, 4096, 6), (48000.0, 1024, 2), (22050.0, 1024, 7),
+                                          (44100.0, 128, 7)])
+def test_fast_tile_kernel_equals_general_kernel(torch, zen, fs, hop, flags):
+    """hpr_tile_fast_kernel (window and overlap-add fused into the FFT stages, eight bins decided per thread) against
+    hpr_tile_kernel (ZEN_B200_NO_FAST=1) on the plans it serves: identical bit for bit, ragged tiles, odd stream count"""
+    n_hops, n_streams = 131, 3
+    audio = np.stack([synth_audio(n_hops * hop, seed=900 + s, fs=int(fs)) for s in range(n_streams)])
+    audio[1, : 7 * hop] = 0.0     # a silent lead-in: zero magnitudes, trivial thresholds
+    x = torch.from_numpy(audio).cuda()
+    res = []
+    for no_fast in (False, True):
+        if no_fast:
+            os.environ["ZEN_B200_NO_FAST"] = "1"
+        else:
+            os.environ.pop("ZEN_B200_NO_FAST", None)
+        b = zen.HPRBatch(fs, hop, 2.5, flags)
+        outs = b.process(x)
+        torch.cuda.synchronize()
+        res.append([o.cpu().numpy() if o is not None else None for o in outs])
+        b.close()
+    os.environ.pop("ZEN_B200_NO_FAST", None)
+    for a, b_ in zip(*res):
+        if a is not None:
+            assert np.array_equal(a, b_)
+            assert np.isfinite(a).all() and np.abs(a).max() > 0
+
+
 @pytest.mark.parametrize("fs,hop,flags,cb,sse,soft", [(44100.0, 1024, 2, True, False, False), (44100.0, 1024, 7, False, False, False),
                                                       (48000.0, 256, 7, True, False, False), (44100.0, 512, 3, True, True, False),
                                                       (44100.0, 512, 7, True, False, True), (44100.0, 4096, 7, True, False, False)])

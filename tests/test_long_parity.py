@@ -16,6 +16,10 @@ from zen_b200.synth import synth_audio
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL_ABS, TOL_SNR = 1e-4, 80.0      # BASELINE.json north_star: max abs <= 1e-4, SNR >= 80 dB (peak-normalised)
+# A flipped hard-mask bin must be a borderline decision of the oracle: |ratio - beta| / beta below this.  The margin
+# a last-bit difference of the two FFTs can bridge grows as the bin gets weaker relative to the frame (the FFT error is
+# absolute); over the 2583 to 10336-hop runs here the largest observed is 2.2e-5 (gpurun_out/long_parity.json).
+MARGIN_TOL = 6e-5
 FS = 44100
 
 
@@ -67,7 +71,7 @@ def test_config4_full_length_streams(torch, zen, oracle):
     for s in range(n_streams):
         o = oracle.OracleHPR(oracle.GEOM_GPU, float(FS), hop, beta, 2, oracle.CAUSAL, True)
         h = zen.HPR(float(FS), hop, beta, 2, 0, True)
-        r = flip_aware_compare(h, o, audio[s], hop, 2, hard_mask=True)
+        r = flip_aware_compare(h, o, audio[s], hop, 2, hard_mask=True, margin_tol=MARGIN_TOL)
         h.close()
         o.close()
         rec = _summ(r, n_hops)
@@ -114,7 +118,7 @@ def test_config2_offline_two_pass_60s(torch, zen, oracle):
         a[:n] = audio
         o = oracle.OracleHPR(oracle.GEOM_GPU, float(FS), hop, beta, flags, oracle.ANTICAUSAL, True)
         h = zen.HPR(float(FS), hop, beta, flags, 1, True)
-        r = flip_aware_compare(h, o, a, hop, flags, hard_mask=True)
+        r = flip_aware_compare(h, o, a, hop, flags, hard_mask=True, margin_tol=MARGIN_TOL)
         h.close()
         o.close()
         rec[name] = _summ(r, n_hops)

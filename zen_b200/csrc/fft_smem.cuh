@@ -1,36 +1,96 @@
-// Shared-memory Stockham FFT (radix 8/4/2, autosort, in place through registers)
-// used by every kernel in this library.  Replaces cuFFT as driven by
-// FFTC2CWrapperGPU (libzen/fftw.h:20-49): unnormalised in both directions.
+// Shared-memory Stockham FFT (radix 8/4/2, autosort) used by every kernel in this library.  Replaces cuFFT as
+// driven by FFTC2CWrapperGPU (libzen/fftw.h:20-49): unnormalised in both directions.
 //
-// Layout: complex values as float2 in shared memory, index padded by one slot
-// every 16 (fpad) so the stride-R stores of the early stages spread over banks.
+// Arithmetic: complex values are float2 and every complex add / subtract / twiddle multiply is ONE or TWO packed
+// fp32x2 instructions of sm_100 (add.rn.f32x2 / mul.rn.f32x2 / fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2).  The SASS
+// forms take a swapped (.LO_HI), half-negated (.NP / .PN) or broadcast (.F32) operand for free, so multiplying by
+// +-i, conjugating a twiddle and broadcasting a real part cost nothing: a radix-8 butterfly is 26 packed
+// instructions instead of ~60 scalar ones, a twiddle multiply 2 instead of 4.
+//
+// Layout: float2 in shared memory, index padded by one slot every 16 (fpad) so the stride-R stores of the early
+// stages spread over banks.  The load index j + r*NB and the store index j0 + r*NS are turned into ONE padded base
+// plus compile-time offsets wherever the stride allows it (fpad is additive over multiples of 16).
+//
+// Every variant below (in place, ping-pong, first stage fed by a functor, last stage drained by a functor) runs
+// the SAME butterfly code, so their results are bit-identical: the batched, the per-launch and the resident
+// real-time kernels may pick whichever suits them.
 #pragma once
 #include <cmath>
 #include <cuda_runtime.h>
 
 namespace zen_b200 {
 
-__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+__host__ __device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
 __host__ __device__ constexpr int fpad_size(int n) { return n + (n >> 4) + 1; }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+// ---- packed fp32x2 ----------------------------------------------------------------------------------------
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk(float lo, float hi)
 {
-	return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+	f32x2_t r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
 }
+__device__ __forceinline__ f32x2_t pk(float2 a) { return pk(a.x, a.y); }
+__device__ __forceinline__ float2 up(f32x2_t v)
+{
+	float2 r;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+	return r;
+}
+__device__ __forceinline__ f32x2_t padd(f32x2_t a, f32x2_t b)
+{
+	f32x2_t d;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ f32x2_t psub(f32x2_t a, f32x2_t b)
+{
+	f32x2_t d;
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ f32x2_t pmul(f32x2_t a, f32x2_t b)
+{
+	f32x2_t d;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ f32x2_t pfma(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+	f32x2_t d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return up(padd(pk(a), pk(b))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return up(psub(pk(a), pk(b))); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-// multiply by S*i  (S = -1 forward, +1 inverse)
+// a * w:  (ax wx - ay wy, ax wy + ay wx) = ax * (wx, wy) + ay * (-wy, wx)
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+	return up(pfma(pk(a.y, a.y), pk(-w.y, w.x), pmul(pk(a.x, a.x), pk(w.x, w.y))));
+}
+// a * conj(w)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 w)
+{
+	return up(pfma(pk(a.y, a.y), pk(w.y, w.x), pmul(pk(a.x, a.x), pk(w.x, -w.y))));
+}
+// a * s (both parts)
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return up(pmul(pk(a), pk(s, s))); }
+// multiply by S*i  (S = -1 forward, +1 inverse): an operand modifier once it feeds a packed instruction
 template <int S>
 __device__ __forceinline__ float2 mul_si(float2 a)
 {
 	return S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
+// a + s * b (both parts scaled by the same real s)
+__device__ __forceinline__ float2 caxpy(float2 a, float s, float2 b) { return up(pfma(pk(b), pk(s, s), pk(a))); }
 
 template <int S>
 __device__ __forceinline__ void dft2(float2* v)
 {
-	float2 t = v[0];
+	const float2 t = v[0];
 	v[0] = cadd(t, v[1]);
 	v[1] = csub(t, v[1]);
 }
@@ -38,12 +98,31 @@ __device__ __forceinline__ void dft2(float2* v)
 template <int S>
 __device__ __forceinline__ void dft4(float2* v)
 {
-	float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
-	float2 a2 = cadd(v[1], v[3]), a3 = mul_si<S>(csub(v[1], v[3]));
+	const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+	const float2 a2 = cadd(v[1], v[3]), a3 = mul_si<S>(csub(v[1], v[3]));
 	v[0] = cadd(a0, a2);
 	v[2] = csub(a0, a2);
 	v[1] = cadd(a1, a3);
 	v[3] = csub(a1, a3);
+}
+
+// second half of the radix-8 butterfly: e = DFT4 of the even inputs, o = DFT4 of the odd ones
+template <int S>
+__device__ __forceinline__ void dft8_combine(float2* v, const float2* e, const float2* o)
+{
+	const float h = 0.70710678118654752440f;
+	// o1 * w8 = h * (o1 + S i o1) ; o2 * w8^2 = S i o2 ; o3 * w8^3 = h * (S i o3 - o3)
+	const float2 t1 = cadd(o[1], mul_si<S>(o[1]));
+	const float2 t3 = csub(mul_si<S>(o[3]), o[3]);
+	const float2 o2 = mul_si<S>(o[2]);
+	v[0] = cadd(e[0], o[0]);
+	v[4] = csub(e[0], o[0]);
+	v[1] = caxpy(e[1], h, t1);
+	v[5] = caxpy(e[1], -h, t1);
+	v[2] = cadd(e[2], o2);
+	v[6] = csub(e[2], o2);
+	v[3] = caxpy(e[3], h, t3);
+	v[7] = caxpy(e[3], -h, t3);
 }
 
 template <int S>
@@ -53,30 +132,48 @@ __device__ __forceinline__ void dft8(float2* v)
 	float2 o[4] = {v[1], v[3], v[5], v[7]};
 	dft4<S>(e);
 	dft4<S>(o);
-	const float h = 0.70710678118654752440f;
-	const float s = (float)S;
-	float2 o1 = make_float2(h * (o[1].x - s * o[1].y), h * (s * o[1].x + o[1].y));
-	float2 o2 = mul_si<S>(o[2]);
-	float2 o3 = make_float2(h * (-o[3].x - s * o[3].y), h * (s * o[3].x - o[3].y));
-	v[0] = cadd(e[0], o[0]);
-	v[4] = csub(e[0], o[0]);
-	v[1] = cadd(e[1], o1);
-	v[5] = csub(e[1], o1);
-	v[2] = cadd(e[2], o2);
-	v[6] = csub(e[2], o2);
-	v[3] = cadd(e[3], o3);
-	v[7] = csub(e[3], o3);
+	dft8_combine<S>(v, e, o);
 }
 
-template <int S, int R>
+// radix-8 butterfly whose inputs 4..7 are zero (first stage of a zero-padded frame): the two inner DFT4 shrink to
+// four packed operations each
+template <int S>
+__device__ __forceinline__ void dft8_zin(float2* v)
+{
+	float2 e[4], o[4];
+	const float2 r2 = mul_si<S>(v[2]), r3 = mul_si<S>(v[3]);
+	e[0] = cadd(v[0], v[2]);
+	e[2] = csub(v[0], v[2]);
+	e[1] = cadd(v[0], r2);
+	e[3] = csub(v[0], r2);
+	o[0] = cadd(v[1], v[3]);
+	o[2] = csub(v[1], v[3]);
+	o[1] = cadd(v[1], r3);
+	o[3] = csub(v[1], r3);
+	dft8_combine<S>(v, e, o);
+}
+
+template <int S, int R, bool ZIN = false>
 __device__ __forceinline__ void dftR(float2* v)
 {
-	if constexpr (R == 8)
-		dft8<S>(v);
+	if constexpr (R == 8) {
+		if constexpr (ZIN)
+			dft8_zin<S>(v);
+		else
+			dft8<S>(v);
+	}
 	else if constexpr (R == 4)
 		dft4<S>(v);
 	else
 		dft2<S>(v);
+}
+
+// radix of the stage that follows sub-transforms of length NS in an M-point transform
+template <int M, int NS>
+constexpr int fft_radix()
+{
+	constexpr int rem = M / NS;
+	return (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
 }
 
 // Per-stage twiddle tables.  Stage (NS, R) needs w^(r*k) for r = 1..R-1, k = 0..NS-1 with
@@ -90,8 +187,7 @@ constexpr int fft_twiddle_count()
 		return 0;
 	}
 	else {
-		constexpr int rem = M / NS;
-		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
+		constexpr int R = fft_radix<M, NS>();
 		return (NS > 1 ? (R - 1) * NS : 0) + fft_twiddle_count<M, NS * R>();
 	}
 }
@@ -128,83 +224,6 @@ inline int fft_twiddle_count_rt(int M)
 	return n;
 }
 
-// One Stockham decimation-in-time stage of radix R on an M-point transform
-// whose already-combined sub-transforms have length NS.  tw points at this stage's table.
-// ZIN : the upper half of the input is known to be zero (zero-padded frame): those loads and the butterfly
-//       arithmetic that depends on them disappear (first stage only).
-// HOUT: only the lower half of the output is needed: the stores of the upper half and the arithmetic feeding
-//       them disappear (last stage only).
-// GT  : tw may point into shared memory (the resident real-time kernel keeps its tables there): plain generic
-//       loads instead of the read-only global path.
-template <int M, int NT, int S, int R, int NS, bool ZIN = false, bool HOUT = false, bool GT = false>
-__device__ __forceinline__ void fft_stage(float2* buf, const float2* __restrict__ tw, int tid)
-{
-	constexpr int NB = M / R;
-	constexpr int PER = (NB + NT - 1) / NT;
-	float2 v[PER][R];
-#pragma unroll
-	for (int b = 0; b < PER; ++b) {
-		int j = tid + b * NT;
-		if ((NB % NT == 0) || j < NB) {
-			int k = j & (NS - 1);
-			float2 w[R];
-			if constexpr (NS > 1) {
-#pragma unroll
-				for (int r = 1; r < R; ++r)
-					w[r] = GT ? tw[(r - 1) * NS + k] : __ldg(&tw[(r - 1) * NS + k]);
-			}
-#pragma unroll
-			for (int r = 0; r < R; ++r) {
-				if (ZIN && r >= R / 2)
-					v[b][r] = make_float2(0.0f, 0.0f);
-				else
-					v[b][r] = buf[fpad(j + r * NB)];
-			}
-			if constexpr (NS > 1) {
-#pragma unroll
-				for (int r = 1; r < R; ++r) {
-					if (S > 0)
-						w[r].y = -w[r].y;
-					v[b][r] = cmul(v[b][r], w[r]);
-				}
-			}
-			dftR<S, R>(v[b]);
-		}
-	}
-	__syncthreads();
-#pragma unroll
-	for (int b = 0; b < PER; ++b) {
-		int j = tid + b * NT;
-		if ((NB % NT == 0) || j < NB) {
-			int k = j & (NS - 1);
-			int j0 = (j - k) * R + k;
-#pragma unroll
-			for (int r = 0; r < R; ++r)
-				if (!(HOUT && r >= R / 2))
-					buf[fpad(j0 + r * NS)] = v[b][r];
-		}
-	}
-	__syncthreads();
-}
-
-// M-point complex FFT in shared memory, all NT threads of the CTA participate.
-// tw: the per-stage tables of fft_fill_twiddles(M).  The caller must have
-// synchronised after filling buf.  Ends synchronised.
-template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
-__device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
-{
-	if constexpr (NS < M) {
-		constexpr int rem = M / NS;
-		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
-		fft_stage<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M), GT>(buf, tw, tid);
-		fft_smem<M, NT, S, NS * R, ZIN, HOUT, GT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
-	}
-}
-
-// ---- out-of-place (ping-pong) variant --------------------------------------
-// Each stage reads src and writes dst, so one barrier per stage suffices (the in-place stage needs one between its
-// loads and its stores as well).  Used where latency, not shared-memory footprint, matters: the resident real-time
-// kernel.  fft_smem_pp returns the buffer that holds the result (a after an even number of stages, else b).
 template <int M, int NS = 1>
 constexpr int fft_stage_count()
 {
@@ -212,66 +231,183 @@ constexpr int fft_stage_count()
 		return 0;
 	}
 	else {
-		constexpr int rem = M / NS;
-		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
-		return 1 + fft_stage_count<M, NS * R>();
+		return 1 + fft_stage_count<M, NS * fft_radix<M, NS>()>();
 	}
 }
 
-template <int M, int NT, int S, int R, int NS, bool ZIN = false, bool HOUT = false, bool GT = false>
-__device__ __forceinline__ void fft_stage_pp(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw, int tid)
+// padded position of element base + r * STRIDE given the padded position of `base`
+template <int STRIDE>
+__device__ __forceinline__ int fpad_step(int base, int base_padded, int r)
+{
+	if constexpr (STRIDE % 16 == 0)
+		return base_padded + r * (STRIDE + STRIDE / 16);
+	else
+		return fpad(base + r * STRIDE);
+}
+
+// shared-memory source / sink of a stage (the default I/O); `p` is the padded position
+struct SmemLoad {
+	const float2* buf;
+	__device__ __forceinline__ float2 operator()(int /*idx*/, int p) const { return buf[p]; }
+};
+struct SmemStore {
+	float2* buf;
+	__device__ __forceinline__ void operator()(int /*idx*/, int p, float2 v) const { buf[p] = v; }
+};
+
+// One Stockham decimation-in-time stage of radix R on an M-point transform whose already-combined sub-transforms
+// have length NS.  tw points at this stage's table.  Element j + r*NB comes from ld(index, padded position), element
+// j0 + r*NS goes to st(index, padded position, value).
+// ZIN : the upper half of the input is known to be zero (zero-padded frame): those loads and the butterfly
+//       arithmetic that depends on them disappear (first stage only).
+// HOUT: only the lower half of the output is needed: the stores of the upper half and the arithmetic feeding
+//       them disappear (last stage only; the packed operations are plain asm, dead ones are dropped).
+// GT  : tw may point into shared memory (the resident real-time kernel keeps its tables there): plain generic
+//       loads instead of the read-only global path.
+// MID : barrier between the loads and the stores (needed when the stage works in place).
+template <int M, int NT, int S, int R, int NS, bool ZIN, bool HOUT, bool GT, bool MID, typename LD, typename ST>
+__device__ __forceinline__ void fft_stage_io(const float2* __restrict__ tw, int tid, LD ld, ST st)
 {
 	constexpr int NB = M / R;
 	constexpr int PER = (NB + NT - 1) / NT;
+	float2 v[PER][R];
 #pragma unroll
 	for (int b = 0; b < PER; ++b) {
-		int j = tid + b * NT;
+		const int j = tid + b * NT;
 		if ((NB % NT == 0) || j < NB) {
-			float2 v[R];
-			int k = j & (NS - 1);
-			float2 w[R];
-			if constexpr (NS > 1) {
-#pragma unroll
-				for (int r = 1; r < R; ++r)
-					w[r] = GT ? tw[(r - 1) * NS + k] : __ldg(&tw[(r - 1) * NS + k]);
-			}
+			const int k = j & (NS - 1);
+			const int jp = fpad(j);
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
 				if (ZIN && r >= R / 2)
-					v[r] = make_float2(0.0f, 0.0f);
+					v[b][r] = make_float2(0.0f, 0.0f);
 				else
-					v[r] = src[fpad(j + r * NB)];
+					v[b][r] = ld(j + r * NB, fpad_step<NB>(j, jp, r));
 			}
 			if constexpr (NS > 1) {
 #pragma unroll
 				for (int r = 1; r < R; ++r) {
-					if (S > 0)
-						w[r].y = -w[r].y;
-					v[r] = cmul(v[r], w[r]);
+					if (ZIN && r >= R / 2)
+						continue;
+					const float2 w = GT ? tw[(r - 1) * NS + k] : __ldg(&tw[(r - 1) * NS + k]);
+					v[b][r] = S > 0 ? cmulc(v[b][r], w) : cmul(v[b][r], w);
 				}
 			}
-			dftR<S, R>(v);
-			int j0 = (j - k) * R + k;
-#pragma unroll
-			for (int r = 0; r < R; ++r)
-				if (!(HOUT && r >= R / 2))
-					dst[fpad(j0 + r * NS)] = v[r];
+			dftR<S, R, ZIN>(v[b]);
 		}
 	}
-	__syncthreads();
+	if (MID) __syncthreads();
+#pragma unroll
+	for (int b = 0; b < PER; ++b) {
+		const int j = tid + b * NT;
+		if ((NB % NT == 0) || j < NB) {
+			const int k = j & (NS - 1);
+			const int j0 = (j - k) * R + k;
+			// padded position of j0 + r*NS as one base plus compile-time offsets where the geometry allows it
+			int base_p;
+			if constexpr (NS == 1 && R == 8)
+				base_p = 8 * j + (j >> 1);                      // (8j + r) >> 4 == j >> 1
+			else if constexpr (NS == 8 && R == 8)
+				base_p = 68 * (j >> 3) + k;                     // (64q + k + 8r) >> 4 == 4q + (r >> 1)
+			else
+				base_p = fpad(j0);
+#pragma unroll
+			for (int r = 0; r < R; ++r) {
+				if (HOUT && r >= R / 2)
+					continue;
+				int p;
+				if constexpr (NS == 1 && R == 8)
+					p = base_p + r;
+				else if constexpr (NS == 8 && R == 8)
+					p = base_p + 8 * r + (r >> 1);
+				else
+					p = fpad_step<NS>(j0, base_p, r);
+				st(j0 + r * NS, p, v[b][r]);
+			}
+		}
+	}
 }
 
+// M-point complex FFT in shared memory, IN PLACE, all NT threads of the CTA participate.
+// tw: the per-stage tables of fft_fill_twiddles(M).  The caller must have synchronised after filling buf.
+// Ends synchronised.
+template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
+__device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
+{
+	if constexpr (NS < M) {
+		constexpr int R = fft_radix<M, NS>();
+		fft_stage_io<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M), GT, true>(tw, tid, SmemLoad{buf}, SmemStore{buf});
+		__syncthreads();
+		fft_smem<M, NT, S, NS * R, ZIN, HOUT, GT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
+	}
+}
+
+// ---- out-of-place (ping-pong) variant --------------------------------------
+// Each stage reads one buffer and writes the other, so one barrier per stage suffices.  The first stage may take its
+// input from a functor `first(index, padded position)` (e.g. the windowed frame straight from global memory) and
+// the last stage may hand its output to a functor `last(index, padded position, value)` (e.g. the overlap-add
+// into global memory) instead of shared memory.  FIRST_FN / LAST_FN select that; with both false this is the plain
+// ping-pong transform from `a` (result in the returned buffer: a after an even number of stages, else b).
+// With FIRST_FN the first stage writes b... see fft_pp_first_target.
+struct NoFn {
+};
+
+template <int M, int NT, int S, int NS, bool ZIN, bool HOUT, bool GT, bool LAST_FN, typename LAST>
+__device__ __forceinline__ float2* fft_pp_rest(float2* src, float2* dst, const float2* __restrict__ tw, int tid, LAST last)
+{
+	if constexpr (NS < M) {
+		constexpr int R = fft_radix<M, NS>();
+		constexpr bool is_last = NS * R == M;
+		if constexpr (is_last && LAST_FN) {
+			fft_stage_io<M, NT, S, R, NS, (ZIN && NS == 1), HOUT, GT, false>(tw, tid, SmemLoad{src}, last);
+			return nullptr;  // the result went to the functor; NOT synchronised (the caller decides)
+		}
+		else {
+			fft_stage_io<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && is_last), GT, false>(tw, tid, SmemLoad{src}, SmemStore{dst});
+			__syncthreads();
+			return fft_pp_rest<M, NT, S, NS * R, ZIN, HOUT, GT, LAST_FN>(dst, src, tw + (NS > 1 ? (R - 1) * NS : 0), tid, last);
+		}
+	}
+	else {
+		return src;
+	}
+}
+
+// plain ping-pong transform: input in a, scratch b
 template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
 __device__ __forceinline__ float2* fft_smem_pp(float2* a, float2* b, const float2* __restrict__ tw, int tid)
 {
+	return fft_pp_rest<M, NT, S, NS, ZIN, HOUT, GT, false>(a, b, tw, tid, NoFn{});
+}
+
+// first stage fed by `first`, written to `a`; the remaining stages ping-pong between a and b.  `last` (LAST_FN)
+// receives the output of the final stage.  Requires at least two stages (M >= 64).  Returns the buffer holding the
+// result (nullptr with LAST_FN).  Ends synchronised unless LAST_FN.
+template <int M, int NT, int S, bool ZIN, bool HOUT, bool GT, bool LAST_FN, typename FIRST, typename LAST>
+__device__ __forceinline__ float2* fft_pp_fused(float2* a, float2* b, const float2* __restrict__ tw, int tid, FIRST first, LAST last)
+{
+	constexpr int R = fft_radix<M, 1>();
+	static_assert(R < M, "fft_pp_fused needs at least two stages");
+	fft_stage_io<M, NT, S, R, 1, ZIN, false, GT, false>(tw, tid, first, SmemStore{a});
+	__syncthreads();
+	return fft_pp_rest<M, NT, S, R, ZIN, HOUT, GT, LAST_FN>(a, b, tw, tid, last);
+}
+
+// in-place transform whose LAST stage hands its output to `last(index, padded position, value)` instead of storing
+// it (the other stages need their barrier between loads and stores).  Not synchronised at the end.
+template <int M, int NT, int S, int NS, bool HOUT, bool GT, typename LAST>
+__device__ __forceinline__ void fft_inplace_last(float2* buf, const float2* __restrict__ tw, int tid, LAST last)
+{
 	if constexpr (NS < M) {
-		constexpr int rem = M / NS;
-		constexpr int R = (rem % 8 == 0 && rem != 16) ? 8 : ((rem % 4 == 0) ? 4 : 2);
-		fft_stage_pp<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M), GT>(a, b, tw, tid);
-		return fft_smem_pp<M, NT, S, NS * R, ZIN, HOUT, GT>(b, a, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
-	}
-	else {
-		return a;
+		constexpr int R = fft_radix<M, NS>();
+		if constexpr (NS * R == M) {
+			fft_stage_io<M, NT, S, R, NS, false, HOUT, GT, false>(tw, tid, SmemLoad{buf}, last);
+		}
+		else {
+			fft_stage_io<M, NT, S, R, NS, false, false, GT, true>(tw, tid, SmemLoad{buf}, SmemStore{buf});
+			__syncthreads();
+			fft_inplace_last<M, NT, S, NS * R, HOUT, GT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid, last);
+		}
 	}
 }
 

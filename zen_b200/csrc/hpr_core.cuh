@@ -168,6 +168,29 @@ __device__ __forceinline__ float mask_sse(float x, float y)
 	return x * x / (x * x + y * y + ZEN_EPS);          // hps.h:132-140
 }
 
+
+// ---- real-input FFT glue, shared by every kernel (so that they agree bit for bit) -----------------------
+// Bins k and M-k (0 < k < M/2) of the nfft-point real-input spectrum from the M-point transform Z of the frame
+// packed as even/odd samples: A = Z[k], Zm = Z[M-k], w = exp(-2 pi i k / nfft).
+__device__ __forceinline__ void rfft_split_pair(float2 A, float2 Zm, float2 w, float2& Xa, float2& Xb)
+{
+	const float2 B = cconj(Zm);
+	const float2 Sm = cadd(A, B);
+	const float2 O = cmul(w, csub(A, B));
+	const float2 Or = make_float2(O.y, -O.x);          // -i O
+	Xa = cscale(cadd(Sm, Or), 0.5f);
+	Xb = cconj(cscale(csub(Sm, Or), 0.5f));
+}
+// the inverse: A = Y[k], Yb = Y[M-k] (masked spectrum), w as above -> Z[k], Z[M-k] of the packed M-point inverse
+__device__ __forceinline__ void rfft_pack_pair(float2 A, float2 Yb, float2 w, float2& Zk, float2& Zmk)
+{
+	const float2 B = cconj(Yb);
+	const float2 E2 = cadd(A, B);
+	const float2 O2 = mul_si<+1>(cmulc(csub(A, B), w));  // i conj(w) (A - B)
+	Zk = cadd(E2, O2);
+	Zmk = cconj(csub(E2, O2));
+}
+
 // masks of the percussive (mp) and harmonic (mh) outputs at half-spectrum bin k
 template <int NFFT>
 __device__ __forceinline__ void hpr_masks(const HprDev& P, const float* prow, const float* hrow, int k, float& mp, float& mh)
@@ -457,13 +480,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 				Xb = Xa;
 			}
 			else {
-				float2 A = sm.zbuf[fpad(k)];
-				float2 B = cconj(sm.zbuf[fpad(M - k)]);
-				float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
-				float2 O = cmul(ldt(&t_twr[k]), csub(A, B));
-				float2 D = make_float2(0.5f * O.y, -0.5f * O.x);
-				Xa = cadd(E, D);
-				Xb = cconj(csub(E, D));
+				rfft_split_pair(sm.zbuf[fpad(k)], sm.zbuf[fpad(M - k)], ldt(&t_twr[k]), Xa, Xb);
 			}
 			float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
 			if (P.sse) {
@@ -712,8 +729,8 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 			float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
 			float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];
-			float2 A = make_float2(Xa.x * ma, Xa.y * ma);   // hps.h:58-66
-			float2 Yb = make_float2(Xb.x * mb, Xb.y * mb);
+			float2 A = cscale(Xa, ma);   // hps.h:58-66
+			float2 Yb = cscale(Xb, mb);
 			if (k == 0) {
 				sm.zbuf[fpad(0)] = make_float2(A.x + Yb.x, A.x - Yb.x);
 			}
@@ -721,11 +738,10 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 				sm.zbuf[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
 			}
 			else {
-				float2 B = cconj(Yb);
-				float2 E2 = cadd(A, B);
-				float2 O2 = cmul(cconj(ldt(&t_twr[k])), csub(A, B));
-				sm.zbuf[fpad(k)] = make_float2(E2.x - O2.y, E2.y + O2.x);
-				sm.zbuf[fpad(kb)] = make_float2(E2.x + O2.y, O2.x - E2.y);
+				float2 Zk, Zmk;
+				rfft_pack_pair(A, Yb, ldt(&t_twr[k]), Zk, Zmk);
+				sm.zbuf[fpad(k)] = Zk;
+				sm.zbuf[fpad(kb)] = Zmk;
 			}
 		}
 		__syncthreads();
@@ -738,6 +754,408 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 		uint4* const pdst = !pk ? nullptr : (o == 0 ? pk->dst[0] : (o == 1 ? pk->dst[1] : pk->dst[2]));
 		hpr_ola_emit<NFFT, NT>(P, sm.zbuf, tail, fresh_tail, ea, eb, pk ? pk->buf : nullptr, pdst, pk ? pk->tag : 0u);
 		stamp(8);
+	}
+}
+
+// ---- the batched fast path -------------------------------------------------------------------------------
+// hpr_fast_iteration serves the default plan of HPRRealtime / the headline batch (hard mask decided by counting,
+// copy-border, lag 1, at most 7 time taps) with about half the instructions of hpr_iteration.  Same arithmetic,
+// same helper functions, bit-identical results; what changes is how the data moves:
+//   * the window multiply is the loader of the first forward-FFT stage (straight from global memory) and the
+//     overlap-add is the sink of the last inverse-FFT stage (straight to global memory): no staging passes;
+//   * the FFTs ping-pong between two shared-memory buffers (one barrier per stage); the spectrum X of the frame
+//     and the packed masked spectrum live in the same two buffers;
+//   * one thread decides EIGHT consecutive bins: their time medians come from 16-byte loads of the |X| ring, the
+//     8 + L - 1 frequency taps they share from 16-byte shared-memory loads, and the per-tap work is two compares
+//     (FSET) and ONE packed add (FADD2) per pair of bins - 1.5 issue slots per (tap, bin) instead of 2;
+//   * decisions travel as one bit per bin.
+template <int NFFT>
+struct FastSmem {
+	static constexpr int M = NFFT / 2;
+	static constexpr int ZN = (fpad_size(M) + 1) & ~1;
+	float2* za;            // ZN
+	float2* zb;            // ZN
+	float* erow;           // |X| of the consumed frame, bin k at erow[midp + k], mirrored borders; 16-byte aligned
+	unsigned short* codes; // entry k >> 3, bit k & 7: percussive decision of bin k; bit 8 + (k & 7): harmonic
+	static __host__ __device__ size_t erow_floats(int Lp) { return (size_t)((M + 1 + Lp + 16 + 3) & ~3); }
+	static __host__ __device__ size_t bytes(int Lp)
+	{
+		return 2 * sizeof(float2) * (size_t)ZN + sizeof(float) * erow_floats(Lp) + sizeof(unsigned short) * (size_t)((M / 8 + 1 + 7) & ~7);
+	}
+	__device__ void carve(unsigned char* base, int Lp)
+	{
+		za = reinterpret_cast<float2*>(base);
+		zb = za + ZN;
+		erow = reinterpret_cast<float*>(zb + ZN);
+		codes = reinterpret_cast<unsigned short*>(erow + erow_floats(Lp));
+	}
+};
+
+// per-CTA state of the fast path (global scratch that stays in L2)
+struct FastState {
+	float* mag_ring;   // W rows of ring_stride floats (multiple of 4, rows 16-byte aligned)
+	int ring_stride;
+	float* tail[3];    // HOP floats per output (H, P, R)
+};
+
+__host__ __device__ inline bool hpr_fast_supported(const HprDev& P)
+{
+	return P.decide && !P.sse && !P.soft && P.copy_bord && P.lag == 1 && P.Lp >= 9 && (P.n_taps == 1 || P.n_taps == 3 || P.n_taps == 5 || P.n_taps == 7);
+}
+
+// peak of |emitted sample| per output, kept by each thread across the hops of a tile (optional)
+struct FastPeaks {
+	float v[3];
+};
+
+// ring offset of time tap t for hop i (ring slot `slot` = i mod W), -1: the frame lies before the stream start
+__device__ __forceinline__ int fast_ring_off(const HprDev& P, const FastState& st, int i, int slot, int t)
+{
+	const int age = P.tap_age[t];
+	int sl = slot - age;
+	sl += sl < 0 ? P.W : 0;
+	return (i - age) >= 0 ? sl * st.ring_stride : -1;
+}
+
+// time medians (hps.cu:495, only the consumed row) of the eight bins k0 .. k0 + 7
+template <int NTAPS>
+__device__ __forceinline__ void fast_h8(const HprDev& P, const FastState& st, int i, int slot, int k0, float (&H)[8])
+{
+#pragma unroll
+	for (int half = 0; half < 2; ++half) {
+		float4 v[NTAPS];
+#pragma unroll
+		for (int t = 0; t < NTAPS; ++t) {
+			const int off = fast_ring_off(P, st, i, slot, t);
+			v[t] = off >= 0 ? *reinterpret_cast<const float4*>(st.mag_ring + off + k0 + 4 * half) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		}
+		float w[NTAPS];
+#pragma unroll
+		for (int t = 0; t < NTAPS; ++t) w[t] = v[t].x;
+		H[4 * half + 0] = median_regs<NTAPS>(w);
+#pragma unroll
+		for (int t = 0; t < NTAPS; ++t) w[t] = v[t].y;
+		H[4 * half + 1] = median_regs<NTAPS>(w);
+#pragma unroll
+		for (int t = 0; t < NTAPS; ++t) w[t] = v[t].z;
+		H[4 * half + 2] = median_regs<NTAPS>(w);
+#pragma unroll
+		for (int t = 0; t < NTAPS; ++t) w[t] = v[t].w;
+		H[4 * half + 3] = median_regs<NTAPS>(w);
+	}
+}
+__device__ __forceinline__ float fast_h1(const HprDev& P, const FastState& st, int i, int slot, int k)
+{
+	float w[7];
+#pragma unroll
+	for (int t = 0; t < 7; ++t) {
+		w[t] = 0.0f;
+		if (t < P.n_taps) {
+			const int off = fast_ring_off(P, st, i, slot, t);
+			w[t] = off >= 0 ? st.mag_ring[off + k] : 0.0f;
+		}
+	}
+	if (P.n_taps == 1) return w[0];
+	if (P.n_taps == 3) {
+		float u[3] = {w[0], w[1], w[2]};
+		return median_regs<3>(u);
+	}
+	if (P.n_taps == 5) {
+		float u[5] = {w[0], w[1], w[2], w[3], w[4]};
+		return median_regs<5>(u);
+	}
+	return median_regs<7>(w);
+}
+
+// one frequency tap x that belongs to bins LO..HI of the eight: counts, two bins per packed register
+template <int LO, int HI, bool WP, bool WH>
+__device__ __forceinline__ void fast_tap(float x, const float (&tau)[8], const float (&sig)[8], f32x2_t (&cp)[4], f32x2_t (&ch)[4])
+{
+	const float xe = x + ZEN_EPS;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		constexpr int dummy = 0;
+		(void)dummy;
+		const int u0 = 2 * q, u1 = 2 * q + 1;
+		const bool a0 = u0 >= LO && u0 <= HI, a1 = u1 >= LO && u1 <= HI;
+		if (!a0 && !a1) continue;
+		if (WP) {
+			const float s0 = a0 ? ((x >= tau[u0]) ? 1.0f : 0.0f) : 0.0f;
+			const float s1 = a1 ? ((x >= tau[u1]) ? 1.0f : 0.0f) : 0.0f;
+			cp[q] = padd(cp[q], pk(s0, s1));
+		}
+		if (WH) {
+			const float s0 = a0 ? ((xe <= sig[u0]) ? 1.0f : 0.0f) : 0.0f;
+			const float s1 = a1 ? ((xe <= sig[u1]) ? 1.0f : 0.0f) : 0.0f;
+			ch[q] = padd(ch[q], pk(s0, s1));
+		}
+	}
+}
+
+// decisions of bins k0 .. k0 + 7 given their time medians: bit u = percussive, bit 8 + u = harmonic
+// (Mp = [P/(H+eps) >= beta], Mh = [H/(P+eps) >= beta-eps], hps.h:100-113, decided by counting: see decide_group_t)
+template <bool WP, bool WH>
+__device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float* __restrict__ Eg, const float (&H)[8])
+{
+	const int L = P.Lp;
+	float tau[8], sig[8];
+#pragma unroll
+	for (int u = 0; u < 8; ++u) {
+		tau[u] = WP ? thr_ratio_ge(H[u] + ZEN_EPS, P.rule_p) : CUDART_INF_F;
+		sig[u] = WH ? thr_ratio_le(H[u], P.rule_h) : -1.0f;
+	}
+	f32x2_t cp[4], ch[4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+		cp[q] = ch[q] = pk(0.0f, 0.0f);
+	// tap j of bin k0 + u is Eg[j] for u <= j < u + L.  Head: taps 0..7 (L >= 9, so tap 7 already belongs to all eight)
+	{
+		const float4 h0 = *reinterpret_cast<const float4*>(Eg), h1 = *reinterpret_cast<const float4*>(Eg + 4);
+		fast_tap<0, 0, WP, WH>(h0.x, tau, sig, cp, ch);
+		fast_tap<0, 1, WP, WH>(h0.y, tau, sig, cp, ch);
+		fast_tap<0, 2, WP, WH>(h0.z, tau, sig, cp, ch);
+		fast_tap<0, 3, WP, WH>(h0.w, tau, sig, cp, ch);
+		fast_tap<0, 4, WP, WH>(h1.x, tau, sig, cp, ch);
+		fast_tap<0, 5, WP, WH>(h1.y, tau, sig, cp, ch);
+		fast_tap<0, 6, WP, WH>(h1.z, tau, sig, cp, ch);
+		fast_tap<0, 7, WP, WH>(h1.w, tau, sig, cp, ch);
+	}
+	// body: whole vectors of taps that belong to all eight bins: 8 <= 4 v and 4 v + 3 <= L - 1
+	const int v_end = (L - 4) / 4;
+	int v = 2;
+#pragma unroll 2
+	for (; v <= v_end; ++v) {
+		const float4 x = *reinterpret_cast<const float4*>(Eg + 4 * v);
+		fast_tap<0, 7, WP, WH>(x.x, tau, sig, cp, ch);
+		fast_tap<0, 7, WP, WH>(x.y, tau, sig, cp, ch);
+		fast_tap<0, 7, WP, WH>(x.z, tau, sig, cp, ch);
+		fast_tap<0, 7, WP, WH>(x.w, tau, sig, cp, ch);
+	}
+	// tail: taps 4 v .. L + 6, tap j belongs to bins j - L + 1 .. 7
+	for (int j = 4 * v; j < L + 7; ++j) {
+		const float x = Eg[j];
+		const float xe = x + ZEN_EPS;
+		const int lo = j - L + 1;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int u0 = 2 * q, u1 = 2 * q + 1;
+			if (WP) {
+				const float s0 = (u0 >= lo && x >= tau[u0]) ? 1.0f : 0.0f;
+				const float s1 = (u1 >= lo && x >= tau[u1]) ? 1.0f : 0.0f;
+				cp[q] = padd(cp[q], pk(s0, s1));
+			}
+			if (WH) {
+				const float s0 = (u0 >= lo && xe <= sig[u0]) ? 1.0f : 0.0f;
+				const float s1 = (u1 >= lo && xe <= sig[u1]) ? 1.0f : 0.0f;
+				ch[q] = padd(ch[q], pk(s0, s1));
+			}
+		}
+	}
+	const float need = (float)(L / 2 + 1);
+	unsigned code = 0u;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const float2 c = up(cp[q]), d = up(ch[q]);
+		if (WP) {
+			code |= (c.x >= need ? 1u : 0u) << (2 * q);
+			code |= (c.y >= need ? 1u : 0u) << (2 * q + 1);
+		}
+		if (WH) {
+			code |= (d.x >= need ? 1u : 0u) << (8 + 2 * q);
+			code |= (d.y >= need ? 1u : 0u) << (8 + 2 * q + 1);
+		}
+	}
+	return code;
+}
+
+template <int NFFT, int NT, bool PEAKS>
+__device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFFT>& sm, const FastState& st, const int i, const int slot,
+                                                   const float* __restrict__ prev, const float* __restrict__ cur, bool full, bool fresh_tail,
+                                                   const HprEmit& em, const float* next_hop, FastPeaks& peaks)
+{
+	constexpr int M = NFFT / 2;   // complex FFT length; also nwin
+	constexpr int HC = M / 4;     // complex (packed even/odd) samples per hop
+	const int tid = threadIdx.x;
+	const int midp = P.midp;
+	// the two FFT buffers swap roles every hop: the last inverse stage of hop i still reads the buffer the first
+	// forward stage of hop i wrote, so hop i + 1 starts in the other one and no barrier is needed in between
+	float2* const a = (i & 1) ? sm.zb : sm.za;
+	float2* const b = (i & 1) ? sm.za : sm.zb;
+
+	if (next_hop != nullptr && tid < (HC * 8) / 128)
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(next_hop) + tid * 128));
+
+	// ---- A + B. sqrt-Hann window (hps.cu:452-462) fused into the forward FFT (hps.cu:465)
+	const float2* const win2 = reinterpret_cast<const float2*>(P.window);
+	const float2* const prev2 = reinterpret_cast<const float2*>(prev);
+	const float2* const cur2 = reinterpret_cast<const float2*>(cur);
+	auto load_frame = [&](int idx, int /*p*/) -> float2 {
+		float2 x;
+		if (idx < HC)  // last use of that hop: streaming load, so it does not push the per-CTA scratch out of L2
+			x = prev2 ? __ldcs(prev2 + idx) : make_float2(0.0f, 0.0f);
+		else
+			x = cur2[idx - HC];
+		const float2 w = __ldg(win2 + idx);
+		return up(pmul(pk(x), pk(w)));
+	};
+	float2* const zres = fft_pp_fused<M, NT, -1, true, false, false, false>(a, b, P.tw, tid, load_frame, NoFn{});
+	float2* const zoth = zres == a ? b : a;
+
+	// ---- C. split into the real-input spectrum X[0..M] (into zoth, natural order), magnitudes into the ring and
+	// into erow (hps.cu:469-472, 492-493)
+	{
+		float* mag_row = st.mag_ring + (size_t)slot * st.ring_stride;
+		float* const E = sm.erow + midp;
+		for (int k = tid; k <= M / 2; k += NT) {
+			float2 Xa, Xb;
+			const int kb = M - k;
+			if (k == 0) {
+				const float2 Z0 = zres[0];
+				Xa = make_float2(Z0.x + Z0.y, 0.0f);
+				Xb = make_float2(Z0.x - Z0.y, 0.0f);
+			}
+			else if (k == M / 2) {
+				Xa = cconj(zres[fpad(M / 2)]);
+				Xb = Xa;
+			}
+			else {
+				rfft_split_pair(zres[fpad(k)], zres[fpad(kb)], __ldg(&P.twr[k]), Xa, Xb);
+			}
+			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
+			mag_row[k] = ma;
+			mag_row[kb] = mb;
+			zoth[k] = Xa;
+			zoth[kb] = Xb;
+			E[k] = ma;
+			E[kb] = mb;
+			// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]|
+			if (k >= 1 && k <= midp) {
+				E[-k] = ma;
+				E[M + k] = mb;
+			}
+		}
+	}
+	__syncthreads();
+	if (!full)
+		return;
+
+	// ---- F' + E'. time medians of eight bins per thread, thresholds, decisions by counting
+	{
+		// a mask is only computed for an output that is enabled; the residual mask 1 - (Mh + Mp) uses whatever the
+		// other two hold, zeros included (hps.cu:498-567)
+		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
+		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
+		for (int g = tid; g < M / 8; g += NT) {
+			const int k0 = 8 * g;
+			float H[8];
+			switch (P.n_taps) {
+			case 1: fast_h8<1>(P, st, i, slot, k0, H); break;
+			case 3: fast_h8<3>(P, st, i, slot, k0, H); break;
+			case 5: fast_h8<5>(P, st, i, slot, k0, H); break;
+			default: fast_h8<7>(P, st, i, slot, k0, H); break;
+			}
+			const float* const Eg = sm.erow + k0;
+			unsigned code;
+			if (want_p && want_h)
+				code = fast_decide8<true, true>(P, Eg, H);
+			else if (want_p)
+				code = fast_decide8<true, false>(P, Eg, H);
+			else if (want_h)
+				code = fast_decide8<false, true>(P, Eg, H);
+			else
+				code = 0u;
+			sm.codes[g] = (unsigned short)code;
+		}
+		// the Nyquist bin k = M: one warp, one tap per lane and round
+		if (tid < 32) {
+			const float Hm = fast_h1(P, st, i, slot, M);
+			const float tau = want_p ? thr_ratio_ge(Hm + ZEN_EPS, P.rule_p) : CUDART_INF_F;
+			const float sig = want_h ? thr_ratio_le(Hm, P.rule_h) : -1.0f;
+			const int L = P.Lp;
+			int np = 0, nh = 0;
+			for (int j0 = 0; j0 < L; j0 += 32) {
+				const int j = j0 + tid;
+				const float x = j < L ? sm.erow[M + j] : -1.0f;   // window of bin M: erow[M .. M + L)
+				np += __popc(__ballot_sync(0xffffffffu, j < L && x >= tau));
+				nh += __popc(__ballot_sync(0xffffffffu, j < L && (x + ZEN_EPS) <= sig));
+			}
+			const int need = L / 2 + 1;
+			if (tid == 0)
+				sm.codes[M / 8] = (unsigned short)((np >= need ? 1u : 0u) | ((nh >= need ? 1u : 0u) << 8));
+		}
+	}
+	__syncthreads();
+
+	// ---- G. per output: mask, inverse real FFT, overlap-add (hps.cu:498-579); order P, H, R as in the reference
+	int last_o = -1;
+#pragma unroll
+	for (int oi = 0; oi < 3; ++oi) {
+		const int o = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
+		if (P.out_flags & (1 << o)) last_o = o;
+	}
+#pragma unroll 1
+	for (int oi = 0; oi < 3; ++oi) {
+		const int o = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
+		if (!(P.out_flags & (1 << o)))
+			continue;
+		// masked spectrum packed for the M-point inverse transform, into zres (X stays in zoth)
+		for (int k = tid; k <= M / 2; k += NT) {
+			const int kb = M - k;
+			const unsigned ca = (unsigned)sm.codes[k >> 3] >> (k & 7), cb = (unsigned)sm.codes[kb >> 3] >> (kb & 7);
+			const float mpa = (float)(ca & 1u), mha = (float)((ca >> 8) & 1u);
+			const float mpb = (float)(cb & 1u), mhb = (float)((cb >> 8) & 1u);
+			const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
+			const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
+			const float2 A = cscale(zoth[k], ma);   // hps.h:58-66
+			const float2 Yb = cscale(zoth[kb], mb);
+			if (k == 0) {
+				zres[0] = make_float2(A.x + Yb.x, A.x - Yb.x);
+			}
+			else if (k == M / 2) {
+				zres[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
+			}
+			else {
+				float2 Zk, Zmk;
+				rfft_pack_pair(A, Yb, __ldg(&P.twr[k]), Zk, Zmk);
+				zres[fpad(k)] = Zk;
+				zres[fpad(kb)] = Zmk;
+			}
+		}
+		__syncthreads();
+		// inverse FFT (hps.cu:522) whose last stage IS the overlap-add (hps.h:68-80): the thread that holds sample
+		// pair n < HC of the frame also holds pair n + HC, i.e. it reads tail[n], emits, then writes the new tail[n]
+		float* const tail = o == 0 ? st.tail[0] : (o == 1 ? st.tail[1] : st.tail[2]);
+		float* const ea = o == 0 ? em.a[0] : (o == 1 ? em.a[1] : em.a[2]);
+		float2* const tail2 = reinterpret_cast<float2*>(tail);
+		float2* const ea2 = reinterpret_cast<float2*>(ea);
+		const float cola = P.cola;
+		float pk_local = 0.0f;
+		auto ola = [&](int idx, int /*p*/, float2 v) {
+			if (idx < HC) {
+				const float2 t = fresh_tail ? make_float2(0.0f, 0.0f) : tail2[idx];
+				const float2 r = up(pfma(pk(v), pk(cola, cola), pk(t)));
+				if (ea2) {
+					__stcs(ea2 + idx, r);  // written once, never re-read by the kernel
+					if (PEAKS) pk_local = fmaxf(pk_local, fmaxf(fabsf(r.x), fabsf(r.y)));
+				}
+			}
+			else {
+				tail2[idx - HC] = up(pmul(pk(v), pk(cola, cola)));
+			}
+		};
+		if (o == last_o) {
+			// nobody needs X any more: ping-pong through its buffer, one barrier per stage, none at the end
+			fft_pp_rest<M, NT, +1, 1, false, true, false, true>(zres, zoth, P.tw, tid, ola);
+		}
+		else {
+			fft_inplace_last<M, NT, +1, 1, true, false>(zres, P.tw, tid, ola);
+			__syncthreads();  // the next output packs into zres
+		}
+		if (PEAKS) {
+			if (o == 0) peaks.v[0] = fmaxf(peaks.v[0], pk_local);
+			else if (o == 1) peaks.v[1] = fmaxf(peaks.v[1], pk_local);
+			else peaks.v[2] = fmaxf(peaks.v[2], pk_local);
+		}
 	}
 }
 
@@ -828,13 +1246,7 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 				Xb = Xa;
 			}
 			else {
-				float2 A = sm.zbuf[fpad(k)];
-				float2 B = cconj(sm.zbuf[fpad(M - k)]);
-				float2 E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y + B.y));
-				float2 O = cmul(tb.twr[k], csub(A, B));
-				float2 D = make_float2(0.5f * O.y, -0.5f * O.x);
-				Xa = cadd(E, D);
-				Xb = cconj(csub(E, D));
+				rfft_split_pair(sm.zbuf[fpad(k)], sm.zbuf[fpad(M - k)], tb.twr[k], Xa, Xb);
 			}
 			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
 			mag_row[ka] = ma;
@@ -917,7 +1329,7 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 			const float mpa = 0.5f * (float)((ca & 1u) + ((ca >> 1) & 1u)), mha = 0.5f * (float)(((ca >> 2) & 1u) + ((ca >> 3) & 1u));
 			const float mpb = 0.5f * (float)((cb & 1u) + ((cb >> 1) & 1u)), mhb = 0.5f * (float)(((cb >> 2) & 1u) + ((cb >> 3) & 1u));
 			const float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];
-			const float2 twc = cconj(tb.twr[k]);
+			const float2 twk = tb.twr[k];
 #pragma unroll
 			for (int o = 0; o < 3; ++o) {
 				if (!sp.recv[o])
@@ -925,8 +1337,8 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 				float2* zb = sp.recv[o] + recv_off;
 				const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 				const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
-				const float2 A = make_float2(Xa.x * ma, Xa.y * ma);   // hps.h:58-66
-				const float2 Yb = make_float2(Xb.x * mb, Xb.y * mb);
+				const float2 A = cscale(Xa, ma);   // hps.h:58-66
+				const float2 Yb = cscale(Xb, mb);
 				if (k == 0) {
 					zb[fpad(0)] = make_float2(A.x + Yb.x, A.x - Yb.x);
 				}
@@ -934,11 +1346,10 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 					zb[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
 				}
 				else {
-					const float2 B = cconj(Yb);
-					const float2 E2 = cadd(A, B);
-					const float2 O2 = cmul(twc, csub(A, B));
-					zb[fpad(k)] = make_float2(E2.x - O2.y, E2.y + O2.x);
-					zb[fpad(kb)] = make_float2(E2.x + O2.y, O2.x - E2.y);
+					float2 Zk, Zmk;
+					rfft_pack_pair(A, Yb, twk, Zk, Zmk);
+					zb[fpad(k)] = Zk;
+					zb[fpad(kb)] = Zmk;
 				}
 			}
 		}

@@ -182,7 +182,9 @@ size_t tile_scratch_floats(const Plan& pl)
 	ring += ring & 1;
 	size_t xr = pl.dev.lag > 1 ? 2 * (size_t)pl.dev.lag * (M + 1) : 0;
 	size_t tails = 3 * (size_t)pl.dev.hop;
-	return (ring + xr + tails + 3) & ~(size_t)3;
+	const size_t general = ring + xr + tails;
+	const size_t fast = (size_t)pl.dev.W * (M + 4) + tails;   // hpr_tile_fast_kernel: 16-byte aligned ring rows
+	return (std::max(general, fast) + 3) & ~(size_t)3;
 }
 
 int resident_ctas_for(const Plan& pl)
@@ -200,11 +202,20 @@ int resident_ctas_for(const Plan& pl)
 	return 0;
 }
 
+// peaks (optional): per output a device array of n_streams floats, zeroed by the caller, that receives max |emitted
+// sample| per stream (only where the fast path applies: tile_peaks_supported)
+bool tile_peaks_supported(const Plan& pl) { return hpr_fast_supported(pl.dev) && !std::getenv("ZEN_B200_NO_FAST"); }
+
 int dispatch_tile(const Plan& pl, const float* in, long in_stride, float* oh, float* op, float* orr, long out_stride,
-                  int n_streams, long n_hops, int tile_hops, float* scratch, int* work_counter, int resident, cudaStream_t s)
+                  int n_streams, long n_hops, int tile_hops, float* scratch, int* work_counter, int resident, cudaStream_t s,
+                  float* const* peaks = nullptr)
 {
 	TileArgs a{pl.dev, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, tile_scratch_floats(pl),
 	           work_counter, resident, s};
+	a.force_general = std::getenv("ZEN_B200_NO_FAST") ? 1 : 0;  // debugging aid / A-B test: the general kernel everywhere
+	if (peaks)
+		for (int o = 0; o < 3; ++o)
+			a.peaks[o] = reinterpret_cast<unsigned*>(peaks[o]);
 	switch (pl.nfft) {
 	case 128: return launch_tile_impl<128>(a);
 	case 256: return launch_tile_impl<256>(a);
@@ -1526,9 +1537,20 @@ int batch_process_host_impl(zen_hpr_batch* b, const T* h_in, long in_stride, int
 		}
 		if (zero_r && h_out[2])
 			ZEN_CUDA_CHECK(cudaMemsetAsync(b->d_stage_out[slot][2], 0, drow * sizeof(float) * ns, st));
+		// PCM16: the peaks the outputs are normalised by come out of the fused kernel itself where it can track them
+		// (max |emitted sample| per stream, one atomicMax per tile), otherwise from a pass over the outputs
+		const bool fused_peaks = PCM && tile_peaks_supported(b->plan) && !(zero_r && h_out[2]);
+		float* pk[3] = {nullptr, nullptr, nullptr};
+		if (fused_peaks)
+			for (int o = 0; o < 3; ++o)
+				if (h_out[o]) {
+					pk[o] = b->d_peaks[slot][o];
+					ZEN_CUDA_CHECK(cudaMemsetAsync(pk[o], 0, sizeof(float) * ns, st));
+				}
 		rc = dispatch_tile(b->plan, b->d_stage_in[slot], (long)drow, h_out[0] ? b->d_stage_out[slot][0] : nullptr,
 		                   h_out[1] ? b->d_stage_out[slot][1] : nullptr, h_out[2] ? b->d_stage_out[slot][2] : nullptr, (long)drow, ns,
-		                   n_hops, tile, b->d_scratch + slot * scratch_half, b->d_counters + slot, b->resident, st);
+		                   n_hops, tile, b->d_scratch + slot * scratch_half, b->d_counters + slot, b->resident, st,
+		                   fused_peaks ? pk : nullptr);
 		if (rc != ZEN_OK)
 			return rc;
 		++launches;
@@ -1536,11 +1558,17 @@ int batch_process_host_impl(zen_hpr_batch* b, const T* h_in, long in_stride, int
 			if (!h_out[o]) continue;
 			if (PCM) {
 				// what the command line does with every output: x / max|x|, then PCM16 (zen/offline.h:180-223)
-				rc = zen_pcm16_encode_normalized_async(b->d_stage_out[slot][o], (long)drow, ns, (long)row,
-				                                       reinterpret_cast<int16_t*>(b->d_pcm_out[slot][o]), (long)drow, b->d_peaks[slot][o], st);
+				if (!fused_peaks) {
+					rc = zen_pcm16_peaks_async(b->d_stage_out[slot][o], (long)drow, ns, (long)row, b->d_peaks[slot][o], st);
+					if (rc != ZEN_OK)
+						return rc;
+					++launches;
+				}
+				rc = zen_pcm16_encode_with_peaks_async(b->d_stage_out[slot][o], (long)drow, ns, (long)row, b->d_peaks[slot][o],
+				                                       reinterpret_cast<int16_t*>(b->d_pcm_out[slot][o]), (long)drow, st);
 				if (rc != ZEN_OK)
 					return rc;
-				launches += 2;
+				++launches;
 				ZEN_CUDA_CHECK(cudaMemcpy2DAsync(h_out[o] + (size_t)s0 * out_stride, (size_t)out_stride * sizeof(T), b->d_pcm_out[slot][o],
 				                                 drow * sizeof(T), row * sizeof(T), ns, cudaMemcpyDeviceToHost, st));
 				if (h_peaks[o])

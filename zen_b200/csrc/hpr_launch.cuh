@@ -39,6 +39,8 @@ struct TileArgs {
 	int* work_counter;       // device int, zeroed by the launcher
 	int resident_ctas;       // grid size (<= SMs * occupancy)
 	cudaStream_t stream;
+	unsigned* peaks[3] = {nullptr, nullptr, nullptr};  // optional per-stream max |out| (fast path only), zeroed by the caller
+	int force_general = 0;   // debugging / A-B: run hpr_iteration even where the fast path applies
 };
 
 struct HopArgs {
@@ -182,6 +184,81 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_kerne
 			em.b[0] = em.b[1] = em.b[2] = nullptr;
 			hpr_iteration<NFFT, NT>(P, sm, st, (int)i, prev, cur, i >= i_full, i == i_full, em, nullptr, nullptr,
 			                        i + 1 < e1 ? cur + HOP : nullptr);
+		}
+	}
+}
+
+// The same walk over (stream, tile) work items on the fast path (hpr_fast_iteration: hard mask, copy-border, lag 1).
+// Per-CTA scratch: W ring rows of RS = M + 4 floats (16-byte aligned rows) followed by the three overlap-add tails.
+// peaks (optional): per stream and output, max |emitted sample| as the bit pattern of a non-negative float
+// (atomicMax): the divisor of the command line's peak normalisation (zen/offline.h:180-192), for free.
+template <int NFFT>
+constexpr int fast_ring_stride()
+{
+	return NFFT / 2 + 4;
+}
+template <int NFFT, int NT, bool PEAKS>
+__global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_fast_kernel(const __grid_constant__ HprDev P,
+                                                                                 const float* __restrict__ in, long in_stride,
+                                                                                 float* out_h, float* out_p, float* out_r, long out_stride,
+                                                                                 long n_hops, int tile_hops, int n_tiles, int total_items,
+                                                                                 int* work_counter, float* scratch, size_t scratch_per_cta,
+                                                                                 unsigned* peaks_h, unsigned* peaks_p, unsigned* peaks_r)
+{
+	constexpr int M = NFFT / 2, HOP = M / 2;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	FastSmem<NFFT> sm;
+	sm.carve(smem_raw, P.Lp);
+	__shared__ int s_item;
+
+	float* sc = scratch + (size_t)blockIdx.x * scratch_per_cta;
+	FastState st;
+	st.mag_ring = sc;
+	st.ring_stride = fast_ring_stride<NFFT>();
+	sc += (size_t)P.W * fast_ring_stride<NFFT>();
+	for (int o = 0; o < 3; ++o)
+		st.tail[o] = sc + (size_t)o * HOP;
+
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_item = atomicAdd(work_counter, 1);
+		__syncthreads();
+		const int item = s_item;
+		if (item >= total_items)
+			break;
+		const int stream = item / n_tiles, tile = item - stream * n_tiles;
+		const float* sin = in + (size_t)stream * in_stride;
+		const long e0 = (long)tile * tile_hops;
+		const long e1 = min(n_hops, e0 + (long)tile_hops);
+		const long i_begin = max(0L, e0 - P.W);
+		const long i_full = max(0L, e0 - 1);
+		int slot = (int)(i_begin % P.W);
+		FastPeaks pk;
+		pk.v[0] = pk.v[1] = pk.v[2] = 0.0f;
+		for (long i = i_begin; i < e1; ++i) {
+			const float* cur = sin + (size_t)i * HOP;
+			const float* prev = i > 0 ? cur - HOP : nullptr;
+			HprEmit em;
+			const bool emit = i >= e0;
+			em.a[0] = (emit && out_h) ? out_h + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+			em.a[1] = (emit && out_p) ? out_p + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+			em.a[2] = (emit && out_r) ? out_r + (size_t)stream * out_stride + (size_t)i * HOP : nullptr;
+			em.b[0] = em.b[1] = em.b[2] = nullptr;
+			hpr_fast_iteration<NFFT, NT, PEAKS>(P, sm, st, (int)i, slot, prev, cur, i >= i_full, i == i_full, em,
+			                                    i + 1 < e1 ? cur + HOP : nullptr, pk);
+			slot = slot + 1 == P.W ? 0 : slot + 1;
+		}
+		if (PEAKS) {
+			unsigned* dst[3] = {peaks_h, peaks_p, peaks_r};
+#pragma unroll
+			for (int o = 0; o < 3; ++o) {
+				if (!dst[o]) continue;
+				float m = o == 0 ? pk.v[0] : (o == 1 ? pk.v[1] : pk.v[2]);
+				for (int sft = 16; sft > 0; sft >>= 1)
+					m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+				if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(dst[o] + stream, __float_as_uint(m));
+			}
 		}
 	}
 }
@@ -680,16 +757,32 @@ template <int NFFT>
 int launch_tile_impl(const TileArgs& a)
 {
 	constexpr int NT = nt_for<NFFT>();
-	auto kern = hpr_tile_kernel<NFFT, NT>;
-	size_t smem = HprSmem<NFFT>::bytes(a.dev.Lp);
-	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	const int n_tiles = (int)((a.n_hops + a.tile_hops - 1) / a.tile_hops);
 	const long total = (long)n_tiles * a.n_streams;
 	if (total > 0x7fffffffL)
 		return ZEN_ERR_UNSUPPORTED;
 	ZEN_CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), a.stream));
 	const int grid = (int)std::min<long>(total, a.resident_ctas);
+	const bool want_peaks = a.peaks[0] || a.peaks[1] || a.peaks[2];
+	if (hpr_fast_supported(a.dev) && !a.force_general) {
+		size_t smem = FastSmem<NFFT>::bytes(a.dev.Lp);
+		auto launch = [&](auto kern) -> int {
+			ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+			kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
+			                                   n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta, a.peaks[0], a.peaks[1],
+			                                   a.peaks[2]);
+			ZEN_CUDA_CHECK(cudaGetLastError());
+			return ZEN_OK;
+		};
+		return want_peaks ? launch(hpr_tile_fast_kernel<NFFT, NT, true>) : launch(hpr_tile_fast_kernel<NFFT, NT, false>);
+	}
+	if (want_peaks)
+		return ZEN_ERR_UNSUPPORTED;  // the caller falls back to a separate peak pass
+	auto kern = hpr_tile_kernel<NFFT, NT>;
+	size_t smem = HprSmem<NFFT>::bytes(a.dev.Lp);
+	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
 	                                   n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta);
 	ZEN_CUDA_CHECK(cudaGetLastError());
@@ -701,16 +794,23 @@ template <int NFFT>
 int tile_resident_ctas(const HprDev& d)
 {
 	constexpr int NT = nt_for<NFFT>();
-	auto kern = hpr_tile_kernel<NFFT, NT>;
-	size_t smem = HprSmem<NFFT>::bytes(d.Lp);
-	if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess
-	    || cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
-		return 0;
 	int per_sm = 0, dev = 0, sms = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess
-	    || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+	auto occ = [&](auto kern, size_t smem) -> bool {
+		return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess
+		       && cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess
+		       && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) == cudaSuccess;
+	};
+	// the general kernel needs at least as much shared memory as the fast one: size the scratch for whichever holds more CTAs
+	int best = 0;
+	if (occ(hpr_tile_kernel<NFFT, NT>, HprSmem<NFFT>::bytes(d.Lp))) best = per_sm;
+	if (hpr_fast_supported(d) && occ(hpr_tile_fast_kernel<NFFT, NT, false>, FastSmem<NFFT>::bytes(d.Lp))) {
+		int f = per_sm;
+		if (occ(hpr_tile_fast_kernel<NFFT, NT, true>, FastSmem<NFFT>::bytes(d.Lp))) f = std::min(f, per_sm);
+		best = std::max(best, f);
+	}
+	if (best < 1 || cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
 		return 0;
-	return per_sm * sms;
+	return best * sms;
 }
 
 template <int NFFT>
