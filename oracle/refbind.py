@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_SO = os.path.join(_HERE, "_ref", "libzen_ref.so")
+# ZEN_REF_SO selects another build of the reference, e.g. oracle/_ref/libzen_ref_norace.so (oracle/Makefile: ref_norace)
+REF_SO = os.environ.get("ZEN_REF_SO") or os.path.join(_HERE, "_ref", "libzen_ref.so")
 
 GPU, CPU = 0, 1
 CAUSAL, ANTICAUSAL, FREQUENCY = 0, 1, 2

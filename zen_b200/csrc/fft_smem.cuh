@@ -248,7 +248,7 @@ __device__ __forceinline__ int fpad_step(int base, int base_padded, int r)
 // shared-memory source / sink of a stage (the default I/O); `p` is the padded position
 struct SmemLoad {
 	const float2* buf;
-	__device__ __forceinline__ float2 operator()(int /*idx*/, int p) const { return buf[p]; }
+	__device__ __forceinline__ float2 operator()(int /*j*/, int /*r*/, int p) const { return buf[p]; }
 };
 struct SmemStore {
 	float2* buf;
@@ -256,7 +256,7 @@ struct SmemStore {
 };
 
 // One Stockham decimation-in-time stage of radix R on an M-point transform whose already-combined sub-transforms
-// have length NS.  tw points at this stage's table.  Element j + r*NB comes from ld(index, padded position), element
+// have length NS.  tw points at this stage's table.  Element j + r*NB comes from ld(j, r, padded position), element
 // j0 + r*NS goes to st(index, padded position, value).
 // ZIN : the upper half of the input is known to be zero (zero-padded frame): those loads and the butterfly
 //       arithmetic that depends on them disappear (first stage only).
@@ -282,7 +282,7 @@ __device__ __forceinline__ void fft_stage_io(const float2* __restrict__ tw, int 
 				if (ZIN && r >= R / 2)
 					v[b][r] = make_float2(0.0f, 0.0f);
 				else
-					v[b][r] = ld(j + r * NB, fpad_step<NB>(j, jp, r));
+					v[b][r] = ld(j, r, fpad_step<NB>(j, jp, r));  // element j + r*NB (r is a constant after unrolling)
 			}
 			if constexpr (NS > 1) {
 #pragma unroll
@@ -344,7 +344,7 @@ __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__
 
 // ---- out-of-place (ping-pong) variant --------------------------------------
 // Each stage reads one buffer and writes the other, so one barrier per stage suffices.  The first stage may take its
-// input from a functor `first(index, padded position)` (e.g. the windowed frame straight from global memory) and
+// input from a functor `first(j, r, padded position)` (element j + r * M/R) (e.g. the windowed frame straight from global memory) and
 // the last stage may hand its output to a functor `last(index, padded position, value)` (e.g. the overlap-add
 // into global memory) instead of shared memory.  FIRST_FN / LAST_FN select that; with both false this is the plain
 // ping-pong transform from `a` (result in the returned buffer: a after an even number of stages, else b).

@@ -181,14 +181,29 @@ __device__ __forceinline__ void rfft_split_pair(float2 A, float2 Zm, float2 w, f
 	Xa = cscale(cadd(Sm, Or), 0.5f);
 	Xb = cconj(cscale(csub(Sm, Or), 0.5f));
 }
-// the inverse: A = Y[k], Yb = Y[M-k] (masked spectrum), w as above -> Z[k], Z[M-k] of the packed M-point inverse
-__device__ __forceinline__ void rfft_pack_pair(float2 A, float2 Yb, float2 w, float2& Zk, float2& Zmk)
+// The inverse: masked spectrum Y[k] = X[k] * ma, Y[M-k] = X[M-k] * mb (hps.h:58-66), w as above -> Z[k], Z[M-k] of the
+// packed M-point inverse.  The mask products are written as the multiplicands of explicit fused multiply-adds:
+// ptxas (12.9) contracts a packed mul.rn.f32x2 into a following add.rn.f32x2 whenever it sees fit, -fmad=false or
+// not, and differently from one kernel to the next - leaving it no mul-then-add to find keeps every kernel that
+// inlines this helper bit-identical.  (For the hard masks the products are exact, so nothing changes at all.)
+__device__ __forceinline__ void rfft_pack_masked(float2 Xa, float ma, float2 Xb, float mb, float2 w, float2& Zk, float2& Zmk)
 {
-	const float2 B = cconj(Yb);
-	const float2 E2 = cadd(A, B);
-	const float2 O2 = mul_si<+1>(cmulc(csub(A, B), w));  // i conj(w) (A - B)
+	const f32x2_t B = pmul(pk(Xb), pk(mb, -mb));                 // conj(X[M-k] * mb); feeds addends only
+	const float2 E2 = up(pfma(pk(Xa), pk(ma, ma), B));            // Y[k] + B
+	const float2 Dm = up(pfma(pk(Xa), pk(ma, ma), pk(-up(B).x, -up(B).y)));  // Y[k] - B
+	const float2 O2 = mul_si<+1>(cmulc(Dm, w));                   // i conj(w) (Y[k] - B)
 	Zk = cadd(E2, O2);
 	Zmk = cconj(csub(E2, O2));
+}
+// bins 0 and M (real): Z[0] = (Y0 + YM, Y0 - YM) ; bin M/2: Z[M/2] = 2 conj(Y[M/2]).  Scalar, never contracted.
+__device__ __forceinline__ float2 rfft_pack_dc(float2 X0, float m0, float2 XM, float mM)
+{
+	const float a = __fmul_rn(X0.x, m0), b = __fmul_rn(XM.x, mM);
+	return make_float2(__fadd_rn(a, b), __fsub_rn(a, b));
+}
+__device__ __forceinline__ float2 rfft_pack_mid(float2 Xm, float m)
+{
+	return make_float2(__fmul_rn(2.0f, __fmul_rn(Xm.x, m)), __fmul_rn(-2.0f, __fmul_rn(Xm.y, m)));
 }
 
 // masks of the percussive (mp) and harmonic (mh) outputs at half-spectrum bin k
@@ -453,7 +468,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
 		}
 		float2 w = ldt(reinterpret_cast<const float2*>(t_window) + n);
-		sm.zbuf[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
+		sm.zbuf[fpad(n)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
 	}
 	__syncthreads();
 	stamp(1);
@@ -729,17 +744,15 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 			float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
 			float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];
-			float2 A = cscale(Xa, ma);   // hps.h:58-66
-			float2 Yb = cscale(Xb, mb);
 			if (k == 0) {
-				sm.zbuf[fpad(0)] = make_float2(A.x + Yb.x, A.x - Yb.x);
+				sm.zbuf[fpad(0)] = rfft_pack_dc(Xa, ma, Xb, mb);
 			}
 			else if (k == M / 2) {
-				sm.zbuf[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
+				sm.zbuf[fpad(M / 2)] = rfft_pack_mid(Xa, ma);
 			}
 			else {
 				float2 Zk, Zmk;
-				rfft_pack_pair(A, Yb, ldt(&t_twr[k]), Zk, Zmk);
+				rfft_pack_masked(Xa, ma, Xb, mb, ldt(&t_twr[k]), Zk, Zmk);
 				sm.zbuf[fpad(k)] = Zk;
 				sm.zbuf[fpad(kb)] = Zmk;
 			}
@@ -931,24 +944,33 @@ __device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float* _
 		fast_tap<0, 7, WP, WH>(x.z, tau, sig, cp, ch);
 		fast_tap<0, 7, WP, WH>(x.w, tau, sig, cp, ch);
 	}
-	// tail: taps 4 v .. L + 6, tap j belongs to bins j - L + 1 .. 7
-	for (int j = 4 * v; j < L + 7; ++j) {
-		const float x = Eg[j];
-		const float xe = x + ZEN_EPS;
-		const int lo = j - L + 1;
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const int u0 = 2 * q, u1 = 2 * q + 1;
-			if (WP) {
-				const float s0 = (u0 >= lo && x >= tau[u0]) ? 1.0f : 0.0f;
-				const float s1 = (u1 >= lo && x >= tau[u1]) ? 1.0f : 0.0f;
-				cp[q] = padd(cp[q], pk(s0, s1));
-			}
-			if (WH) {
-				const float s0 = (u0 >= lo && xe <= sig[u0]) ? 1.0f : 0.0f;
-				const float s1 = (u1 >= lo && xe <= sig[u1]) ? 1.0f : 0.0f;
-				ch[q] = padd(ch[q], pk(s0, s1));
-			}
+	// tail: taps 4 v .. L + 6, tap j belongs to bins j - L + 1 .. 7.  L is odd: either L = 4 v + 3 (three more taps that
+	// belong to all eight bins, then L .. L + 6) or L = 4 v + 1 (one more, then L .. L + 6); both fully unrolled.
+	{
+		const float* const T = Eg + 4 * v;
+		const float4 t0 = *reinterpret_cast<const float4*>(T), t1 = *reinterpret_cast<const float4*>(T + 4);
+		if ((L & 3) == 3) {
+			const float4 t2 = *reinterpret_cast<const float4*>(T + 8);
+			fast_tap<0, 7, WP, WH>(t0.x, tau, sig, cp, ch);
+			fast_tap<0, 7, WP, WH>(t0.y, tau, sig, cp, ch);
+			fast_tap<0, 7, WP, WH>(t0.z, tau, sig, cp, ch);
+			fast_tap<1, 7, WP, WH>(t0.w, tau, sig, cp, ch);
+			fast_tap<2, 7, WP, WH>(t1.x, tau, sig, cp, ch);
+			fast_tap<3, 7, WP, WH>(t1.y, tau, sig, cp, ch);
+			fast_tap<4, 7, WP, WH>(t1.z, tau, sig, cp, ch);
+			fast_tap<5, 7, WP, WH>(t1.w, tau, sig, cp, ch);
+			fast_tap<6, 7, WP, WH>(t2.x, tau, sig, cp, ch);
+			fast_tap<7, 7, WP, WH>(t2.y, tau, sig, cp, ch);
+		}
+		else {
+			fast_tap<0, 7, WP, WH>(t0.x, tau, sig, cp, ch);
+			fast_tap<1, 7, WP, WH>(t0.y, tau, sig, cp, ch);
+			fast_tap<2, 7, WP, WH>(t0.z, tau, sig, cp, ch);
+			fast_tap<3, 7, WP, WH>(t0.w, tau, sig, cp, ch);
+			fast_tap<4, 7, WP, WH>(t1.x, tau, sig, cp, ch);
+			fast_tap<5, 7, WP, WH>(t1.y, tau, sig, cp, ch);
+			fast_tap<6, 7, WP, WH>(t1.z, tau, sig, cp, ch);
+			fast_tap<7, 7, WP, WH>(t1.w, tau, sig, cp, ch);
 		}
 	}
 	const float need = (float)(L / 2 + 1);
@@ -989,14 +1011,20 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 	const float2* const win2 = reinterpret_cast<const float2*>(P.window);
 	const float2* const prev2 = reinterpret_cast<const float2*>(prev);
 	const float2* const cur2 = reinterpret_cast<const float2*>(cur);
-	auto load_frame = [&](int idx, int /*p*/) -> float2 {
+	// element j + r * NB of the packed frame, NB = M / 8: r = 0, 1 lie in the previous hop, r = 2, 3 in the current one
+	// (r is a constant once the stage is unrolled, so the choice costs nothing)
+	auto load_frame = [&](int j, int r, int /*p*/) -> float2 {
+		constexpr int NB = M / 8;
+		static_assert(HC == 2 * NB, "first stage must be radix 8");
 		float2 x;
-		if (idx < HC)  // last use of that hop: streaming load, so it does not push the per-CTA scratch out of L2
-			x = prev2 ? __ldcs(prev2 + idx) : make_float2(0.0f, 0.0f);
+		if (r < 2)  // last use of that hop: streaming load, so it does not push the per-CTA scratch out of L2
+			x = prev2 ? __ldcs(prev2 + j + r * NB) : make_float2(0.0f, 0.0f);
 		else
-			x = cur2[idx - HC];
-		const float2 w = __ldg(win2 + idx);
-		return up(pmul(pk(x), pk(w)));
+			x = cur2[j + (r - 2) * NB];
+		const float2 w = __ldg(win2 + j + r * NB);
+		// scalar products: ptxas would contract a packed multiply into the butterfly's first additions (see
+		// rfft_pack_masked), and the kernels that window through shared memory could not follow
+		return make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
 	};
 	float2* const zres = fft_pp_fused<M, NT, -1, true, false, false, false>(a, b, P.tw, tid, load_frame, NoFn{});
 	float2* const zoth = zres == a ? b : a;
@@ -1006,21 +1034,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 	{
 		float* mag_row = st.mag_ring + (size_t)slot * st.ring_stride;
 		float* const E = sm.erow + midp;
-		for (int k = tid; k <= M / 2; k += NT) {
-			float2 Xa, Xb;
-			const int kb = M - k;
-			if (k == 0) {
-				const float2 Z0 = zres[0];
-				Xa = make_float2(Z0.x + Z0.y, 0.0f);
-				Xb = make_float2(Z0.x - Z0.y, 0.0f);
-			}
-			else if (k == M / 2) {
-				Xa = cconj(zres[fpad(M / 2)]);
-				Xb = Xa;
-			}
-			else {
-				rfft_split_pair(zres[fpad(k)], zres[fpad(kb)], __ldg(&P.twr[k]), Xa, Xb);
-			}
+		auto put = [&](int k, int kb, float2 Xa, float2 Xb) {
 			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
 			mag_row[k] = ma;
 			mag_row[kb] = mb;
@@ -1033,6 +1047,26 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 				E[-k] = ma;
 				E[M + k] = mb;
 			}
+		};
+		// pairs (k, M - k), k = 1 .. M/2 - 1, unrolled so that the addresses of one trip are constant offsets from the
+		// previous one; bins 0 / M and M/2 (their own partners) are one thread's extra work
+		constexpr int TRIPS = (M / 2 + NT - 1) / NT;
+#pragma unroll
+		for (int it = 0; it < TRIPS; ++it) {
+			const int k = tid + it * NT;
+			if (((M / 2) % NT == 0 || k < M / 2) && (it > 0 || k > 0)) {
+				float2 Xa, Xb;
+				rfft_split_pair(zres[fpad(k)], zres[fpad(M - k)], __ldg(&P.twr[k]), Xa, Xb);
+				put(k, M - k, Xa, Xb);
+			}
+		}
+		if (tid == 0) {
+			const float2 Z0 = zres[0];
+			put(0, M, make_float2(Z0.x + Z0.y, 0.0f), make_float2(Z0.x - Z0.y, 0.0f));
+		}
+		else if (tid == 32 % NT) {
+			const float2 Xm = cconj(zres[fpad(M / 2)]);
+			put(M / 2, M / 2, Xm, Xm);
 		}
 	}
 	__syncthreads();
@@ -1099,27 +1133,35 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 		if (!(P.out_flags & (1 << o)))
 			continue;
 		// masked spectrum packed for the M-point inverse transform, into zres (X stays in zoth)
-		for (int k = tid; k <= M / 2; k += NT) {
-			const int kb = M - k;
+		auto masks = [&](int k, int kb, float& ma, float& mb) {
 			const unsigned ca = (unsigned)sm.codes[k >> 3] >> (k & 7), cb = (unsigned)sm.codes[kb >> 3] >> (kb & 7);
 			const float mpa = (float)(ca & 1u), mha = (float)((ca >> 8) & 1u);
 			const float mpb = (float)(cb & 1u), mhb = (float)((cb >> 8) & 1u);
-			const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
-			const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
-			const float2 A = cscale(zoth[k], ma);   // hps.h:58-66
-			const float2 Yb = cscale(zoth[kb], mb);
-			if (k == 0) {
-				zres[0] = make_float2(A.x + Yb.x, A.x - Yb.x);
-			}
-			else if (k == M / 2) {
-				zres[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
-			}
-			else {
+			ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
+			mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
+		};
+		constexpr int TRIPS = (M / 2 + NT - 1) / NT;
+#pragma unroll
+		for (int it = 0; it < TRIPS; ++it) {
+			const int k = tid + it * NT;
+			if (((M / 2) % NT == 0 || k < M / 2) && (it > 0 || k > 0)) {
+				float ma, mb;
 				float2 Zk, Zmk;
-				rfft_pack_pair(A, Yb, __ldg(&P.twr[k]), Zk, Zmk);
+				masks(k, M - k, ma, mb);
+				rfft_pack_masked(zoth[k], ma, zoth[M - k], mb, __ldg(&P.twr[k]), Zk, Zmk);
 				zres[fpad(k)] = Zk;
-				zres[fpad(kb)] = Zmk;
+				zres[fpad(M - k)] = Zmk;
 			}
+		}
+		if (tid == 0) {
+			float ma, mb;
+			masks(0, M, ma, mb);
+			zres[0] = rfft_pack_dc(zoth[0], ma, zoth[M], mb);
+		}
+		else if (tid == 32 % NT) {
+			float ma, mb;
+			masks(M / 2, M / 2, ma, mb);
+			zres[fpad(M / 2)] = rfft_pack_mid(zoth[M / 2], ma);
 		}
 		__syncthreads();
 		// inverse FFT (hps.cu:522) whose last stage IS the overlap-add (hps.h:68-80): the thread that holds sample
@@ -1221,7 +1263,7 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
 		}
 		float2 w = reinterpret_cast<const float2*>(tb.window)[n];
-		za[fpad(n)] = make_float2(x.x * w.x, x.y * w.y);
+		za[fpad(n)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
 	}
 	__syncthreads();
 	stamp(1);
@@ -1337,17 +1379,15 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 				float2* zb = sp.recv[o] + recv_off;
 				const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 				const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
-				const float2 A = cscale(Xa, ma);   // hps.h:58-66
-				const float2 Yb = cscale(Xb, mb);
 				if (k == 0) {
-					zb[fpad(0)] = make_float2(A.x + Yb.x, A.x - Yb.x);
+					zb[fpad(0)] = rfft_pack_dc(Xa, ma, Xb, mb);
 				}
 				else if (k == M / 2) {
-					zb[fpad(M / 2)] = make_float2(2.0f * A.x, -2.0f * A.y);
+					zb[fpad(M / 2)] = rfft_pack_mid(Xa, ma);
 				}
 				else {
 					float2 Zk, Zmk;
-					rfft_pack_pair(A, Yb, twk, Zk, Zmk);
+					rfft_pack_masked(Xa, ma, Xb, mb, twk, Zk, Zmk);   // hps.h:58-66
 					zb[fpad(k)] = Zk;
 					zb[fpad(kb)] = Zmk;
 				}
