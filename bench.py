@@ -218,12 +218,13 @@ def parity_sample(torch, hps, x, out_p, rows, n_hops):
     from tests.util import flip_aware_compare
     res = {"streams": [], "hops": 0, "flips": 0, "flip_hops": 0, "worst_margin": 0.0, "max_abs_err": 0.0, "min_snr_db": float("inf"),
            "batched_equals_checked_path": True, "oracle": "oracle/hpr_oracle.c (GPU geometry), pinned by tests/test_oracle_golden.py",
-           "tolerance": "max-abs <= 1e-4 and SNR >= 80 dB after peak normalisation on every hop without a flipped bin"}
+           "tolerance": "max-abs <= 1e-4 and SNR >= 80 dB after peak normalisation on every hop without a flipped bin; a flipped "
+                        "bin must be a borderline decision of the oracle (|ratio - beta| / beta <= 6e-5)"}
     for r in rows:
         a = x[r, : n_hops * HOP].cpu().numpy()
         o = ob.OracleHPR(ob.GEOM_GPU, float(FS), HOP, BETA, 2, ob.CAUSAL, True)
         h = hps.HPR(float(FS), HOP, BETA, 2, 0, True)
-        c = flip_aware_compare(h, o, a, HOP, 2, hard_mask=True)
+        c = flip_aware_compare(h, o, a, HOP, 2, hard_mask=True, margin_tol=6e-5)
         h.close()
         o.close()
         res["streams"].append(int(r))
@@ -236,7 +237,7 @@ def parity_sample(torch, hps, x, out_p, rows, n_hops):
         same = bool(np.array_equal(out_p[r, : n_hops * HOP].cpu().numpy(), c["got"][1]))
         res["batched_equals_checked_path"] = res["batched_equals_checked_path"] and same
     res["ok"] = bool(res["batched_equals_checked_path"] and res["max_abs_err"] <= 1e-4 and res["min_snr_db"] >= 80.0
-                     and res["worst_margin"] <= 2e-5)
+                     and res["worst_margin"] <= 6e-5)
     return res
 
 

@@ -154,7 +154,9 @@ def lroundf(v):
 
 def pcm16_encode_normalized(x):
     """float32 [n] -> (int16 [n], peak): x / max(-min, max), then (int16_t)lroundf(x * 32767.f).
-    A silent signal (peak 0: the reference divides by zero) stays silent - the one deliberate difference."""
+    A silent signal (peak 0) stays silent: the reference divides 0 by 0 and hands NaN to lroundf, which its x86-64
+    build turns into PCM16 zeros as well (tests/golden/nyq_pcm.npz: silence_out, from the compiled libnyquist).
+    Pinned by tests/test_pcm.py::test_pcm16_oracle_pinned_by_libnyquist."""
     x = x.astype(np.float32)
     if x.size == 0:
         return np.zeros(0, np.int16), np.float32(0.0)

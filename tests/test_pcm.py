@@ -1,6 +1,8 @@
 """The on-disk format either side of the path: PCM16 decode + mono fold and peak
 normalisation + PCM16 encode, batched on the device, against the NumPy restatement of libnyquist's / the zen command
 line's host code (oracle/np_model.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -44,6 +46,49 @@ def test_pcm16_oracle_matches_the_wav_helpers_of_the_cli_tests(tmp_path):
     fs, ch, got = read_wav(str(tmp_path / "a.wav"))
     assert fs == 44100 and ch == 1
     assert np.array_equal(np_model.pcm16_decode_mono(got.astype(np.int16), 1), xq)
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nyq_pcm.npz")
+
+
+def test_pcm16_oracle_pinned_by_libnyquist():
+    """oracle/np_model.py against the UNMODIFIED libnyquist conversion code compiled from /root/reference/vendor
+    (oracle/Makefile ref_nyq, fixtures by oracle/ref/make_pcm_golden.py): every PCM16 code decoded, the stereo fold,
+    the PCM16 encode on halfway cases, and the command line's peak normalisation (zen/offline.h:180-192)."""
+    g = np.load(GOLD)
+    all16 = np.arange(-32768, 32768, dtype=np.int16)
+    assert np.array_equal(np_model.pcm16_decode_mono(all16, 1).view(np.uint32), g["decode_all_int16"].view(np.uint32))
+    assert np.array_equal(np_model.pcm16_decode_mono(g["stereo_pcm"], 2).view(np.uint32), g["stereo_mono"].view(np.uint32))
+    e = g["encode_in"]
+    assert np.array_equal(np_model.lroundf((e * np.float32(32767.0)).astype(np.float32)).astype(np.int16), g["encode_out"])
+    for i in range(5):
+        q, pk = np_model.pcm16_encode_normalized(g["norm%d_in" % i])
+        assert pk == g["norm%d_peak" % i] and np.array_equal(q, g["norm%d_out" % i]), i
+    # silence: 0 / 0 = NaN in the reference, which its x86-64 build converts to 0 - the same PCM16 our path writes
+    assert not g["silence_out"].any()
+    q, pk = np_model.pcm16_encode_normalized(np.zeros(64, np.float32))
+    assert np.array_equal(q, g["silence_out"])
+
+
+@pytest.mark.gpu
+def test_pcm16_kernels_pinned_by_libnyquist():
+    """csrc/pcm.cu against the same libnyquist fixtures, bit for bit"""
+    import torch as t
+    if not t.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from zen_b200 import hps
+    g = np.load(GOLD)
+    all16 = np.arange(-32768, 32768, dtype=np.int16)
+    got = hps.pcm16_decode_mono(t.from_numpy(all16[None]).cuda(), 1).cpu().numpy()[0]
+    assert np.array_equal(got.view(np.uint32), g["decode_all_int16"].view(np.uint32))
+    got = hps.pcm16_decode_mono(t.from_numpy(g["stereo_pcm"][None]).cuda(), 2).cpu().numpy()[0]
+    assert np.array_equal(got.view(np.uint32), g["stereo_mono"].view(np.uint32))
+    x = np.stack([g["norm%d_in" % i] for i in range(5)] + [np.zeros(g["norm0_in"].size, np.float32)])
+    q, pk = hps.pcm16_encode_normalized(t.from_numpy(x).cuda())
+    q, pk = q.cpu().numpy(), pk.cpu().numpy()
+    for i in range(5):
+        assert pk[i] == g["norm%d_peak" % i] and np.array_equal(q[i], g["norm%d_out" % i]), i
+    assert not q[5].any()
 
 
 @pytest.fixture(scope="module")

@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ in,
 
 __device__ __forceinline__ int pcm_from_float(float v, float peak)
 {
-	// a silent stream has no peak to divide by (the reference would write lroundf(NaN)): it stays silent
+	// a silent stream has no peak to divide by: it stays silent.  (The reference divides 0 by 0 and hands NaN to
+	// lroundf; its x86-64 build converts that to PCM16 zeros as well - tests/golden/nyq_pcm.npz, silence_out.)
 	const float x = peak > 0.0f ? __fdiv_rn(v, peak) : 0.0f;
 	return (int)(int16_t)lroundf(__fmul_rn(x, 32767.0f));
 }
