@@ -19,11 +19,11 @@ __global__ void __launch_bounds__(NT) fft_c2c_kernel(float2* __restrict__ data, 
 	extern __shared__ __align__(16) unsigned char fft_smem_raw[];
 	float2* buf = reinterpret_cast<float2*>(fft_smem_raw);
 	for (int i = threadIdx.x; i < N; i += NT)
-		buf[fpad(i)] = data[i];
+		buf[i] = data[i];
 	__syncthreads();
 	fft_smem<N, NT, S>(buf, tw, threadIdx.x);
 	for (int i = threadIdx.x; i < N; i += NT)
-		data[i] = buf[fpad(i)];
+		data[i] = buf[i];
 }
 
 // per-stage twiddle tables (fft_fill_twiddles), one per size and device, built on first use
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT) fft_large_cols_kernel(const float2* __rest
 	float2* buf = reinterpret_cast<float2*>(fft_smem_raw);
 	const int n2 = blockIdx.x;
 	for (int n1 = threadIdx.x; n1 < N1; n1 += NT)
-		buf[fpad(n1)] = x[(size_t)n1 * N2 + n2];
+		buf[n1] = x[(size_t)n1 * N2 + n2];
 	__syncthreads();
 	fft_smem<N1, NT, S>(buf, tw1, threadIdx.x);
 	constexpr int N = N1 * N2;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NT) fft_large_cols_kernel(const float2* __rest
 		float sn, cs;
 		sincospif(2.0f * (float)(((long)n2 * k1) % N) / (float)N, &sn, &cs);  // accurate to ~1 ulp on the reduced angle
 		float2 w = make_float2(cs, S > 0 ? sn : -sn);
-		y[(size_t)k1 * N2 + n2] = cmul(buf[fpad(k1)], w);
+		y[(size_t)k1 * N2 + n2] = cmul(buf[k1], w);
 	}
 }
 
@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(NT) fft_large_rows_kernel(const float2* __rest
 	float2* buf = reinterpret_cast<float2*>(fft_smem_raw);
 	const int k1 = blockIdx.x;
 	for (int n2 = threadIdx.x; n2 < N2; n2 += NT)
-		buf[fpad(n2)] = y[(size_t)k1 * N2 + n2];
+		buf[n2] = y[(size_t)k1 * N2 + n2];
 	__syncthreads();
 	fft_smem<N2, NT, S>(buf, tw2, threadIdx.x);
 	for (int k2 = threadIdx.x; k2 < N2; k2 += NT)
-		x[(size_t)k1 + (size_t)N1 * k2] = buf[fpad(k2)];
+		x[(size_t)k1 + (size_t)N1 * k2] = buf[k2];
 }
 
 template <int N1, int N2>

@@ -7,9 +7,13 @@
 // +-i, conjugating a twiddle and broadcasting a real part cost nothing: a radix-8 butterfly is 26 packed
 // instructions instead of ~60 scalar ones, a twiddle multiply 2 instead of 4.
 //
-// Layout: float2 in shared memory, index padded by one slot every 16 (fpad) so the stride-R stores of the early
-// stages spread over banks.  The load index j + r*NB and the store index j0 + r*NS are turned into ONE padded base
-// plus compile-time offsets wherever the stride allows it (fpad is additive over multiples of 16).
+// Layout: float2 in shared memory.  The transform's input and output are in NATURAL order (element i at i): every
+// access pattern outside the stages is unit-stride across lanes.  Between two stages the layout is chosen by the
+// stage that WRITES, so that its stride-NS stores spread over the banks (the loads of every stage are unit-stride):
+//   after the NS = 1 stage (lane j writes 8 j + r):            one slot of padding every 16   (LAY_F)
+//   after the NS = 8 radix-8 stage (64 q + k + 8 r, k < 8):    eight slots every 64           (LAY_L2, M >= 1024)
+//   after any stage with NS >= 16, and after the last stage:   natural                        (LAY_N)
+// Buffers hold fpad_size(M) = M + M/8 + 1 elements.  Load / store positions are one base plus compile-time offsets.
 //
 // Every variant below (in place, ping-pong, first stage fed by a functor, last stage drained by a functor) runs
 // the SAME butterfly code, so their results are bit-identical: the batched, the per-launch and the resident
@@ -20,8 +24,31 @@
 
 namespace zen_b200 {
 
-__host__ __device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
-__host__ __device__ constexpr int fpad_size(int n) { return n + (n >> 4) + 1; }
+__host__ __device__ constexpr int fpad_size(int n) { return n + (n >> 3) + 1; }
+
+enum { LAY_N = 0, LAY_F = 1, LAY_L2 = 2 };
+template <int LAY>
+__device__ __forceinline__ int lay_pos(int i)
+{
+	if constexpr (LAY == LAY_F) return i + (i >> 4);
+	else if constexpr (LAY == LAY_L2) return i + 8 * (i >> 6);
+	else return i;
+}
+// position of element base + r * STRIDE given the position `base_p` of `base`
+template <int LAY, int STRIDE>
+__device__ __forceinline__ int lay_step(int base, int base_p, int r)
+{
+	if constexpr (LAY == LAY_N) return base_p + r * STRIDE;
+	else if constexpr (LAY == LAY_F && STRIDE % 16 == 0) return base_p + r * (STRIDE + STRIDE / 16);
+	else if constexpr (LAY == LAY_L2 && STRIDE % 64 == 0) return base_p + r * (STRIDE + STRIDE / 8);
+	else return lay_pos<LAY>(base + r * STRIDE);
+}
+// layout of what the stage (NS, R) of an M-point transform writes
+template <int M, int NS, int R>
+constexpr int fft_layout_out()
+{
+	return (NS * R >= M) ? LAY_N : (NS == 1 ? LAY_F : ((NS == 8 && R == 8 && M >= 1024) ? LAY_L2 : (NS < 16 ? LAY_F : LAY_N)));
+}
 
 // ---- packed fp32x2 ----------------------------------------------------------------------------------------
 typedef unsigned long long f32x2_t;
@@ -235,17 +262,7 @@ constexpr int fft_stage_count()
 	}
 }
 
-// padded position of element base + r * STRIDE given the padded position of `base`
-template <int STRIDE>
-__device__ __forceinline__ int fpad_step(int base, int base_padded, int r)
-{
-	if constexpr (STRIDE % 16 == 0)
-		return base_padded + r * (STRIDE + STRIDE / 16);
-	else
-		return fpad(base + r * STRIDE);
-}
-
-// shared-memory source / sink of a stage (the default I/O); `p` is the padded position
+// shared-memory source / sink of a stage (the default I/O); `p` is the position in the layout at hand
 struct SmemLoad {
 	const float2* buf;
 	__device__ __forceinline__ float2 operator()(int /*j*/, int /*r*/, int p) const { return buf[p]; }
@@ -265,24 +282,25 @@ struct SmemStore {
 // GT  : tw may point into shared memory (the resident real-time kernel keeps its tables there): plain generic
 //       loads instead of the read-only global path.
 // MID : barrier between the loads and the stores (needed when the stage works in place).
-template <int M, int NT, int S, int R, int NS, bool ZIN, bool HOUT, bool GT, bool MID, typename LD, typename ST>
+template <int M, int NT, int S, int R, int NS, int LIN, bool ZIN, bool HOUT, bool GT, bool MID, typename LD, typename ST>
 __device__ __forceinline__ void fft_stage_io(const float2* __restrict__ tw, int tid, LD ld, ST st)
 {
 	constexpr int NB = M / R;
 	constexpr int PER = (NB + NT - 1) / NT;
+	constexpr int LOUT = fft_layout_out<M, NS, R>();
 	float2 v[PER][R];
 #pragma unroll
 	for (int b = 0; b < PER; ++b) {
 		const int j = tid + b * NT;
 		if ((NB % NT == 0) || j < NB) {
 			const int k = j & (NS - 1);
-			const int jp = fpad(j);
+			const int jp = lay_pos<LIN>(j);
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
 				if (ZIN && r >= R / 2)
 					v[b][r] = make_float2(0.0f, 0.0f);
 				else
-					v[b][r] = ld(j, r, fpad_step<NB>(j, jp, r));  // element j + r*NB (r is a constant after unrolling)
+					v[b][r] = ld(j, r, lay_step<LIN, NB>(j, jp, r));  // element j + r*NB (r is a constant after unrolling)
 			}
 			if constexpr (NS > 1) {
 #pragma unroll
@@ -303,25 +321,29 @@ __device__ __forceinline__ void fft_stage_io(const float2* __restrict__ tw, int 
 		if ((NB % NT == 0) || j < NB) {
 			const int k = j & (NS - 1);
 			const int j0 = (j - k) * R + k;
-			// padded position of j0 + r*NS as one base plus compile-time offsets where the geometry allows it
+			// position of j0 + r*NS as one base plus compile-time offsets where the geometry allows it
 			int base_p;
-			if constexpr (NS == 1 && R == 8)
+			if constexpr (NS == 1 && R == 8 && LOUT == LAY_F)
 				base_p = 8 * j + (j >> 1);                      // (8j + r) >> 4 == j >> 1
-			else if constexpr (NS == 8 && R == 8)
+			else if constexpr (NS == 8 && R == 8 && LOUT == LAY_L2)
+				base_p = 72 * (j >> 3) + k;                     // 64q + k + 8r lies in block q of 64
+			else if constexpr (NS == 8 && R == 8 && LOUT == LAY_F)
 				base_p = 68 * (j >> 3) + k;                     // (64q + k + 8r) >> 4 == 4q + (r >> 1)
 			else
-				base_p = fpad(j0);
+				base_p = lay_pos<LOUT>(j0);
 #pragma unroll
 			for (int r = 0; r < R; ++r) {
 				if (HOUT && r >= R / 2)
 					continue;
 				int p;
-				if constexpr (NS == 1 && R == 8)
+				if constexpr (NS == 1 && R == 8 && LOUT == LAY_F)
 					p = base_p + r;
-				else if constexpr (NS == 8 && R == 8)
+				else if constexpr (NS == 8 && R == 8 && LOUT == LAY_L2)
+					p = base_p + 8 * r;
+				else if constexpr (NS == 8 && R == 8 && LOUT == LAY_F)
 					p = base_p + 8 * r + (r >> 1);
 				else
-					p = fpad_step<NS>(j0, base_p, r);
+					p = lay_step<LOUT, NS>(j0, base_p, r);
 				st(j0 + r * NS, p, v[b][r]);
 			}
 		}
@@ -331,14 +353,14 @@ __device__ __forceinline__ void fft_stage_io(const float2* __restrict__ tw, int 
 // M-point complex FFT in shared memory, IN PLACE, all NT threads of the CTA participate.
 // tw: the per-stage tables of fft_fill_twiddles(M).  The caller must have synchronised after filling buf.
 // Ends synchronised.
-template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
+template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false, int LIN = LAY_N>
 __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__ tw, int tid)
 {
 	if constexpr (NS < M) {
 		constexpr int R = fft_radix<M, NS>();
-		fft_stage_io<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && NS * R == M), GT, true>(tw, tid, SmemLoad{buf}, SmemStore{buf});
+		fft_stage_io<M, NT, S, R, NS, LIN, (ZIN && NS == 1), (HOUT && NS * R == M), GT, true>(tw, tid, SmemLoad{buf}, SmemStore{buf});
 		__syncthreads();
-		fft_smem<M, NT, S, NS * R, ZIN, HOUT, GT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
+		fft_smem<M, NT, S, NS * R, ZIN, HOUT, GT, fft_layout_out<M, NS, R>()>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid);
 	}
 }
 
@@ -352,20 +374,21 @@ __device__ __forceinline__ void fft_smem(float2* buf, const float2* __restrict__
 struct NoFn {
 };
 
-template <int M, int NT, int S, int NS, bool ZIN, bool HOUT, bool GT, bool LAST_FN, typename LAST>
+template <int M, int NT, int S, int NS, bool ZIN, bool HOUT, bool GT, bool LAST_FN, int LIN, typename LAST>
 __device__ __forceinline__ float2* fft_pp_rest(float2* src, float2* dst, const float2* __restrict__ tw, int tid, LAST last)
 {
 	if constexpr (NS < M) {
 		constexpr int R = fft_radix<M, NS>();
 		constexpr bool is_last = NS * R == M;
 		if constexpr (is_last && LAST_FN) {
-			fft_stage_io<M, NT, S, R, NS, (ZIN && NS == 1), HOUT, GT, false>(tw, tid, SmemLoad{src}, last);
+			fft_stage_io<M, NT, S, R, NS, LIN, (ZIN && NS == 1), HOUT, GT, false>(tw, tid, SmemLoad{src}, last);
 			return nullptr;  // the result went to the functor; NOT synchronised (the caller decides)
 		}
 		else {
-			fft_stage_io<M, NT, S, R, NS, (ZIN && NS == 1), (HOUT && is_last), GT, false>(tw, tid, SmemLoad{src}, SmemStore{dst});
+			fft_stage_io<M, NT, S, R, NS, LIN, (ZIN && NS == 1), (HOUT && is_last), GT, false>(tw, tid, SmemLoad{src}, SmemStore{dst});
 			__syncthreads();
-			return fft_pp_rest<M, NT, S, NS * R, ZIN, HOUT, GT, LAST_FN>(dst, src, tw + (NS > 1 ? (R - 1) * NS : 0), tid, last);
+			return fft_pp_rest<M, NT, S, NS * R, ZIN, HOUT, GT, LAST_FN, fft_layout_out<M, NS, R>()>(dst, src, tw + (NS > 1 ? (R - 1) * NS : 0),
+			                                                                                    tid, last);
 		}
 	}
 	else {
@@ -377,7 +400,8 @@ __device__ __forceinline__ float2* fft_pp_rest(float2* src, float2* dst, const f
 template <int M, int NT, int S, int NS = 1, bool ZIN = false, bool HOUT = false, bool GT = false>
 __device__ __forceinline__ float2* fft_smem_pp(float2* a, float2* b, const float2* __restrict__ tw, int tid)
 {
-	return fft_pp_rest<M, NT, S, NS, ZIN, HOUT, GT, false>(a, b, tw, tid, NoFn{});
+	static_assert(NS == 1, "fft_smem_pp starts at the first stage");
+	return fft_pp_rest<M, NT, S, NS, ZIN, HOUT, GT, false, LAY_N>(a, b, tw, tid, NoFn{});
 }
 
 // first stage fed by `first`, written to `a`; the remaining stages ping-pong between a and b.  `last` (LAST_FN)
@@ -388,25 +412,25 @@ __device__ __forceinline__ float2* fft_pp_fused(float2* a, float2* b, const floa
 {
 	constexpr int R = fft_radix<M, 1>();
 	static_assert(R < M, "fft_pp_fused needs at least two stages");
-	fft_stage_io<M, NT, S, R, 1, ZIN, false, GT, false>(tw, tid, first, SmemStore{a});
+	fft_stage_io<M, NT, S, R, 1, LAY_N, ZIN, false, GT, false>(tw, tid, first, SmemStore{a});
 	__syncthreads();
-	return fft_pp_rest<M, NT, S, R, ZIN, HOUT, GT, LAST_FN>(a, b, tw, tid, last);
+	return fft_pp_rest<M, NT, S, R, ZIN, HOUT, GT, LAST_FN, fft_layout_out<M, 1, R>()>(a, b, tw, tid, last);
 }
 
 // in-place transform whose LAST stage hands its output to `last(index, padded position, value)` instead of storing
 // it (the other stages need their barrier between loads and stores).  Not synchronised at the end.
-template <int M, int NT, int S, int NS, bool HOUT, bool GT, typename LAST>
+template <int M, int NT, int S, int NS, bool HOUT, bool GT, int LIN = LAY_N, typename LAST>
 __device__ __forceinline__ void fft_inplace_last(float2* buf, const float2* __restrict__ tw, int tid, LAST last)
 {
 	if constexpr (NS < M) {
 		constexpr int R = fft_radix<M, NS>();
 		if constexpr (NS * R == M) {
-			fft_stage_io<M, NT, S, R, NS, false, HOUT, GT, false>(tw, tid, SmemLoad{buf}, last);
+			fft_stage_io<M, NT, S, R, NS, LIN, false, HOUT, GT, false>(tw, tid, SmemLoad{buf}, last);
 		}
 		else {
-			fft_stage_io<M, NT, S, R, NS, false, false, GT, true>(tw, tid, SmemLoad{buf}, SmemStore{buf});
+			fft_stage_io<M, NT, S, R, NS, LIN, false, false, GT, true>(tw, tid, SmemLoad{buf}, SmemStore{buf});
 			__syncthreads();
-			fft_inplace_last<M, NT, S, NS * R, HOUT, GT>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid, last);
+			fft_inplace_last<M, NT, S, NS * R, HOUT, GT, fft_layout_out<M, NS, R>()>(buf, tw + (NS > 1 ? (R - 1) * NS : 0), tid, last);
 		}
 	}
 }

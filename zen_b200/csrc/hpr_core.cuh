@@ -385,7 +385,7 @@ __device__ __forceinline__ void hpr_ola_emit(const HprDev& P, const float2* zb, 
 	constexpr int M = NFFT / 2, HOP = M / 2;
 	const int tid = threadIdx.x;
 	for (int n = tid; n < HOP / 2; n += NT) {
-		float2 v = zb[fpad(n)];
+		float2 v = zb[n];
 		float2 t = fresh_tail ? make_float2(0.0f, 0.0f) : reinterpret_cast<const float2*>(tail)[n];
 		float2 r = make_float2(fmaf(v.x, P.cola, t.x), fmaf(v.y, P.cola, t.y));
 		if (ea) __stcs(reinterpret_cast<float2*>(ea) + n, r);  // written once, never re-read by the kernel
@@ -410,7 +410,7 @@ __device__ __forceinline__ void hpr_ola_emit(const HprDev& P, const float2* zb, 
 		}
 	}
 	for (int n = HOP / 2 + tid; n < HOP; n += NT) {
-		float2 v = zb[fpad(n)];
+		float2 v = zb[n];
 		reinterpret_cast<float2*>(tail)[n - HOP / 2] = make_float2(v.x * P.cola, v.y * P.cola);
 	}
 	__syncthreads();
@@ -468,7 +468,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
 		}
 		float2 w = ldt(reinterpret_cast<const float2*>(t_window) + n);
-		sm.zbuf[fpad(n)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+		sm.zbuf[n] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
 	}
 	__syncthreads();
 	stamp(1);
@@ -486,16 +486,16 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			float2 Xa, Xb;
 			int ka = k, kb = M - k;
 			if (k == 0) {
-				float2 Z0 = sm.zbuf[fpad(0)];
+				float2 Z0 = sm.zbuf[0];
 				Xa = make_float2(Z0.x + Z0.y, 0.0f);
 				Xb = make_float2(Z0.x - Z0.y, 0.0f);
 			}
 			else if (k == M / 2) {
-				Xa = cconj(sm.zbuf[fpad(M / 2)]);
+				Xa = cconj(sm.zbuf[M / 2]);
 				Xb = Xa;
 			}
 			else {
-				rfft_split_pair(sm.zbuf[fpad(k)], sm.zbuf[fpad(M - k)], ldt(&t_twr[k]), Xa, Xb);
+				rfft_split_pair(sm.zbuf[k], sm.zbuf[M - k], ldt(&t_twr[k]), Xa, Xb);
 			}
 			float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
 			if (P.sse) {
@@ -745,16 +745,16 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
 			float2 Xa = sm.xbuf[k], Xb = sm.xbuf[kb];
 			if (k == 0) {
-				sm.zbuf[fpad(0)] = rfft_pack_dc(Xa, ma, Xb, mb);
+				sm.zbuf[0] = rfft_pack_dc(Xa, ma, Xb, mb);
 			}
 			else if (k == M / 2) {
-				sm.zbuf[fpad(M / 2)] = rfft_pack_mid(Xa, ma);
+				sm.zbuf[M / 2] = rfft_pack_mid(Xa, ma);
 			}
 			else {
 				float2 Zk, Zmk;
 				rfft_pack_masked(Xa, ma, Xb, mb, ldt(&t_twr[k]), Zk, Zmk);
-				sm.zbuf[fpad(k)] = Zk;
-				sm.zbuf[fpad(kb)] = Zmk;
+				sm.zbuf[k] = Zk;
+				sm.zbuf[kb] = Zmk;
 			}
 		}
 		__syncthreads();
@@ -788,9 +788,11 @@ struct FastSmem {
 	static constexpr int ZN = (fpad_size(M) + 1) & ~1;
 	float2* za;            // ZN
 	float2* zb;            // ZN
-	float* erow;           // |X| of the consumed frame, bin k at erow[midp + k], mirrored borders; 16-byte aligned
+	float* erow;           // |X| of the consumed frame with mirrored borders: bin k is element midp + k, stored at
+	                       // fast_esw(midp + k) (16-byte chunks swizzled against bank conflicts); 16-byte aligned
 	unsigned short* codes; // entry k >> 3, bit k & 7: percussive decision of bin k; bit 8 + (k & 7): harmonic
-	static __host__ __device__ size_t erow_floats(int Lp) { return (size_t)((M + 1 + Lp + 16 + 3) & ~3); }
+	// (a multiple of 32 floats: the swizzle permutes chunks within blocks of eight)
+	static __host__ __device__ size_t erow_floats(int Lp) { return (size_t)((M + 1 + Lp + 16 + 31) & ~31); }
 	static __host__ __device__ size_t bytes(int Lp)
 	{
 		return 2 * sizeof(float2) * (size_t)ZN + sizeof(float) * erow_floats(Lp) + sizeof(unsigned short) * (size_t)((M / 8 + 1 + 7) & ~7);
@@ -803,6 +805,13 @@ struct FastSmem {
 		codes = reinterpret_cast<unsigned short*>(erow + erow_floats(Lp));
 	}
 };
+
+// Element e of the magnitude row lives at fast_esw(e): the 16-byte chunk index c = e >> 2 has its lowest bit flipped in
+// every other block of eight chunks.  The decision threads read one chunk each at a stride of TWO chunks (eight bins
+// per thread): the lanes t and t + 4 of a quarter-warp then hit the same four banks in the plain layout - with the
+// swizzle they are in neighbouring blocks, one of which is flipped.
+__device__ __forceinline__ int fast_esw_chunk(int c) { return c ^ ((c >> 3) & 1); }
+__device__ __forceinline__ int fast_esw(int e) { return (fast_esw_chunk(e >> 2) << 2) | (e & 3); }
 
 // per-CTA state of the fast path (global scratch that stays in L2)
 struct FastState {
@@ -907,9 +916,11 @@ __device__ __forceinline__ void fast_tap(float x, const float (&tau)[8], const f
 
 // decisions of bins k0 .. k0 + 7 given their time medians: bit u = percussive, bit 8 + u = harmonic
 // (Mp = [P/(H+eps) >= beta], Mh = [H/(P+eps) >= beta-eps], hps.h:100-113, decided by counting: see decide_group_t)
+// erow4: the swizzled magnitude row as 16-byte chunks; c0 = chunk of the group's first tap (k0 / 4)
 template <bool WP, bool WH>
-__device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float* __restrict__ Eg, const float (&H)[8])
+__device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float4* __restrict__ erow4, int c0, const float (&H)[8])
 {
+	auto ldv = [&](int v) -> float4 { return erow4[fast_esw_chunk(c0 + v)]; };
 	const int L = P.Lp;
 	float tau[8], sig[8];
 #pragma unroll
@@ -921,9 +932,9 @@ __device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float* _
 #pragma unroll
 	for (int q = 0; q < 4; ++q)
 		cp[q] = ch[q] = pk(0.0f, 0.0f);
-	// tap j of bin k0 + u is Eg[j] for u <= j < u + L.  Head: taps 0..7 (L >= 9, so tap 7 already belongs to all eight)
+	// tap j of bin k0 + u is element 4 c0 + j for u <= j < u + L.  Head: taps 0..7 (L >= 9, so tap 7 already belongs to all eight)
 	{
-		const float4 h0 = *reinterpret_cast<const float4*>(Eg), h1 = *reinterpret_cast<const float4*>(Eg + 4);
+		const float4 h0 = ldv(0), h1 = ldv(1);
 		fast_tap<0, 0, WP, WH>(h0.x, tau, sig, cp, ch);
 		fast_tap<0, 1, WP, WH>(h0.y, tau, sig, cp, ch);
 		fast_tap<0, 2, WP, WH>(h0.z, tau, sig, cp, ch);
@@ -938,7 +949,7 @@ __device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float* _
 	int v = 2;
 #pragma unroll 2
 	for (; v <= v_end; ++v) {
-		const float4 x = *reinterpret_cast<const float4*>(Eg + 4 * v);
+		const float4 x = ldv(v);
 		fast_tap<0, 7, WP, WH>(x.x, tau, sig, cp, ch);
 		fast_tap<0, 7, WP, WH>(x.y, tau, sig, cp, ch);
 		fast_tap<0, 7, WP, WH>(x.z, tau, sig, cp, ch);
@@ -947,10 +958,9 @@ __device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float* _
 	// tail: taps 4 v .. L + 6, tap j belongs to bins j - L + 1 .. 7.  L is odd: either L = 4 v + 3 (three more taps that
 	// belong to all eight bins, then L .. L + 6) or L = 4 v + 1 (one more, then L .. L + 6); both fully unrolled.
 	{
-		const float* const T = Eg + 4 * v;
-		const float4 t0 = *reinterpret_cast<const float4*>(T), t1 = *reinterpret_cast<const float4*>(T + 4);
+		const float4 t0 = ldv(v), t1 = ldv(v + 1);
 		if ((L & 3) == 3) {
-			const float4 t2 = *reinterpret_cast<const float4*>(T + 8);
+			const float4 t2 = ldv(v + 2);
 			fast_tap<0, 7, WP, WH>(t0.x, tau, sig, cp, ch);
 			fast_tap<0, 7, WP, WH>(t0.y, tau, sig, cp, ch);
 			fast_tap<0, 7, WP, WH>(t0.z, tau, sig, cp, ch);
@@ -1033,19 +1043,19 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 	// into erow (hps.cu:469-472, 492-493)
 	{
 		float* mag_row = st.mag_ring + (size_t)slot * st.ring_stride;
-		float* const E = sm.erow + midp;
+		float* const E = sm.erow;
 		auto put = [&](int k, int kb, float2 Xa, float2 Xb) {
 			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
 			mag_row[k] = ma;
 			mag_row[kb] = mb;
 			zoth[k] = Xa;
 			zoth[kb] = Xb;
-			E[k] = ma;
-			E[kb] = mb;
+			E[fast_esw(midp + k)] = ma;
+			E[fast_esw(midp + kb)] = mb;
 			// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]|
 			if (k >= 1 && k <= midp) {
-				E[-k] = ma;
-				E[M + k] = mb;
+				E[fast_esw(midp - k)] = ma;
+				E[fast_esw(midp + M + k)] = mb;
 			}
 		};
 		// pairs (k, M - k), k = 1 .. M/2 - 1, unrolled so that the addresses of one trip are constant offsets from the
@@ -1056,7 +1066,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 			const int k = tid + it * NT;
 			if (((M / 2) % NT == 0 || k < M / 2) && (it > 0 || k > 0)) {
 				float2 Xa, Xb;
-				rfft_split_pair(zres[fpad(k)], zres[fpad(M - k)], __ldg(&P.twr[k]), Xa, Xb);
+				rfft_split_pair(zres[k], zres[M - k], __ldg(&P.twr[k]), Xa, Xb);
 				put(k, M - k, Xa, Xb);
 			}
 		}
@@ -1065,7 +1075,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 			put(0, M, make_float2(Z0.x + Z0.y, 0.0f), make_float2(Z0.x - Z0.y, 0.0f));
 		}
 		else if (tid == 32 % NT) {
-			const float2 Xm = cconj(zres[fpad(M / 2)]);
+			const float2 Xm = cconj(zres[M / 2]);
 			put(M / 2, M / 2, Xm, Xm);
 		}
 	}
@@ -1088,14 +1098,14 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 			case 5: fast_h8<5>(P, st, i, slot, k0, H); break;
 			default: fast_h8<7>(P, st, i, slot, k0, H); break;
 			}
-			const float* const Eg = sm.erow + k0;
+			const float4* const erow4 = reinterpret_cast<const float4*>(sm.erow);
 			unsigned code;
 			if (want_p && want_h)
-				code = fast_decide8<true, true>(P, Eg, H);
+				code = fast_decide8<true, true>(P, erow4, 2 * g, H);
 			else if (want_p)
-				code = fast_decide8<true, false>(P, Eg, H);
+				code = fast_decide8<true, false>(P, erow4, 2 * g, H);
 			else if (want_h)
-				code = fast_decide8<false, true>(P, Eg, H);
+				code = fast_decide8<false, true>(P, erow4, 2 * g, H);
 			else
 				code = 0u;
 			sm.codes[g] = (unsigned short)code;
@@ -1109,7 +1119,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 			int np = 0, nh = 0;
 			for (int j0 = 0; j0 < L; j0 += 32) {
 				const int j = j0 + tid;
-				const float x = j < L ? sm.erow[M + j] : -1.0f;   // window of bin M: erow[M .. M + L)
+				const float x = j < L ? sm.erow[fast_esw(M + j)] : -1.0f;   // window of bin M: elements M .. M + L - 1
 				np += __popc(__ballot_sync(0xffffffffu, j < L && x >= tau));
 				nh += __popc(__ballot_sync(0xffffffffu, j < L && (x + ZEN_EPS) <= sig));
 			}
@@ -1149,8 +1159,8 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 				float2 Zk, Zmk;
 				masks(k, M - k, ma, mb);
 				rfft_pack_masked(zoth[k], ma, zoth[M - k], mb, __ldg(&P.twr[k]), Zk, Zmk);
-				zres[fpad(k)] = Zk;
-				zres[fpad(M - k)] = Zmk;
+				zres[k] = Zk;
+				zres[M - k] = Zmk;
 			}
 		}
 		if (tid == 0) {
@@ -1161,7 +1171,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 		else if (tid == 32 % NT) {
 			float ma, mb;
 			masks(M / 2, M / 2, ma, mb);
-			zres[fpad(M / 2)] = rfft_pack_mid(zoth[M / 2], ma);
+			zres[M / 2] = rfft_pack_mid(zoth[M / 2], ma);
 		}
 		__syncthreads();
 		// inverse FFT (hps.cu:522) whose last stage IS the overlap-add (hps.h:68-80): the thread that holds sample
@@ -1187,7 +1197,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 		};
 		if (o == last_o) {
 			// nobody needs X any more: ping-pong through its buffer, one barrier per stage, none at the end
-			fft_pp_rest<M, NT, +1, 1, false, true, false, true>(zres, zoth, P.tw, tid, ola);
+			fft_pp_rest<M, NT, +1, 1, false, true, false, true, LAY_N>(zres, zoth, P.tw, tid, ola);
 		}
 		else {
 			fft_inplace_last<M, NT, +1, 1, true, false>(zres, P.tw, tid, ola);
@@ -1263,7 +1273,7 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
 		}
 		float2 w = reinterpret_cast<const float2*>(tb.window)[n];
-		za[fpad(n)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+		za[n] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
 	}
 	__syncthreads();
 	stamp(1);
@@ -1279,16 +1289,16 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 			float2 Xa, Xb;
 			const int ka = k, kb = M - k;
 			if (k == 0) {
-				float2 Z0 = sm.zbuf[fpad(0)];
+				float2 Z0 = sm.zbuf[0];
 				Xa = make_float2(Z0.x + Z0.y, 0.0f);
 				Xb = make_float2(Z0.x - Z0.y, 0.0f);
 			}
 			else if (k == M / 2) {
-				Xa = cconj(sm.zbuf[fpad(M / 2)]);
+				Xa = cconj(sm.zbuf[M / 2]);
 				Xb = Xa;
 			}
 			else {
-				rfft_split_pair(sm.zbuf[fpad(k)], sm.zbuf[fpad(M - k)], tb.twr[k], Xa, Xb);
+				rfft_split_pair(sm.zbuf[k], sm.zbuf[M - k], tb.twr[k], Xa, Xb);
 			}
 			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
 			mag_row[ka] = ma;
@@ -1380,16 +1390,16 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 				const float ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
 				const float mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
 				if (k == 0) {
-					zb[fpad(0)] = rfft_pack_dc(Xa, ma, Xb, mb);
+					zb[0] = rfft_pack_dc(Xa, ma, Xb, mb);
 				}
 				else if (k == M / 2) {
-					zb[fpad(M / 2)] = rfft_pack_mid(Xa, ma);
+					zb[M / 2] = rfft_pack_mid(Xa, ma);
 				}
 				else {
 					float2 Zk, Zmk;
 					rfft_pack_masked(Xa, ma, Xb, mb, twk, Zk, Zmk);   // hps.h:58-66
-					zb[fpad(k)] = Zk;
-					zb[fpad(kb)] = Zmk;
+					zb[k] = Zk;
+					zb[kb] = Zmk;
 				}
 			}
 		}
