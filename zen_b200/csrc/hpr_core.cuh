@@ -811,7 +811,7 @@ struct FastSmem {
 // per thread): the lanes t and t + 4 of a quarter-warp then hit the same four banks in the plain layout - with the
 // swizzle they are in neighbouring blocks, one of which is flipped.
 __device__ __forceinline__ int fast_esw_chunk(int c) { return c ^ ((c >> 3) & 1); }
-__device__ __forceinline__ int fast_esw(int e) { return (fast_esw_chunk(e >> 2) << 2) | (e & 3); }
+__device__ __forceinline__ int fast_esw(int e) { return e ^ ((e >> 3) & 4); }  // == (fast_esw_chunk(e >> 2) << 2) | (e & 3)
 
 // per-CTA state of the fast path (global scratch that stays in L2)
 struct FastState {

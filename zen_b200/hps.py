@@ -426,7 +426,9 @@ def pcm16_decode_mono(pcm, channels=1):
     out = torch.empty((n_streams, n_frames), dtype=torch.float32, device=pcm.device)
     if n_frames == 0:
         return out
-    check(_lib.lib().zen_pcm16_decode_mono(pcm.data_ptr(), pcm.stride(0), channels, n_streams, n_frames, out.data_ptr(), max(1, out.stride(0))),
+    # (a one-row tensor may carry any stride for its first axis, 0 included)
+    in_stride = pcm.stride(0) if n_streams > 1 else pcm.shape[1]
+    check(_lib.lib().zen_pcm16_decode_mono(pcm.data_ptr(), in_stride, channels, n_streams, n_frames, out.data_ptr(), max(1, out.stride(0))),
           "zen_pcm16_decode_mono")
     return out
 
@@ -440,6 +442,7 @@ def pcm16_encode_normalized(x):
     peaks = torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
     if x.shape[1] == 0:
         return out, peaks
-    check(_lib.lib().zen_pcm16_encode_normalized(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), max(1, out.stride(0)),
+    in_stride = x.stride(0) if x.shape[0] > 1 else x.shape[1]
+    check(_lib.lib().zen_pcm16_encode_normalized(x.data_ptr(), in_stride, x.shape[0], x.shape[1], out.data_ptr(), max(1, out.stride(0)),
                                                  peaks.data_ptr()), "zen_pcm16_encode_normalized")
     return out, peaks
