@@ -24,7 +24,7 @@
 
 namespace zen_b200 {
 
-__host__ __device__ constexpr int fpad_size(int n) { return n + (n >> 3) + 1; }
+__host__ __device__ constexpr int fpad_size(int n) { return (n + (n >> 3) + 2) & ~1; }  // even: what follows stays 16-byte aligned
 
 enum { LAY_N = 0, LAY_F = 1, LAY_L2 = 2 };
 template <int LAY>

@@ -140,7 +140,7 @@ struct HprSmem {
 	{
 		size_t z = sizeof(float2) * (size_t)fpad_size(M);
 		size_t x = sizeof(float2) * (size_t)(M + 2);
-		size_t e = sizeof(float) * (size_t)((M + 1 + Lp + 3 + 3) & ~3);
+		size_t e = sizeof(float) * (size_t)((M + 1 + Lp + 3 + 12 + 3) & ~3);
 		size_t p = sizeof(float) * (size_t)((M + 1 + 3) & ~3);
 		return z + x + e + p + sizeof(int) * ZEN_MAX_TAPS;
 	}
@@ -149,7 +149,7 @@ struct HprSmem {
 		zbuf = reinterpret_cast<float2*>(base);
 		xbuf = zbuf + fpad_size(M);
 		erow = reinterpret_cast<float*>(xbuf + (M + 2));
-		prow = erow + ((M + 1 + Lp + 3 + 3) & ~3);
+		prow = erow + ((M + 1 + Lp + 3 + 12 + 3) & ~3);
 		taps = reinterpret_cast<int*>(prow + ((M + 1 + 3) & ~3));
 	}
 };
@@ -889,15 +889,13 @@ __device__ __forceinline__ float fast_h1(const HprDev& P, const FastState& st, i
 	return median_regs<7>(w);
 }
 
-// one frequency tap x that belongs to bins LO..HI of the eight: counts, two bins per packed register
-template <int LO, int HI, bool WP, bool WH>
-__device__ __forceinline__ void fast_tap(float x, const float (&tau)[8], const float (&sig)[8], f32x2_t (&cp)[4], f32x2_t (&ch)[4])
+// one frequency tap x that belongs to bins LO..HI of the U a thread decides: counts, two bins per packed register
+template <int LO, int HI, int U, bool WP, bool WH>
+__device__ __forceinline__ void fast_tap(float x, const float (&tau)[U], const float (&sig)[U], f32x2_t (&cp)[U / 2], f32x2_t (&ch)[U / 2])
 {
 	const float xe = x + ZEN_EPS;
 #pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		constexpr int dummy = 0;
-		(void)dummy;
+	for (int q = 0; q < U / 2; ++q) {
 		const int u0 = 2 * q, u1 = 2 * q + 1;
 		const bool a0 = u0 >= LO && u0 <= HI, a1 = u1 >= LO && u1 <= HI;
 		if (!a0 && !a1) continue;
@@ -913,80 +911,91 @@ __device__ __forceinline__ void fast_tap(float x, const float (&tau)[8], const f
 		}
 	}
 }
-
-// decisions of bins k0 .. k0 + 7 given their time medians: bit u = percussive, bit 8 + u = harmonic
-// (Mp = [P/(H+eps) >= beta], Mh = [H/(P+eps) >= beta-eps], hps.h:100-113, decided by counting: see decide_group_t)
-// erow4: the swizzled magnitude row as 16-byte chunks; c0 = chunk of the group's first tap (k0 / 4)
-template <bool WP, bool WH>
-__device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float4* __restrict__ erow4, int c0, const float (&H)[8])
+// taps i = 0 .. N-1 of a run: tap i belongs to bins max(0, i - FULL + 1) + ... i.e. the first FULL taps to all U bins,
+// tap FULL + t to bins t + 1 .. U - 1 (the tail of the window sweep); tv holds the run
+template <int I, int N, int FULL, int U, bool WP, bool WH>
+__device__ __forceinline__ void fast_tail(const float* tv, const float (&tau)[U], const float (&sig)[U], f32x2_t (&cp)[U / 2], f32x2_t (&ch)[U / 2])
 {
-	auto ldv = [&](int v) -> float4 { return erow4[fast_esw_chunk(c0 + v)]; };
+	if constexpr (I < N) {
+		constexpr int LO = I < FULL ? 0 : I - FULL + 1;
+		fast_tap<LO, U - 1, U, WP, WH>(tv[I], tau, sig, cp, ch);
+		fast_tail<I + 1, N, FULL, U, WP, WH>(tv, tau, sig, cp, ch);
+	}
+}
+template <int I, int U, bool WP, bool WH>
+__device__ __forceinline__ void fast_head(const float* tv, const float (&tau)[U], const float (&sig)[U], f32x2_t (&cp)[U / 2], f32x2_t (&ch)[U / 2])
+{
+	if constexpr (I < U) {
+		fast_tap<0, I, U, WP, WH>(tv[I], tau, sig, cp, ch);
+		fast_head<I + 1, U, WP, WH>(tv, tau, sig, cp, ch);
+	}
+}
+
+// Decisions of U consecutive bins (U = 8 in the batched kernel, 4 where latency counts) given their time medians:
+// bit u = percussive, bit 8 + u = harmonic (Mp = [P/(H+eps) >= beta], Mh = [H/(P+eps) >= beta-eps], hps.h:100-113,
+// decided by counting: see decide_group_t).  ldv(v) returns taps 4 v .. 4 v + 3 of the group: tap j belongs to bin u for
+// u <= j < u + L (L = P.Lp odd, >= U + 1).
+template <int U, bool WP, bool WH, typename LDV>
+__device__ __forceinline__ unsigned fast_decide(const HprDev& P, LDV ldv, const float (&H)[U])
+{
+	static_assert(U == 4 || U == 8, "four or eight bins per thread");
 	const int L = P.Lp;
-	float tau[8], sig[8];
+	float tau[U], sig[U];
 #pragma unroll
-	for (int u = 0; u < 8; ++u) {
+	for (int u = 0; u < U; ++u) {
 		tau[u] = WP ? thr_ratio_ge(H[u] + ZEN_EPS, P.rule_p) : CUDART_INF_F;
 		sig[u] = WH ? thr_ratio_le(H[u], P.rule_h) : -1.0f;
 	}
-	f32x2_t cp[4], ch[4];
+	f32x2_t cp[U / 2], ch[U / 2];
 #pragma unroll
-	for (int q = 0; q < 4; ++q)
+	for (int q = 0; q < U / 2; ++q)
 		cp[q] = ch[q] = pk(0.0f, 0.0f);
-	// tap j of bin k0 + u is element 4 c0 + j for u <= j < u + L.  Head: taps 0..7 (L >= 9, so tap 7 already belongs to all eight)
+	// head: taps 0 .. U-1, tap j belongs to bins 0 .. j (L > U, so tap U-1 already belongs to all of them)
 	{
-		const float4 h0 = ldv(0), h1 = ldv(1);
-		fast_tap<0, 0, WP, WH>(h0.x, tau, sig, cp, ch);
-		fast_tap<0, 1, WP, WH>(h0.y, tau, sig, cp, ch);
-		fast_tap<0, 2, WP, WH>(h0.z, tau, sig, cp, ch);
-		fast_tap<0, 3, WP, WH>(h0.w, tau, sig, cp, ch);
-		fast_tap<0, 4, WP, WH>(h1.x, tau, sig, cp, ch);
-		fast_tap<0, 5, WP, WH>(h1.y, tau, sig, cp, ch);
-		fast_tap<0, 6, WP, WH>(h1.z, tau, sig, cp, ch);
-		fast_tap<0, 7, WP, WH>(h1.w, tau, sig, cp, ch);
+		float tv[U];
+#pragma unroll
+		for (int v = 0; v < U / 4; ++v) {
+			const float4 x = ldv(v);
+			tv[4 * v] = x.x;
+			tv[4 * v + 1] = x.y;
+			tv[4 * v + 2] = x.z;
+			tv[4 * v + 3] = x.w;
+		}
+		fast_head<0, U, WP, WH>(tv, tau, sig, cp, ch);
 	}
-	// body: whole vectors of taps that belong to all eight bins: 8 <= 4 v and 4 v + 3 <= L - 1
+	// body: whole vectors of taps that belong to every bin: U <= 4 v and 4 v + 3 <= L - 1
 	const int v_end = (L - 4) / 4;
-	int v = 2;
+	int v = U / 4;
 #pragma unroll 2
 	for (; v <= v_end; ++v) {
 		const float4 x = ldv(v);
-		fast_tap<0, 7, WP, WH>(x.x, tau, sig, cp, ch);
-		fast_tap<0, 7, WP, WH>(x.y, tau, sig, cp, ch);
-		fast_tap<0, 7, WP, WH>(x.z, tau, sig, cp, ch);
-		fast_tap<0, 7, WP, WH>(x.w, tau, sig, cp, ch);
+		fast_tap<0, U - 1, U, WP, WH>(x.x, tau, sig, cp, ch);
+		fast_tap<0, U - 1, U, WP, WH>(x.y, tau, sig, cp, ch);
+		fast_tap<0, U - 1, U, WP, WH>(x.z, tau, sig, cp, ch);
+		fast_tap<0, U - 1, U, WP, WH>(x.w, tau, sig, cp, ch);
 	}
-	// tail: taps 4 v .. L + 6, tap j belongs to bins j - L + 1 .. 7.  L is odd: either L = 4 v + 3 (three more taps that
-	// belong to all eight bins, then L .. L + 6) or L = 4 v + 1 (one more, then L .. L + 6); both fully unrolled.
+	// tail: taps 4 v .. L + U - 2, tap j belongs to bins j - L + 1 .. U - 1.  L is odd: either L = 4 v + 3 (three more
+	// taps that belong to every bin, then L .. L + U - 2) or L = 4 v + 1 (one more, then the same); both fully unrolled.
 	{
-		const float4 t0 = ldv(v), t1 = ldv(v + 1);
-		if ((L & 3) == 3) {
-			const float4 t2 = ldv(v + 2);
-			fast_tap<0, 7, WP, WH>(t0.x, tau, sig, cp, ch);
-			fast_tap<0, 7, WP, WH>(t0.y, tau, sig, cp, ch);
-			fast_tap<0, 7, WP, WH>(t0.z, tau, sig, cp, ch);
-			fast_tap<1, 7, WP, WH>(t0.w, tau, sig, cp, ch);
-			fast_tap<2, 7, WP, WH>(t1.x, tau, sig, cp, ch);
-			fast_tap<3, 7, WP, WH>(t1.y, tau, sig, cp, ch);
-			fast_tap<4, 7, WP, WH>(t1.z, tau, sig, cp, ch);
-			fast_tap<5, 7, WP, WH>(t1.w, tau, sig, cp, ch);
-			fast_tap<6, 7, WP, WH>(t2.x, tau, sig, cp, ch);
-			fast_tap<7, 7, WP, WH>(t2.y, tau, sig, cp, ch);
+		constexpr int NV = (3 + U - 1 + 3) / 4;  // vectors that hold the longer of the two runs
+		float tv[4 * NV];
+#pragma unroll
+		for (int w = 0; w < NV; ++w) {
+			const float4 x = ldv(v + w);
+			tv[4 * w] = x.x;
+			tv[4 * w + 1] = x.y;
+			tv[4 * w + 2] = x.z;
+			tv[4 * w + 3] = x.w;
 		}
-		else {
-			fast_tap<0, 7, WP, WH>(t0.x, tau, sig, cp, ch);
-			fast_tap<1, 7, WP, WH>(t0.y, tau, sig, cp, ch);
-			fast_tap<2, 7, WP, WH>(t0.z, tau, sig, cp, ch);
-			fast_tap<3, 7, WP, WH>(t0.w, tau, sig, cp, ch);
-			fast_tap<4, 7, WP, WH>(t1.x, tau, sig, cp, ch);
-			fast_tap<5, 7, WP, WH>(t1.y, tau, sig, cp, ch);
-			fast_tap<6, 7, WP, WH>(t1.z, tau, sig, cp, ch);
-			fast_tap<7, 7, WP, WH>(t1.w, tau, sig, cp, ch);
-		}
+		if ((L & 3) == 3)
+			fast_tail<0, 3 + U - 1, 3, U, WP, WH>(tv, tau, sig, cp, ch);
+		else
+			fast_tail<0, 1 + U - 1, 1, U, WP, WH>(tv, tau, sig, cp, ch);
 	}
 	const float need = (float)(L / 2 + 1);
 	unsigned code = 0u;
 #pragma unroll
-	for (int q = 0; q < 4; ++q) {
+	for (int q = 0; q < U / 2; ++q) {
 		const float2 c = up(cp[q]), d = up(ch[q]);
 		if (WP) {
 			code |= (c.x >= need ? 1u : 0u) << (2 * q);
@@ -998,6 +1007,17 @@ __device__ __forceinline__ unsigned fast_decide8(const HprDev& P, const float4* 
 		}
 	}
 	return code;
+}
+// dispatch on the enabled masks (a mask is only computed for an output that is enabled, hps.cu:498-567)
+template <int U, typename LDV>
+__device__ __forceinline__ unsigned fast_decide_flags(const HprDev& P, LDV ldv, const float (&H)[U])
+{
+	const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
+	const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
+	if (want_p && want_h) return fast_decide<U, true, true>(P, ldv, H);
+	if (want_p) return fast_decide<U, true, false>(P, ldv, H);
+	if (want_h) return fast_decide<U, false, true>(P, ldv, H);
+	return 0u;
 }
 
 template <int NFFT, int NT, bool PEAKS>
@@ -1099,15 +1119,7 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 			default: fast_h8<7>(P, st, i, slot, k0, H); break;
 			}
 			const float4* const erow4 = reinterpret_cast<const float4*>(sm.erow);
-			unsigned code;
-			if (want_p && want_h)
-				code = fast_decide8<true, true>(P, erow4, 2 * g, H);
-			else if (want_p)
-				code = fast_decide8<true, false>(P, erow4, 2 * g, H);
-			else if (want_h)
-				code = fast_decide8<false, true>(P, erow4, 2 * g, H);
-			else
-				code = 0u;
+			const unsigned code = fast_decide_flags<8>(P, [&](int v) -> float4 { return erow4[fast_esw_chunk(2 * g + v)]; }, H);
 			sm.codes[g] = (unsigned short)code;
 		}
 		// the Nyquist bin k = M: one warp, one tap per lane and round
@@ -1245,13 +1257,14 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
                                                   const float* __restrict__ prev, const float* __restrict__ cur, float* cur_stash,
                                                   const HprTables& tb, const HprSplit& sp, float2* zpp, int recv_off, unsigned long long* stamps)
 {
+	static_assert(US == 4, "the split hop decides four bins per thread");
 	auto stamp = [&](int idx) {
 		if (stamps && threadIdx.x == 0)
 			stamps[idx] = (unsigned long long)clock64();
 	};
 	stamp(0);
 	constexpr int M = NFFT / 2;
-	constexpr int HOP = M / 2;
+	constexpr int HC = M / 4;  // complex (packed even / odd) samples per hop
 	const int tid = threadIdx.x;
 	const int W = P.W;
 	const int eoff = P.midp;
@@ -1259,28 +1272,32 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 		int j = i - P.tap_age[t];
 		sm.taps[t] = j >= 0 ? (j % W) * (M + 1) : -1;
 	}
-	// ---- A. window (prev is in this CTA's shared memory, cur in this or in the leader CTA's).  The forward FFT
-	// ping-pongs between zbuf and zpp; it starts in the one that makes it END in zbuf.
-	float2* const za = (fft_stage_count<M>() % 2 == 0) ? sm.zbuf : zpp;
-	float2* const zb2 = (fft_stage_count<M>() % 2 == 0) ? zpp : sm.zbuf;
-#pragma unroll 4
-	for (int n = tid; n < HOP; n += NT) {
+	// ---- A + B. sqrt-Hann window fused into the first stage of the forward FFT (prev is in this CTA's shared memory,
+	// cur in this or in the leader CTA's; every element of the hop is read by exactly one thread, which also keeps the
+	// copy that becomes the next hop's `prev`).  The stages ping-pong between zbuf and zpp and END in zbuf.
+	constexpr bool even_stages = fft_stage_count<M>() % 2 == 0;
+	float2* const fa = even_stages ? zpp : sm.zbuf;
+	float2* const fb = even_stages ? sm.zbuf : zpp;
+	const float2* const prev2 = reinterpret_cast<const float2*>(prev);
+	const float2* const cur2 = reinterpret_cast<const float2*>(cur);
+	float2* const stash2 = reinterpret_cast<float2*>(cur_stash);
+	const float2* const win2 = reinterpret_cast<const float2*>(tb.window);
+	auto load_frame = [&](int j, int r, int /*p*/) -> float2 {
+		constexpr int NB = M / 8;
+		static_assert(HC == 2 * NB, "first stage must be radix 8");
 		float2 x;
-		if (n < HOP / 2)
-			x = reinterpret_cast<const float2*>(prev)[n];
+		if (r < 2)
+			x = prev2[j + r * NB];
 		else {
-			x = reinterpret_cast<const float2*>(cur)[n - HOP / 2];
-			if (cur_stash) reinterpret_cast<float2*>(cur_stash)[n - HOP / 2] = x;
+			x = cur2[j + (r - 2) * NB];
+			if (stash2) stash2[j + (r - 2) * NB] = x;
 		}
-		float2 w = reinterpret_cast<const float2*>(tb.window)[n];
-		za[n] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
-	}
-	__syncthreads();
-	stamp(1);
-	// ---- B. forward FFT, whole frame
-	fft_smem_pp<M, NT, -1, 1, true, false, true>(za, zb2, tb.tw, tid);
+		const float2 w = win2[j + r * NB];
+		return make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+	};
+	fft_pp_fused<M, NT, -1, true, false, true, false>(fa, fb, tb.tw, tid, load_frame, NoFn{});
 	stamp(2);
-	// ---- C. real-input spectrum and |X| of the own pairs and their halo
+	// ---- C. real-input spectrum and |X| of the own pairs and their halo (mirrored borders included)
 	const int halo = P.midp + US;
 	const int pl = max(0, sp.k0 - halo), ph = min(M / 2, sp.k1 - 1 + halo);
 	{
@@ -1309,65 +1326,50 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 				sm.xbuf[kb] = Xb;
 				sm.erow[eoff + kb] = mb;
 			}
+			// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]|
+			if (k >= 1 && k <= P.midp) {
+				sm.erow[eoff - k] = ma;
+				sm.erow[eoff + M + k] = mb;
+			}
 		}
 	}
 	__syncthreads();
 	stamp(3);
-	// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]| (only the CTAs whose windows reach them)
-	if (pl == 0) {
-		for (int t = tid; t < P.midp; t += NT) {
-			sm.erow[eoff - 1 - t] = sm.erow[eoff + 1 + t];
-			sm.erow[eoff + M + 1 + t] = sm.erow[eoff + M - 1 - t];
-		}
-	}
-	// ---- F'. time median of the own bins (the H row goes into zbuf, free until the next hop)
-	float* hrow = reinterpret_cast<float*>(sm.zbuf);
-	const int nA = sp.a1 - sp.a0, nB = sp.b1 - sp.b0;
-	{
-		const int nt = P.n_taps;
-		auto tap = [&](int t, int k) -> float {
-			int off = sm.taps[t];
-			return off >= 0 ? st.mag_ring[off + k] : 0.0f;
-		};
-		for (int idx = tid; idx < nA + nB; idx += NT) {
-			const int k = idx < nA ? sp.a0 + idx : sp.b0 + (idx - nA);
-			float H;
-			switch (nt) {
-			case 0: H = 0.0f; break;
-			case 1: H = tap(0, k); break;
-			case 3: H = median_fixed<3>([&](int t) { return tap(t, k); }); break;
-			case 5: H = median_fixed<5>([&](int t) { return tap(t, k); }); break;
-			case 7: H = median_fixed<7>([&](int t) { return tap(t, k); }); break;
-			case 9: H = median_fixed<9>([&](int t) { return tap(t, k); }); break;
-			case 11: H = median_fixed<11>([&](int t) { return tap(t, k); }); break;
-			case 13: H = median_fixed<13>([&](int t) { return tap(t, k); }); break;
-			default: H = median_generic([&](int t) { return tap(t, k); }, nt); break;
-			}
-			hrow[k] = H;
-		}
-	}
-	__syncthreads();
-	stamp(4);
-	// ---- E'. hard-mask decisions of the own bins (decide_group), codes as in hpr_iteration (bit0|bit1 P, bit2|bit3 H)
+	// ---- F' + E'. time medians (hps.cu:495, consumed row only) and hard-mask decisions of the own bins, four
+	// consecutive bins per thread (fast_decide); codes as in hpr_iteration (bit0|bit1 P, bit2|bit3 H)
 	{
 		unsigned* codes = reinterpret_cast<unsigned*>(sm.prow);
-		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
-		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
-		const int gA = (nA + US - 1) / US, gB = (nB + US - 1) / US;
-		for (int g = tid; g < gA + gB; g += NT) {
-			const bool inA = g < gA;
-			const int kg = inA ? sp.a0 + g * US : sp.b0 + (g - gA) * US;
-			const int kmax = (inA ? sp.a1 : sp.b1) - 1;
-			unsigned fp, fh;
-			decide_group<US>(sm.erow, hrow, kg, kmax, 0, P.Lp, P.rule_p, P.rule_h, want_p, want_h, fp, fh);
+		const int nt = P.n_taps;
+		auto tap = [&](int t, int k) -> float {
+			const int off = sm.taps[t];
+			return off >= 0 ? st.mag_ring[off + k] : 0.0f;
+		};
+		const int qa0 = sp.a0 >> 2, nqa = sp.a1 > sp.a0 ? ((sp.a1 - 1) >> 2) - qa0 + 1 : 0;
+		const int qb0 = sp.b0 >> 2, nqb = sp.b1 > sp.b0 ? ((sp.b1 - 1) >> 2) - qb0 + 1 : 0;
+		for (int g = tid; g < nqa + nqb; g += NT) {
+			const int k0 = 4 * (g < nqa ? qa0 + g : qb0 + (g - nqa));
+			float H[4];
 #pragma unroll
-			for (int u = 0; u < US; ++u) {
-				const int k = kg + u;
-				if (k <= kmax) {
-					const unsigned p0 = (fp >> u) & 1u, h0 = (fh >> u) & 1u;
-					codes[k] = p0 * 3u | (h0 * 3u) << 2;
+			for (int u = 0; u < 4; ++u) {
+				const int k = min(k0 + u, M);
+				switch (nt) {
+				case 0: H[u] = 0.0f; break;
+				case 1: H[u] = tap(0, k); break;
+				case 3: H[u] = median_fixed<3>([&](int t) { return tap(t, k); }); break;
+				case 5: H[u] = median_fixed<5>([&](int t) { return tap(t, k); }); break;
+				case 7: H[u] = median_fixed<7>([&](int t) { return tap(t, k); }); break;
+				case 9: H[u] = median_fixed<9>([&](int t) { return tap(t, k); }); break;
+				case 11: H[u] = median_fixed<11>([&](int t) { return tap(t, k); }); break;
+				case 13: H[u] = median_fixed<13>([&](int t) { return tap(t, k); }); break;
+				default: H[u] = median_generic([&](int t) { return tap(t, k); }, nt); break;
 				}
 			}
+			const float4* const e4 = reinterpret_cast<const float4*>(sm.erow + k0);  // tap j of bin k0 + u: erow[k0 + j], u <= j < u + L
+			const unsigned code = fast_decide_flags<4>(P, [&](int v) -> float4 { return e4[v]; }, H);
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+				if (k0 + u <= M)
+					codes[k0 + u] = ((code >> u) & 1u) * 3u | (((code >> (8 + u)) & 1u) * 3u) << 2;
 		}
 	}
 	__syncthreads();
@@ -1406,17 +1408,59 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 	}
 }
 
+// tagged emission of one hop held in pbuf (HOP floats of shared memory): see HprPack.  All NT threads must call it.
+template <int NFFT, int NT>
+__device__ __forceinline__ void hpr_pack_groups(const float* pbuf, uint4* pdst, unsigned ptag)
+{
+	constexpr int HOP = NFFT / 4;
+	constexpr int NG = (HOP + 2) / 3, NLG = 4 * (HOP / 12);
+	const int tid = threadIdx.x;
+	for (int g0 = 0; g0 < NG; g0 += NT) {  // (every thread makes every trip: zen_group_key shuffles)
+		const int g = g0 + tid;
+		uint4 v = make_uint4(0u, 0u, 0u, 0u);
+		if (g < NG) {
+			v.x = __float_as_uint(pbuf[3 * g]);
+			v.y = 3 * g + 1 < HOP ? __float_as_uint(pbuf[3 * g + 1]) : 0u;
+			v.z = 3 * g + 2 < HOP ? __float_as_uint(pbuf[3 * g + 2]) : 0u;
+		}
+		v.w = ptag ^ zen_group_key(v.x, v.y, v.z, g, NLG);
+		if (g < NG)
+			asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pdst + g), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+			             : "memory");
+	}
+}
+
 // G (second half), run by the CTA that owns output o after the cluster barrier: inverse FFT of the received masked
-// spectrum, overlap-add, emission.
+// spectrum whose last stage is the overlap-add (hps.h:68-80: the thread that holds sample pair n < HC of the frame also
+// holds pair n + HC, so it reads tail[n], emits, then writes the new tail[n]), then the tagged emission.
 template <int NFFT, int NT>
 __device__ __forceinline__ void hpr_split_synth(const HprDev& P, float2* zb, float2* zpp, float* tail, float* ea, float* eb, float* pbuf,
                                                 uint4* pdst, unsigned ptag, const HprTables& tb, unsigned long long* stamps)
 {
-	constexpr int M = NFFT / 2;
+	constexpr int M = NFFT / 2, HC = M / 4;
 	if (stamps && threadIdx.x == 0) stamps[6] = (unsigned long long)clock64();
-	const float2* y = fft_smem_pp<M, NT, +1, 1, false, true, true>(zb, zpp, tb.tw, threadIdx.x);
+	float2* const tail2 = reinterpret_cast<float2*>(tail);
+	float2* const ea2 = reinterpret_cast<float2*>(ea);
+	float2* const eb2 = reinterpret_cast<float2*>(eb);
+	float2* const pb2 = reinterpret_cast<float2*>(pbuf);
+	const float cola = P.cola;
+	auto ola = [&](int idx, int /*p*/, float2 v) {
+		if (idx < HC) {
+			const float2 t = tail2[idx];
+			const float2 r = up(pfma(pk(v), pk(cola, cola), pk(t)));
+			if (ea2) __stcs(ea2 + idx, r);
+			if (eb2) __stcs(eb2 + idx, r);
+			if (pdst) pb2[idx] = r;
+		}
+		else {
+			tail2[idx - HC] = up(pmul(pk(v), pk(cola, cola)));
+		}
+	};
+	fft_pp_rest<M, NT, +1, 1, false, true, true, true, LAY_N>(zb, zpp, tb.tw, threadIdx.x, ola);
 	if (stamps && threadIdx.x == 0) stamps[7] = (unsigned long long)clock64();
-	hpr_ola_emit<NFFT, NT>(P, y, tail, false, ea, eb, pbuf, pdst, ptag);
+	__syncthreads();
+	if (pdst) hpr_pack_groups<NFFT, NT>(pbuf, pdst, ptag);
+	__syncthreads();
 	if (stamps && threadIdx.x == 0) stamps[8] = (unsigned long long)clock64();
 }
 

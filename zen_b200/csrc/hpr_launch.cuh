@@ -329,11 +329,11 @@ constexpr int rt_table_floats()
 	// window (nwin) + per-stage twiddles + split twiddles, as floats
 	return NFFT / 2 + 2 * fft_twiddle_count<NFFT / 2>() + 2 * (NFFT / 4 + 1);
 }
-// bins decided per thread in the cluster-split hop: a quarter of the half spectrum over NT threads
+// bins decided per thread in the cluster-split hop (hpr_split_analyse)
 template <int NFFT, int NT>
 constexpr int rt_us_for()
 {
-	return (NFFT / 8 + 1 + NT - 1) / NT;
+	return 4;
 }
 
 // Everything the resident kernel needs from one hop to the next lives in SHARED memory, not in registers or local
