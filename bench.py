@@ -488,7 +488,7 @@ def measure_latency(args):
     res["region"] = "zen/fakert.h:221-247 (host copy-in, process_next_hop, copy_percussive, host copy-out)"
     res["two_call_api"] = "HPRRealtime::process_next_hop + copy_percussive (2 launches)"
     res["fused_call_api"] = "zen_hpr_process_hop_io (1 launch)"
-    res["resident_kernel_api"] = ("zen_hpr_realtime_begin + zen_hpr_process_hop_io (persistent 4-CTA cluster kernel, hop pushed / output returned as tagged "
+    res["resident_kernel_api"] = ("zen_hpr_realtime_begin + zen_hpr_process_hop_io (persistent 8-CTA cluster kernel, hop pushed / output returned as tagged "
                                   "16-byte groups in mapped memory, 0 launches and 0 fences per hop)")
     res["resident_two_call_api"] = "zen_hpr_realtime_begin, then the reference's own pair HPRRealtime::process_next_hop + copy_percussive"
     res["p50_us"] = res["resident_kernel"]["p50_us"]

@@ -131,7 +131,7 @@ int zen_hpr_wait_input_consumed(zen_hpr* h);
  * is PUSHED to the kernel as tagged 16-byte groups {x0, x1, x2, tag} and the
  * outputs come back the same way; device-memory pointers are read / written by
  * the kernel itself behind a completion flag.  With the default plan (hard mask,
- * copy-border) the hop is split over a 4-CTA thread-block cluster
+ * copy-border) the hop is split over an 8-CTA thread-block cluster
  * (ZEN_B200_RT_CLUSTER=1|2|4|8).  Calls stay synchronous: on return the outputs
  * are readable by the host.  The kernel leaves by itself after
  * ZEN_B200_RT_IDLE_MS (default 250) without a hop and is brought back
@@ -172,6 +172,7 @@ int zen_rt_unpack_groups(const void* groups, int hop, unsigned tag, float* dst);
 /* diagnostics (ZEN_B200_RT_STAMPS=1): SM cycle counter at the phase boundaries of the last hop the resident kernel
  * served, [9] / [12] = %globaltimer (ns) at its start / end */
 int zen_hpr_realtime_stamps(zen_hpr* h, unsigned long long* out16);
+int zen_hpr_realtime_stamps_rank1(zen_hpr* h, unsigned long long* out16); /* CTA 1 of the cluster; [9] = when it saw the command */
 /* Make caller-owned device buffers (nwin floats each, 8-byte aligned) the object's
  * streaming state, so that e.g. thrust::device_vector members named like the
  * reference's (hps.h:182-197) ARE the state; zeroes them (reset_buffers). */

@@ -1020,6 +1020,36 @@ __device__ __forceinline__ unsigned fast_decide_flags(const HprDev& P, LDV ldv, 
 	return 0u;
 }
 
+// masked spectrum of output O (0 harmonic, 1 percussive, 2 residual) packed for the M-point inverse transform:
+// X (natural order) * mask -> Z (natural order); hps.h:35-43, 58-66
+template <int NFFT, int NT, int O>
+__device__ __forceinline__ void fast_pack(const HprDev& P, const unsigned short* __restrict__ codes, const float2* __restrict__ X, float2* __restrict__ Z)
+{
+	constexpr int M = NFFT / 2;
+	const int tid = threadIdx.x;
+	auto mask = [&](int k) -> float {
+		const unsigned c = (unsigned)codes[k >> 3] >> (k & 7);
+		if (O == 1) return (float)(c & 1u);
+		if (O == 0) return (float)((c >> 8) & 1u);
+		return 1.0f - ((float)((c >> 8) & 1u) + (float)(c & 1u));
+	};
+	constexpr int TRIPS = (M / 2 + NT - 1) / NT;
+#pragma unroll
+	for (int it = 0; it < TRIPS; ++it) {
+		const int k = tid + it * NT;
+		if (((M / 2) % NT == 0 || k < M / 2) && (it > 0 || k > 0)) {
+			float2 Zk, Zmk;
+			rfft_pack_masked(X[k], mask(k), X[M - k], mask(M - k), __ldg(&P.twr[k]), Zk, Zmk);
+			Z[k] = Zk;
+			Z[M - k] = Zmk;
+		}
+	}
+	if (tid == 0)
+		Z[0] = rfft_pack_dc(X[0], mask(0), X[M], mask(M));
+	else if (tid == 32 % NT)
+		Z[M / 2] = rfft_pack_mid(X[M / 2], mask(M / 2));
+}
+
 template <int NFFT, int NT, bool PEAKS>
 __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFFT>& sm, const FastState& st, const int i, const int slot,
                                                    const float* __restrict__ prev, const float* __restrict__ cur, bool full, bool fresh_tail,
@@ -1122,21 +1152,23 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 			const unsigned code = fast_decide_flags<8>(P, [&](int v) -> float4 { return erow4[fast_esw_chunk(2 * g + v)]; }, H);
 			sm.codes[g] = (unsigned short)code;
 		}
-		// the Nyquist bin k = M: one warp, one tap per lane and round
-		if (tid < 32) {
+		// the Nyquist bin k = M: one warp, one tap per lane and round.  The LAST warp takes it: the scheduler favours the
+		// higher warp ids, so it is the one with slack before the barrier.
+		if (tid >= NT - 32) {
+			const int lane = tid & 31;
 			const float Hm = fast_h1(P, st, i, slot, M);
 			const float tau = want_p ? thr_ratio_ge(Hm + ZEN_EPS, P.rule_p) : CUDART_INF_F;
 			const float sig = want_h ? thr_ratio_le(Hm, P.rule_h) : -1.0f;
 			const int L = P.Lp;
 			int np = 0, nh = 0;
 			for (int j0 = 0; j0 < L; j0 += 32) {
-				const int j = j0 + tid;
+				const int j = j0 + lane;
 				const float x = j < L ? sm.erow[fast_esw(M + j)] : -1.0f;   // window of bin M: elements M .. M + L - 1
 				np += __popc(__ballot_sync(0xffffffffu, j < L && x >= tau));
 				nh += __popc(__ballot_sync(0xffffffffu, j < L && (x + ZEN_EPS) <= sig));
 			}
 			const int need = L / 2 + 1;
-			if (tid == 0)
+			if (lane == 0)
 				sm.codes[M / 8] = (unsigned short)((np >= need ? 1u : 0u) | ((nh >= need ? 1u : 0u) << 8));
 		}
 	}
@@ -1155,35 +1187,10 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 		if (!(P.out_flags & (1 << o)))
 			continue;
 		// masked spectrum packed for the M-point inverse transform, into zres (X stays in zoth)
-		auto masks = [&](int k, int kb, float& ma, float& mb) {
-			const unsigned ca = (unsigned)sm.codes[k >> 3] >> (k & 7), cb = (unsigned)sm.codes[kb >> 3] >> (kb & 7);
-			const float mpa = (float)(ca & 1u), mha = (float)((ca >> 8) & 1u);
-			const float mpb = (float)(cb & 1u), mhb = (float)((cb >> 8) & 1u);
-			ma = (o == 1) ? mpa : (o == 0 ? mha : 1.0f - (mha + mpa));  // hps.h:35-43
-			mb = (o == 1) ? mpb : (o == 0 ? mhb : 1.0f - (mhb + mpb));
-		};
-		constexpr int TRIPS = (M / 2 + NT - 1) / NT;
-#pragma unroll
-		for (int it = 0; it < TRIPS; ++it) {
-			const int k = tid + it * NT;
-			if (((M / 2) % NT == 0 || k < M / 2) && (it > 0 || k > 0)) {
-				float ma, mb;
-				float2 Zk, Zmk;
-				masks(k, M - k, ma, mb);
-				rfft_pack_masked(zoth[k], ma, zoth[M - k], mb, __ldg(&P.twr[k]), Zk, Zmk);
-				zres[k] = Zk;
-				zres[M - k] = Zmk;
-			}
-		}
-		if (tid == 0) {
-			float ma, mb;
-			masks(0, M, ma, mb);
-			zres[0] = rfft_pack_dc(zoth[0], ma, zoth[M], mb);
-		}
-		else if (tid == 32 % NT) {
-			float ma, mb;
-			masks(M / 2, M / 2, ma, mb);
-			zres[M / 2] = rfft_pack_mid(zoth[M / 2], ma);
+		switch (o) {
+		case 1: fast_pack<NFFT, NT, 1>(P, sm.codes, zoth, zres); break;
+		case 0: fast_pack<NFFT, NT, 0>(P, sm.codes, zoth, zres); break;
+		default: fast_pack<NFFT, NT, 2>(P, sm.codes, zoth, zres); break;
 		}
 		__syncthreads();
 		// inverse FFT (hps.cu:522) whose last stage IS the overlap-add (hps.h:68-80): the thread that holds sample
@@ -1257,7 +1264,7 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
                                                   const float* __restrict__ prev, const float* __restrict__ cur, float* cur_stash,
                                                   const HprTables& tb, const HprSplit& sp, float2* zpp, int recv_off, unsigned long long* stamps)
 {
-	static_assert(US == 4, "the split hop decides four bins per thread");
+	(void)US;
 	auto stamp = [&](int idx) {
 		if (stamps && threadIdx.x == 0)
 			stamps[idx] = (unsigned long long)clock64();
@@ -1295,10 +1302,11 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 		const float2 w = win2[j + r * NB];
 		return make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
 	};
+	stamp(1);
 	fft_pp_fused<M, NT, -1, true, false, true, false>(fa, fb, tb.tw, tid, load_frame, NoFn{});
 	stamp(2);
 	// ---- C. real-input spectrum and |X| of the own pairs and their halo (mirrored borders included)
-	const int halo = P.midp + US;
+	const int halo = P.midp;
 	const int pl = max(0, sp.k0 - halo), ph = min(M / 2, sp.k1 - 1 + halo);
 	{
 		float* mag_row = st.mag_ring + (size_t)(i % W) * (M + 1);
@@ -1335,41 +1343,97 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 	}
 	__syncthreads();
 	stamp(3);
-	// ---- F' + E'. time medians (hps.cu:495, consumed row only) and hard-mask decisions of the own bins, four
-	// consecutive bins per thread (fast_decide); codes as in hpr_iteration (bit0|bit1 P, bit2|bit3 H)
+	stamp(4);
+	// ---- F' + E'. time median (hps.cu:495, consumed row only) and hard-mask decision of the own bins: ONE bin per
+	// thread.  This is the latency path: a hop is a chain of short phases, and a phase is as long as its slowest
+	// thread, so the work is spread as thin as it goes (the batched kernel does the opposite: eight bins per thread,
+	// taps shared, fewer instructions).  Codes as in hpr_iteration (bit0|bit1 P, bit2|bit3 H).
 	{
 		unsigned* codes = reinterpret_cast<unsigned*>(sm.prow);
 		const int nt = P.n_taps;
+		const bool want_p = (P.out_flags & ZEN_OUTPUT_PERCUSSIVE) != 0;
+		const bool want_h = (P.out_flags & ZEN_OUTPUT_HARMONIC) != 0;
+		const int L = P.Lp;
+		const float need = (float)(L / 2 + 1);
+		const float* const ring = st.mag_ring;
 		auto tap = [&](int t, int k) -> float {
 			const int off = sm.taps[t];
-			return off >= 0 ? st.mag_ring[off + k] : 0.0f;
+			return off >= 0 ? ring[off + k] : 0.0f;
 		};
-		const int qa0 = sp.a0 >> 2, nqa = sp.a1 > sp.a0 ? ((sp.a1 - 1) >> 2) - qa0 + 1 : 0;
-		const int qb0 = sp.b0 >> 2, nqb = sp.b1 > sp.b0 ? ((sp.b1 - 1) >> 2) - qb0 + 1 : 0;
-		for (int g = tid; g < nqa + nqb; g += NT) {
-			const int k0 = 4 * (g < nqa ? qa0 + g : qb0 + (g - nqa));
-			float H[4];
+		auto hmed = [&](int k) -> float {
+			switch (nt) {
+			case 0: return 0.0f;
+			case 1: return tap(0, k);
+			case 3: return median_fixed<3>([&](int t) { return tap(t, k); });
+			case 5: return median_fixed<5>([&](int t) { return tap(t, k); });
+			case 7: return median_fixed<7>([&](int t) { return tap(t, k); });
+			case 9: return median_fixed<9>([&](int t) { return tap(t, k); });
+			case 11: return median_fixed<11>([&](int t) { return tap(t, k); });
+			case 13: return median_fixed<13>([&](int t) { return tap(t, k); });
+			default: return median_generic([&](int t) { return tap(t, k); }, nt);
+			}
+		};
+		const int nA = sp.a1 - sp.a0, nB = sp.b1 - sp.b0;
+		const int n_own = nA + nB;
+		auto bin_of = [&](int idx) { return idx < nA ? sp.a0 + idx : sp.b0 + (idx - nA); };
+		// counts of one bin, specialised on the enabled masks: two taps per packed add (FADD2), two independent chains
+		auto count1 = [&](auto wp_c, auto wh_c, const float* E, float tau, float sig, float& cp, float& ch) {
+			constexpr bool WP = decltype(wp_c)::value, WH = decltype(wh_c)::value;
+			f32x2_t ap[2] = {pk(0.0f, 0.0f), pk(0.0f, 0.0f)}, ah[2] = {pk(0.0f, 0.0f), pk(0.0f, 0.0f)};
+			int j = 0;
+#pragma unroll 2
+			for (; j + 3 < L; j += 4) {
 #pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				const int k = min(k0 + u, M);
-				switch (nt) {
-				case 0: H[u] = 0.0f; break;
-				case 1: H[u] = tap(0, k); break;
-				case 3: H[u] = median_fixed<3>([&](int t) { return tap(t, k); }); break;
-				case 5: H[u] = median_fixed<5>([&](int t) { return tap(t, k); }); break;
-				case 7: H[u] = median_fixed<7>([&](int t) { return tap(t, k); }); break;
-				case 9: H[u] = median_fixed<9>([&](int t) { return tap(t, k); }); break;
-				case 11: H[u] = median_fixed<11>([&](int t) { return tap(t, k); }); break;
-				case 13: H[u] = median_fixed<13>([&](int t) { return tap(t, k); }); break;
-				default: H[u] = median_generic([&](int t) { return tap(t, k); }, nt); break;
+				for (int c = 0; c < 2; ++c) {
+					const float x0 = E[j + 2 * c], x1 = E[j + 2 * c + 1];
+					if (WP) ap[c] = padd(ap[c], pk((x0 >= tau) ? 1.0f : 0.0f, (x1 >= tau) ? 1.0f : 0.0f));
+					if (WH) ah[c] = padd(ah[c], pk(((x0 + ZEN_EPS) <= sig) ? 1.0f : 0.0f, ((x1 + ZEN_EPS) <= sig) ? 1.0f : 0.0f));
 				}
 			}
-			const float4* const e4 = reinterpret_cast<const float4*>(sm.erow + k0);  // tap j of bin k0 + u: erow[k0 + j], u <= j < u + L
-			const unsigned code = fast_decide_flags<4>(P, [&](int v) -> float4 { return e4[v]; }, H);
-#pragma unroll
-			for (int u = 0; u < 4; ++u)
-				if (k0 + u <= M)
-					codes[k0 + u] = ((code >> u) & 1u) * 3u | (((code >> (8 + u)) & 1u) * 3u) << 2;
+			for (; j < L; ++j) {
+				const float x0 = E[j];
+				if (WP) ap[0] = padd(ap[0], pk((x0 >= tau) ? 1.0f : 0.0f, 0.0f));
+				if (WH) ah[0] = padd(ah[0], pk(((x0 + ZEN_EPS) <= sig) ? 1.0f : 0.0f, 0.0f));
+			}
+			const float2 a = up(padd(ap[0], ap[1])), h2 = up(padd(ah[0], ah[1]));
+			cp = a.x + a.y;
+			ch = h2.x + h2.y;
+		};
+		if (tid < n_own) {
+			const int k = bin_of(tid);
+			const float H = hmed(k);
+			const float tau = want_p ? thr_ratio_ge(H + ZEN_EPS, P.rule_p) : CUDART_INF_F;
+			const float sig = want_h ? thr_ratio_le(H, P.rule_h) : -1.0f;
+			const float* const E = sm.erow + k;   // taps of bin k: erow[k .. k + L)
+			float cp = 0.0f, ch = 0.0f;
+			if (stamps && tid == 0) stamps[13] = (unsigned long long)clock64() + (unsigned long long)(tau > 1e30f);
+			if (want_p && want_h) count1(std::true_type{}, std::true_type{}, E, tau, sig, cp, ch);
+			else if (want_p) count1(std::true_type{}, std::false_type{}, E, tau, sig, cp, ch);
+			else if (want_h) count1(std::false_type{}, std::true_type{}, E, tau, sig, cp, ch);
+			const unsigned p0 = (want_p && cp >= need) ? 1u : 0u, h0 = (want_h && ch >= need) ? 1u : 0u;
+			codes[k] = p0 * 3u | (h0 * 3u) << 2;
+			if (stamps && tid == 0) stamps[14] = (unsigned long long)clock64() + (unsigned long long)p0;
+		}
+		// the few bins beyond one per thread (2049 bins do not divide by the CTAs' threads): one warp each, a tap per lane
+		for (int e = 0; NT + e < n_own; ++e) {
+			const int wid = tid >> 5, lane = tid & 31;
+			if (wid != NT / 32 - 1 - (e % (NT / 32)))
+				continue;
+			const int k = bin_of(NT + e);
+			const float H = hmed(k);
+			const float tau = want_p ? thr_ratio_ge(H + ZEN_EPS, P.rule_p) : CUDART_INF_F;
+			const float sig = want_h ? thr_ratio_le(H, P.rule_h) : -1.0f;
+			int np = 0, nh = 0;
+			for (int j0 = 0; j0 < L; j0 += 32) {
+				const int j = j0 + lane;
+				const float x = j < L ? sm.erow[k + j] : -1.0f;
+				np += __popc(__ballot_sync(0xffffffffu, j < L && x >= tau));
+				nh += __popc(__ballot_sync(0xffffffffu, j < L && (x + ZEN_EPS) <= sig));
+			}
+			if (lane == 0) {
+				const unsigned p0 = (want_p && (float)np >= need) ? 1u : 0u, h0 = (want_h && (float)nh >= need) ? 1u : 0u;
+				codes[k] = p0 * 3u | (h0 * 3u) << 2;
+			}
 		}
 	}
 	__syncthreads();

@@ -269,7 +269,7 @@ struct zen_hpr {
 	float* rt_out_host[3] = {nullptr, nullptr, nullptr};
 	bool rt_out_all_host = false;    // every non-null destination of the current call is host memory
 	bool rt_stamps = false;          // ZEN_B200_RT_STAMPS=1: the kernel records its phase boundaries (diagnostics)
-	int rt_cluster = 4;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop
+	int rt_cluster = 8;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop (8: p50 10.7 us / p99 11.2 us at hop 1024 against 11.0 / 14.1 with 4, profiles/r02_rt_latency.json)
 	// A process_next_hop without destinations is only SUBMITTED (like the reference's, which queues its kernels and lets
 	// copy_* wait, hps.cu:341-363): its outputs land in the tagged staging buffers and the copy_* that follows unpacks them
 	// on the host - the two-call sequence of zen/fakert.h:229-230 costs one round trip to the device, not two.
@@ -1009,6 +1009,14 @@ int zen_hpr_realtime_stamps(zen_hpr* h, unsigned long long* out16)
 	if (!h || !out16 || !h->rt_ctrl) return ZEN_ERR_ARG;
 	for (int i = 0; i < 16; ++i)
 		out16[i] = h->rt_ctrl->stamps[i];
+	return ZEN_OK;
+}
+// the same for CTA 1 of the cluster (when the hop is split): [9] is the globaltimer at which it saw the command
+int zen_hpr_realtime_stamps_rank1(zen_hpr* h, unsigned long long* out16)
+{
+	if (!h || !out16 || !h->rt_ctrl) return ZEN_ERR_ARG;
+	for (int i = 0; i < 16; ++i)
+		out16[i] = h->rt_ctrl->stamps_r1[i];
 	return ZEN_OK;
 }
 

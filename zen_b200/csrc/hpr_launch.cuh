@@ -78,6 +78,7 @@ struct RtCtrl {
 	volatile unsigned exit_reason; // 1 stop requested, 2 idle time-out
 	unsigned pad1[13];
 	unsigned long long stamps[16]; // RT_F_STAMPS: SM cycle counter at the phase boundaries of the last hop, [9]/[12] globaltimer
+	unsigned long long stamps_r1[16]; // the same as seen by CTA 1 of the cluster ([9]: globaltimer when it saw the command)
 };
 enum { RT_OP_PROCESS = 1, RT_OP_COPY = 2, RT_OP_STOP = 3, RT_OP_EXIT = 4 /* device-internal: idle time-out */, RT_OP_MASK = 0x0f, RT_F_NEW_ARGS = 0x10, RT_F_PUSH_IN = 0x20, RT_F_TAG_OUT = 0x40, RT_F_STAMPS = 0x80 };
 
@@ -628,6 +629,10 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				else
 					asm volatile("" ::: "memory");
 				fill_request(c & 0xffu, seq + 1u);
+				if ((c & RT_F_STAMPS) && rank == 1) {
+					S.stamps[9] = rt_globaltimer();
+					S.stamps[10] = (unsigned long long)clock64();
+				}
 			}
 			__syncthreads();
 		}
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 		const bool tagged = (opw & RT_F_TAG_OUT) != 0;
 		if (op == RT_OP_PROCESS) {
 			const bool pushed = (opw & RT_F_PUSH_IN) != 0;
-			unsigned long long* stamps = ((opw & RT_F_STAMPS) && leader) ? S.stamps : nullptr;
+			unsigned long long* stamps = ((opw & RT_F_STAMPS) && (leader || rank == 1)) ? S.stamps : nullptr;
 			if constexpr (!SPLIT) {
 				hpr_iteration<NFFT, NT, rt_u_for<NFFT>(), true>(P, sm, S.st, iter, S.hopbuf[prev_idx],
 				                                                pushed ? S.hopbuf[prev_idx ^ 1] : S.in, true, false, S.em,
@@ -704,9 +709,9 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 			if (leader && tid == 0)
 				asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&ctrl->seq_out), "r"(seq) : "memory");
 		}
-		if (leader && op == RT_OP_PROCESS && (opw & RT_F_STAMPS)) {
+		if ((leader || rank == 1) && op == RT_OP_PROCESS && (opw & RT_F_STAMPS)) {
 			__syncthreads();
-			if (tid < 16) ctrl->stamps[tid] = S.stamps[tid];  // diagnostics
+			if (tid < 16) (leader ? ctrl->stamps : ctrl->stamps_r1)[tid] = S.stamps[tid];  // diagnostics
 		}
 	}
 
