@@ -183,3 +183,19 @@ def test_cluster_split_owns_every_bin_exactly_once(nfft, cluster):
     assert next_k == M // 2 + 1
     assert np.all(owners == 1)
     assert L.zen_rt_split_ranges(nfft, cluster, cluster, (ctypes.c_int * 6)()) != 0
+
+
+def test_portable_host_path_of_the_tagged_groups():
+    """the host code of the resident session no longer depends on x86 SSE intrinsics - a portable path
+    (GCC vector extensions, one aligned 16-byte access per group) is selected off x86-64, or by -DZEN_PORTABLE_GROUPS.
+    Built here with it forced on and put through the very same format tests as the SSE2 path."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "zen_b200", "csrc"), "portable"])
+    so = os.path.join(root, "tests", "cpp", "_build", "libzen_b200_portable.so")
+    assert os.path.exists(so)
+    env = dict(os.environ, ZEN_B200_LIB=so)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(root, "tests", "test_capi_host.py"), "-k",
+                        "tagged_group_format_round_trip or exports"], capture_output=True, text=True, env=env, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

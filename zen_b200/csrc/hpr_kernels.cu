@@ -8,8 +8,19 @@
 #include <chrono>
 #include <vector>
 
+// The host side of the tagged 16-byte groups (RtCtrl, hpr_launch.cuh) has an SSE2 fast path and a portable one
+// (GCC / clang vector extensions: one aligned 16-byte load / store per group on x86-64 and aarch64 alike);
+// -DZEN_PORTABLE_GROUPS selects the portable one on x86-64 too (tests/test_capi_host.py builds and checks both).
+#if defined(__x86_64__) && !defined(ZEN_PORTABLE_GROUPS)
+#define ZEN_GROUPS_SSE 1
 #include <xmmintrin.h>
 #include <emmintrin.h>
+static inline void zen_host_store_fence() { _mm_sfence(); }
+#else
+#define ZEN_GROUPS_SSE 0
+#include <atomic>
+static inline void zen_host_store_fence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+#endif
 
 #include "hpr_launch.cuh"
 
@@ -406,7 +417,7 @@ int rt_launch(zen_hpr* h)
 	h->rt_ctrl->seq_out = h->rt_seq;
 	h->rt_ctrl->exit_reason = 0;
 	h->rt_ctrl->alive = 1;
-	_mm_sfence();
+	zen_host_store_fence();
 	int rc = ZEN_ERR_UNSUPPORTED;
 	const size_t limit = 227 * 1024;
 	// The hop is split over a thread-block cluster (hpr_split_analyse) for the default real-time path: hard mask decided
@@ -460,6 +471,7 @@ int rt_collect(zen_hpr* h)
 	return ZEN_OK;
 }
 
+#if ZEN_GROUPS_SSE
 // ---- tagged 16-byte groups {x[3g], x[3g+1], x[3g+2], tag ^ zen_group_hash(x)} (RtCtrl, hpr_launch.cuh), host side ----
 inline __m128i rotl32(__m128i v, int n) { return _mm_or_si128(_mm_slli_epi32(v, n), _mm_srli_epi32(v, 32 - n)); }
 
@@ -575,6 +587,110 @@ void rt_publish(zen_hpr* h, unsigned tag, const float* src)
 		for (int g = 0; g < h->rt_groups; ++g)  // no samples: {0, 0, 0, tag} (the hash of zeros is zero)
 			_mm_store_si128(reinterpret_cast<__m128i*>(st + g), _mm_set_epi32((int)tag, 0, 0, 0));
 }
+
+#else  // portable: the same groups, bit for bit, without intrinsics
+typedef unsigned zen_v4u __attribute__((vector_size(16), aligned(16)));
+inline unsigned rotl32s(unsigned v, int n) { return (v << n) | (v >> (32 - n)); }
+inline unsigned fbits(float f)
+{
+	unsigned u;
+	std::memcpy(&u, &f, sizeof(u));
+	return u;
+}
+inline float bitsf(unsigned u)
+{
+	float f;
+	std::memcpy(&f, &u, sizeof(f));
+	return f;
+}
+// one aligned 16-byte store / load (str q / ldr q, movdqa): a group never becomes visible in two pieces
+inline void st16(uint4* dst, unsigned a, unsigned b, unsigned c, unsigned d)
+{
+	const zen_v4u v = {a, b, c, d};
+	*reinterpret_cast<volatile zen_v4u*>(dst) = v;
+}
+inline void ld16(const uint4* src, unsigned (&o)[4])
+{
+	const zen_v4u v = *reinterpret_cast<const volatile zen_v4u*>(src);
+	o[0] = v[0];
+	o[1] = v[1];
+	o[2] = v[2];
+	o[3] = v[3];
+}
+
+void rt_pack_groups(const float* src, int hop, unsigned tag, uint4* st)
+{
+	const int groups = (hop + 2) / 3;
+	const int line_groups = 4 * (hop / 12);
+	int g = 0;
+	for (; g < line_groups; g += 4) {
+		unsigned y[12], V[4];
+		for (int l = 0; l < 12; ++l)
+			y[l] = fbits(src[3 * g + l]);
+		for (int l = 0; l < 4; ++l)
+			V[l] = y[l] ^ rotl32s(y[4 + l], 11) ^ rotl32s(y[8 + l], 22);  // zen_group_key's line hash
+		for (int q = 0; q < 4; ++q)
+			st16(st + g + q, y[3 * q], y[3 * q + 1], y[3 * q + 2], tag ^ V[q]);
+	}
+	for (; g < groups; ++g) {
+		const unsigned x0 = fbits(src[3 * g]), x1 = 3 * g + 1 < hop ? fbits(src[3 * g + 1]) : 0u, x2 = 3 * g + 2 < hop ? fbits(src[3 * g + 2]) : 0u;
+		st16(st + g, x0, x1, x2, tag ^ zen_group_hash(x0, x1, x2));
+	}
+}
+
+bool rt_unpack_groups(const uint4* st, int hop, unsigned tag, float* dst, int& g)
+{
+	const int groups = (hop + 2) / 3;
+	const int line_groups = 4 * (hop / 12);
+	for (; g < line_groups; g += 4) {
+		unsigned y[12], w[4], v[4];
+		for (int q = 0; q < 4; ++q) {
+			ld16(st + g + q, v);
+			y[3 * q] = v[0];
+			y[3 * q + 1] = v[1];
+			y[3 * q + 2] = v[2];
+			w[q] = v[3];
+		}
+		for (int l = 0; l < 4; ++l)
+			if ((w[l] ^ y[l] ^ rotl32s(y[4 + l], 11) ^ rotl32s(y[8 + l], 22)) != tag)
+				return false;  // the line is taken as a whole or not at all
+		for (int l = 0; l < 12; ++l)
+			dst[3 * g + l] = bitsf(y[l]);
+	}
+	for (; g < groups; ++g) {
+		unsigned v[4];
+		ld16(st + g, v);
+		if ((v[3] ^ zen_group_hash(v[0], v[1], v[2])) != tag)
+			return false;
+		for (int j = 0; j < 3 && 3 * g + j < hop; ++j)
+			dst[3 * g + j] = bitsf(v[j]);
+	}
+	return true;
+}
+
+bool rt_last_group_ready(const uint4* st, int hop, unsigned tag)
+{
+	const int groups = (hop + 2) / 3, line_groups = 4 * (hop / 12);
+	if (groups > line_groups) {
+		unsigned v[4];
+		ld16(st + groups - 1, v);
+		return (v[3] ^ zen_group_hash(v[0], v[1], v[2])) == tag;
+	}
+	float scratch[12];
+	int g0 = 0;
+	return rt_unpack_groups(st + groups - 4, 12, tag, scratch, g0);
+}
+
+void rt_publish(zen_hpr* h, unsigned tag, const float* src)
+{
+	uint4* st = h->rt_stage_in;
+	if (src)
+		rt_pack_groups(src, h->hop, tag, st);
+	else
+		for (int g = 0; g < h->rt_groups; ++g)  // no samples: {0, 0, 0, tag} (the hash of zeros is zero)
+			st16(st + g, 0u, 0u, 0u, tag);
+}
+#endif
 
 bool rt_unpack(const zen_hpr* h, int o, unsigned tag, float* dst, int& g)
 {
@@ -734,7 +850,7 @@ int rt_call(zen_hpr* h, unsigned op, const float* in, float* o0, float* o1, floa
 	std::chrono::steady_clock::time_point tr0, tr1, tr2;
 	if (h->rt_trace) tr0 = std::chrono::steady_clock::now();
 	c->op = opw;
-	_mm_sfence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
+	zen_host_store_fence();  // a pulled hop may sit in write-combined memory: drain it (and the arguments) before the tags
 	rt_publish(h, tag, push_src);
 	if (h->rt_trace) tr2 = tr1 = std::chrono::steady_clock::now();
 	if (defer) {
