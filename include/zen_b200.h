@@ -247,6 +247,15 @@ int zen_offline_process_device(float fs, int hop_h, int hop_p, float beta_h, flo
                                const float* d_audio, long n, float* d_harmonic, float* d_percussive,
                                float* d_residual, void* cuda_stream);
 
+/* ---- downstream consumer: McLeod pitch on the harmonic output (demos/pitch-tracking/pitch.cpp:40-135) ----
+ * MPM(audio_buffer_size, sample_rate).pitch(buffer), batched and on the device: d_audio holds n_buffers buffers of n
+ * samples (n = 256 ... 4096, a power of two; buffer b starts at d_audio + b * stride), e.g. the harmonic hops of
+ * zen_hpr_batch_process / zen_hpr_copy_harmonic where the kernels left them (the reference's demo takes them through
+ * io.host_out, main.cu:90-107).  d_pitch[b] = pitch in Hz, or -1 as the reference returns it; d_nsdf (optional,
+ * n_buffers * n floats) receives real_autocorrelation's output. */
+int zen_mpm_pitch(int n, float sample_rate, const float* d_audio, long stride, int n_buffers, float* d_pitch, float* d_nsdf,
+                  void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -591,3 +591,122 @@ long zo_fakert_n_chunks(long size, long hop)
 			++cnt;
 	return cnt;
 }
+
+/* ------------------------------------------------------ downstream: pitch ---
+ * McLeod pitch method as the reference's pitch-tracking demo runs it on the harmonic output of HPRRealtime<GPU>
+ * (demos/pitch-tracking/pitch.cpp:40-135, pitch_detection.h:17-93, main.cu:90-107).  Restated as written, quirks
+ * included: the power spectrum is only formed for the first N of the 2N bins (pitch.cpp:50-52), the autocorrelation is
+ * not normalised into an NSDF, a missing estimate above the cut-off leaves period = 0 (pitch = +inf). */
+static void mpm_parabolic(const float* a, int n, int x_, float* ox, float* oy)
+{
+	/* pitch.cpp:16-38 */
+	float x = (float)x_;
+	int xa;
+	if (x < 1) {
+		xa = (a[x_] <= a[x_ + 1]) ? x_ : x_ + 1;
+	}
+	else if (x > (float)(n - 1)) {
+		xa = (a[x_] <= a[x_ - 1]) ? x_ : x_ - 1;
+	}
+	else {
+		float den = a[x_ + 1] + a[x_ - 1] - 2 * a[x_];
+		float delta = a[x_ - 1] - a[x_ + 1];
+		if (!den) {
+			*ox = x;
+			*oy = a[x_];
+		}
+		else {
+			*ox = x + delta / (2 * den);
+			*oy = a[x_] - delta * delta / (8 * den);
+		}
+		return;
+	}
+	*ox = (float)xa;
+	*oy = a[xa];
+}
+
+/* audio: n samples; nsdf_out (optional): n floats receiving real_autocorrelation's output.  Returns MPM::pitch. */
+float zo_mpm_pitch(const float* audio, int n, float sample_rate, float* nsdf_out)
+{
+	const int n2 = 2 * n;
+	float* z = (float*)calloc((size_t)2 * n2, sizeof(float)); /* out_im, interleaved, zero beyond n (pitch.cpp:42-45, clear()) */
+	float* r = (float*)malloc(sizeof(float) * (size_t)n);
+	for (int i = 0; i < n; ++i)
+		z[2 * i] = audio[i];
+	zo_fft(n2, z, 0); /* pitch.cpp:47-48 */
+	{
+		/* pitch.cpp:50-52: out_im[i] *= conj(out_im[i]) * scale for i < N only; complex products as (ac - bd, ad + bc) */
+		const float sr = 1.0f / (float)(n * 2), si = 0.0f;
+		for (int i = 0; i < n; ++i) {
+			const float a = z[2 * i], b = z[2 * i + 1];
+			const float cr = a * sr - (-b) * si, ci = a * si + (-b) * sr; /* conj(x) * scale */
+			z[2 * i] = a * cr - b * ci;
+			z[2 * i + 1] = a * ci + b * cr;
+		}
+	}
+	zo_fft(n2, z, 1); /* pitch.cpp:54-55 */
+	for (int i = 0; i < n; ++i)
+		r[i] = z[2 * i]; /* pitch.cpp:57-60 */
+	if (nsdf_out)
+		memcpy(nsdf_out, r, sizeof(float) * (size_t)n);
+	/* peak_picking, pitch.cpp:63-99 */
+	int* maxpos = (int*)malloc(sizeof(int) * (size_t)(n / 2 + 2));
+	int n_max = 0, pos = 0, cur = 0;
+	const long size = n;
+	while (pos < (size - 1) / 3 && r[pos] > 0)
+		pos++;
+	while (pos < size - 1 && r[pos] <= 0.0)
+		pos++;
+	if (pos == 0)
+		pos = 1;
+	while (pos < size - 1) {
+		if (r[pos] > r[pos - 1] && r[pos] >= r[pos + 1] && (cur == 0 || r[pos] > r[cur]))
+			cur = pos;
+		pos++;
+		if (pos < size - 1 && r[pos] <= 0) {
+			if (cur > 0) {
+				maxpos[n_max++] = cur;
+				cur = 0;
+			}
+			while (pos < size - 1 && r[pos] <= 0.0)
+				pos++;
+		}
+	}
+	if (cur > 0)
+		maxpos[n_max++] = cur;
+	/* MPM::pitch, pitch.cpp:101-135 */
+	float highest = -INFINITY; /* (float)-DBL_MAX */
+	float* ex = (float*)malloc(sizeof(float) * (size_t)(n_max + 1));
+	float* ey = (float*)malloc(sizeof(float) * (size_t)(n_max + 1));
+	int n_est = 0;
+	for (int m = 0; m < n_max; ++m) {
+		const int i = maxpos[m];
+		highest = r[i] > highest ? r[i] : highest;
+		if (r[i] > 0.5) {
+			mpm_parabolic(r, n, i, &ex[n_est], &ey[n_est]);
+			highest = ey[n_est] > highest ? ey[n_est] : highest;
+			n_est++;
+		}
+	}
+	float result;
+	if (n_est == 0) {
+		result = -1.0f;
+	}
+	else {
+		const float cutoff = (float)(0.93 * (double)highest);
+		float period = 0;
+		for (int m = 0; m < n_est; ++m)
+			if (ey[m] >= cutoff) {
+				period = ex[m];
+				break;
+			}
+		const float est = sample_rate / period;
+		result = (est > 80.0) ? est : -1.0f;
+	}
+	free(z);
+	free(r);
+	free(maxpos);
+	free(ex);
+	free(ey);
+	return result;
+}

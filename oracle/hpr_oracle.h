@@ -71,6 +71,10 @@ int zo_offline_process(int geom, float fs, int hop_h, int hop_p, float beta_h, f
                        int nocopybord, int flags, const float* audio, long n,
                        float* h_out, float* p_out, float* r_out);
 
+/* demos/pitch-tracking/pitch.cpp:40-135 MPM::pitch (the consumer of the harmonic output, main.cu:90-107): n samples in,
+ * pitch in Hz or -1; nsdf_out (optional, n floats) receives real_autocorrelation's output */
+float zo_mpm_pitch(const float* audio, int n, float sample_rate, float* nsdf_out);
+
 /* zen/fakert.h:15-34 get_chunk_limits: number of hops fakert processes */
 long zo_fakert_n_chunks(long size, long hop);
 

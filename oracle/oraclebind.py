@@ -56,6 +56,8 @@ def lib():
         L.zo_hpr_get.argtypes = [vp, ci, vp]
         L.zo_hpr_run.argtypes = [vp, vp, ci, vp, vp, vp]
         L.zo_offline_process.argtypes = [ci, cf, ci, ci, cf, cf, ci, ci, vp, cl, vp, vp, vp]
+        L.zo_mpm_pitch.argtypes = [vp, ci, cf, vp]
+        L.zo_mpm_pitch.restype = cf
         L.zo_fakert_n_chunks.argtypes = [cl, cl]
         L.zo_fakert_n_chunks.restype = cl
         _lib = L
@@ -172,3 +174,11 @@ def offline_process(geom, fs, hop_h, hop_p, beta_h, beta_p, audio, nocopybord=Fa
 
 def fakert_n_chunks(size, hop):
     return int(lib().zo_fakert_n_chunks(size, hop))
+
+
+def mpm_pitch(audio, sample_rate, want_nsdf=False):
+    """demos/pitch-tracking/pitch.cpp MPM::pitch on one buffer: pitch in Hz or -1 (and the autocorrelation it picked from)"""
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    nsdf = np.zeros(a.size, dtype=np.float32) if want_nsdf else None
+    p = float(lib().zo_mpm_pitch(_p(a), a.size, sample_rate, _p(nsdf)))
+    return (p, nsdf) if want_nsdf else p

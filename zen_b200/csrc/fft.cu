@@ -159,6 +159,17 @@ int launch_fft_large(float2* d, int inverse, cudaStream_t s)
 
 }  // namespace
 
+// per-stage twiddle table of the n-point transform (device pointer, cached per device), for other translation units
+namespace zen_b200 {
+const float2* fft_twiddle_table(int n)
+{
+	int order = 0;
+	while ((1 << order) < n)
+		++order;
+	return g_tw.get(n, order);
+}
+}  // namespace zen_b200
+
 extern "C" int zen_fft_c2c(int nfft, float* d_inout, int inverse, void* cuda_stream)
 {
 	if (!d_inout || nfft < 2)

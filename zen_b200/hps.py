@@ -446,3 +446,29 @@ def pcm16_encode_normalized(x):
     check(_lib.lib().zen_pcm16_encode_normalized(x.data_ptr(), in_stride, x.shape[0], x.shape[1], out.data_ptr(), max(1, out.stride(0)),
                                                  peaks.data_ptr()), "zen_pcm16_encode_normalized")
     return out, peaks
+
+
+class MPM:
+    """McLeod pitch method of the reference's pitch-tracking demo (demos/pitch-tracking/pitch_detection.h:17-93,
+    pitch.cpp:101-135), batched on the device: pitch(x) takes a float32 CUDA tensor [n_buffers, N] (or [N]) - e.g. the
+    harmonic output of HPRBatch reshaped to hops - and returns the pitch of every buffer in Hz (-1 where the reference
+    returns -1)."""
+
+    def __init__(self, audio_buffer_size, sample_rate):
+        if audio_buffer_size == 0:
+            raise MemoryError("std::bad_alloc")          # pitch_detection.h:48-50
+        self.N, self.sample_rate = int(audio_buffer_size), float(sample_rate)
+
+    def pitch(self, x, want_nsdf=False):
+        torch = _torch()
+        one = x.dim() == 1
+        x2 = x.reshape(1, -1) if one else x
+        assert x2.is_cuda and x2.dtype == torch.float32 and x2.shape[1] == self.N and (self.N == 1 or x2.stride(1) == 1)
+        nb = x2.shape[0]
+        out = torch.empty(nb, dtype=torch.float32, device=x.device)
+        nsdf = torch.empty((nb, self.N), dtype=torch.float32, device=x.device) if want_nsdf else None
+        stride = x2.stride(0) if nb > 1 else self.N
+        check(_lib.lib().zen_mpm_pitch(self.N, self.sample_rate, x2.data_ptr(), stride, nb, out.data_ptr(),
+                                       nsdf.data_ptr() if want_nsdf else None, torch.cuda.current_stream().cuda_stream), "zen_mpm_pitch")
+        res = out[0] if one else out
+        return (res, nsdf[0] if one else nsdf) if want_nsdf else res
