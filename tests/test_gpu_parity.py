@@ -123,6 +123,43 @@ def test_box_vs_npp(torch, zen):
     assert n >= 50
 
 
+@pytest.mark.parametrize("T,F,L,dr", [(12, 4100, 46, 2), (6, 2049, 7, 2), (40, 300, 11, 0), (40, 300, 12, 1), (9, 5000, 3, 2), (30, 64, 23, 0),
+                                      (5, 9000, 187, 2)])
+def test_box_vs_oracle_with_inf(torch, zen, oracle, T, F, L, dr):
+    """BoxFilterGPU (wrap-padded moving average, box.h:194-213) against the oracle's NPP-geometry restatement, on
+    reciprocal-of-power data with zeros in it, i.e. +inf inputs (hps.cu:591-592): an inf inside the window gives inf,
+    one that has left it leaves no NaN behind (the kernels never subtract)"""
+    rng = np.random.default_rng(T * F + L)
+    mag = np.abs(rng.standard_normal((T, F))).astype(np.float32)
+    mag[rng.random((T, F)) < 0.02] = 0.0
+    with np.errstate(divide="ignore"):
+        src = (np.float32(1.0) / (mag * mag)).astype(np.float32)
+    ref = oracle.box_filter(oracle.GEOM_GPU, src, L, dr)
+    dst = torch.zeros((T, F), dtype=torch.float32, device="cuda")
+    zen.BoxFilterGPU(T, F, L, dr).filter(torch.from_numpy(src).cuda(), dst)
+    got = dst.cpu().numpy()
+    assert not np.isnan(got).any()
+    assert np.array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    assert np.all(np.abs(got[fin] - ref[fin]) <= 4e-6 * np.abs(ref[fin]) + 1e-30)
+
+
+def test_filters_on_tall_matrices(torch, zen, oracle):
+    """more than 65535 rows (rows used to be grid.y)"""
+    T, F = 70001, 24
+    rng = np.random.default_rng(3)
+    src = np.abs(rng.standard_normal((T, F))).astype(np.float32)
+    d = torch.from_numpy(src).cuda()
+    for L, dr in ((3, 2), (5, 0)):
+        dst = torch.zeros((T, F), dtype=torch.float32, device="cuda")
+        zen.MedianFilterGPU(T, F, L, dr, True).filter(d, dst)
+        assert np.array_equal(dst.cpu().numpy(), oracle.median_filter(oracle.GEOM_GPU, src, L, dr, True))
+        dst.zero_()
+        zen.BoxFilterGPU(T, F, L, dr).filter(d, dst)
+        ref = oracle.box_filter(oracle.GEOM_GPU, src, L, dr)
+        assert np.all(np.abs(dst.cpu().numpy() - ref) <= 4e-6 * np.abs(ref))
+
+
 # --------------------------------------------------------------------- fft ---
 
 @pytest.mark.parametrize("n", [64, 1024, 4096])

@@ -176,6 +176,14 @@ extern "C" int zen_fft_c2c(int nfft, float* d_inout, int inverse, void* cuda_str
 		return ZEN_ERR_ARG;
 	if (!is_pow2(nfft) || nfft > 65536)
 		return ZEN_ERR_UNSUPPORTED;
+	// From 8192 points on the transform is spread over many CTAs (four-step: N1 column FFTs, twiddle, N2 row FFTs through
+	// a scratch buffer): one CTA running all of it is bound by its own stage-to-stage latency (measured on a B200,
+	// forward + backward: 8192 points 20.6 us in one CTA against cuFFT's 20.3, 16384 points 28.7 against 23.6, while the
+	// four-step 32768-point transform takes 16.4 us; profiles/r02_fft_bench_vs_cufft.json).
+	if (nfft == 8192)
+		return launch_fft_large<64, 128>(reinterpret_cast<float2*>(d_inout), inverse, (cudaStream_t)cuda_stream);
+	if (nfft == 16384)
+		return launch_fft_large<128, 128>(reinterpret_cast<float2*>(d_inout), inverse, (cudaStream_t)cuda_stream);
 	if (nfft == 32768)
 		return launch_fft_large<128, 256>(reinterpret_cast<float2*>(d_inout), inverse, (cudaStream_t)cuda_stream);
 	if (nfft == 65536)

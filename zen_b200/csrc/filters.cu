@@ -26,6 +26,14 @@ struct AxisGeom {
 	int L;
 };
 
+// rows (or outputs) beyond the 65535 limit of grid.y fold into grid.z: rows_grid(n) launches, grid_row() reads back
+__device__ __forceinline__ long grid_row() { return (long)blockIdx.y + (long)blockIdx.z * gridDim.y; }
+static inline dim3 rows_grid(unsigned gx, long n)
+{
+	const unsigned gy = (unsigned)(n < 32768 ? (n < 1 ? 1 : n) : 32768);
+	return dim3(gx, gy, (unsigned)((n + gy - 1) / gy));
+}
+
 __device__ __forceinline__ int wrap_idx(int i, int dim)
 {
 	i %= dim;
@@ -69,7 +77,9 @@ __global__ void __launch_bounds__(SM_NT) median_run_freq_kernel(const float* __r
 	constexpr int CHUNK = SM_NT * RUN_F;
 	float* E = run_smem;                    // CHUNK + L - 1
 	float* O = run_smem + CHUNK + g.L + 3;  // CHUNK
-	const int r = blockIdx.y;
+	const long r = grid_row();
+	if (r >= g.T)
+		return;
 	const int q0 = blockIdx.x * CHUNK;
 	const int nq = min(CHUNK, g.n_out - q0);
 	const float* row = src + (size_t)r * g.F;
@@ -93,8 +103,8 @@ __global__ void __launch_bounds__(256) copy_axis_kernel(const float* __restrict_
 {
 	// L == 1: the median of one tap is the tap
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	const int r = blockIdx.y;
-	if (c >= g.F)
+	const long r = grid_row();
+	if (c >= g.F || r >= g.T)
 		return;
 	if (g.axis == 1) {
 		if (c < g.first || c >= g.first + g.n_out)
@@ -123,7 +133,9 @@ __global__ void __launch_bounds__(SL_NT) median_slide_freq_kernel(const float* _
 	extern __shared__ unsigned sl_smem[];
 	unsigned* E = sl_smem;                       // SL_CHUNK + L - 1
 	unsigned* O = sl_smem + SL_CHUNK + g.L + 3;  // SL_CHUNK
-	const int r = blockIdx.y;
+	const long r = grid_row();
+	if (r >= g.T)
+		return;
 	const int q0 = blockIdx.x * SL_CHUNK;
 	const int nq = min(SL_CHUNK, g.n_out - q0);
 	const float* row = src + (size_t)r * g.F;
@@ -147,11 +159,11 @@ __global__ void __launch_bounds__(SL_NT) median_slide_freq_kernel(const float* _
 __global__ void __launch_bounds__(256) median_generic_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
 {
 	const int other = blockIdx.x * blockDim.x + threadIdx.x;  // index along the non-filtered axis
-	const int q = blockIdx.y;
+	const long q = grid_row();
 	const int n_other = g.axis == 0 ? g.F : g.T;
-	if (other >= n_other)
+	if (other >= n_other || q >= g.n_out)
 		return;
-	const int a = g.first + q;
+	const int a = g.first + (int)q;
 	const int dim = g.axis == 0 ? g.T : g.F;
 	auto get = [&](int t) -> float {
 		int i = a + g.tap_off + t;
@@ -166,22 +178,101 @@ __global__ void __launch_bounds__(256) median_generic_kernel(const float* __rest
 }
 
 // ---- box filter: wrap-padded moving average (box.h:194-213) ----
-__global__ void __launch_bounds__(256) box_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+// A sliding sum that NEVER subtracts: the SSE path feeds it 1 / |X|^2, which is +inf on silent bins (hps.cu:591-592),
+// and "add the tap that enters, subtract the one that leaves" would turn inf - inf into NaN for the rest of the row.
+//
+// Frequency axis: a CTA stages one row segment (+ L - 1 taps of halo, wrap by index arithmetic) in shared memory and
+// cuts it into blocks of L taps.  P[p] = sum of the block's taps up to p, S[p] = sum from p to the block's end (one
+// thread per block, 2 L additions); a window of L taps covers the tail of one block and the head of the next, so
+// out[q] = S[q] + P[q + L - 1] (or P alone when the window is a whole block): about three additions per output
+// whatever L is, every tap read from HBM once.  An inf inside the window makes the sum inf, one outside cannot touch it.
+constexpr int BOX_CHUNK = 2048;
+constexpr int BOX_NT = 256;
+
+__global__ void __launch_bounds__(BOX_NT) box_freq_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+{
+	extern __shared__ float box_smem[];
+	const int L = g.L;
+	const int n_in = BOX_CHUNK + L - 1;
+	float* E = box_smem;                         // n_in
+	float* P = E + ((n_in + 3) & ~3);            // n_in
+	float* S = P + ((n_in + 3) & ~3);            // n_in
+	const long r = grid_row();
+	if (r >= g.T)
+		return;
+	const int q0 = blockIdx.x * BOX_CHUNK;
+	const int nq = min(BOX_CHUNK, g.F - q0);
+	const int n_used = nq + L - 1;
+	const float* row = src + (size_t)r * g.F;
+	for (int t = threadIdx.x; t < n_used; t += BOX_NT)
+		E[t] = __ldg(row + wrap_idx(q0 + g.tap_off + t, g.F));
+	__syncthreads();
+	const int n_blocks = (n_used + L - 1) / L;
+	for (int b = threadIdx.x; b < n_blocks; b += BOX_NT) {
+		const int lo = b * L, hi = min(n_used, lo + L);
+		float acc = 0.0f;
+		for (int p = lo; p < hi; ++p) {
+			acc += E[p];
+			P[p] = acc;
+		}
+		acc = 0.0f;
+		for (int p = hi - 1; p >= lo; --p) {
+			acc += E[p];
+			S[p] = acc;
+		}
+	}
+	__syncthreads();
+	const float inv = (float)L;
+	for (int q = threadIdx.x; q < nq; q += BOX_NT) {
+		const int o = q % L;
+		const float sum = o == 0 ? P[q + L - 1] : S[q] + P[q + L - 1];
+		dst[(size_t)r * g.F + q0 + q] = sum / inv;
+	}
+}
+
+// Time axis: a thread owns one column and walks down a strip of rows with the last L taps in registers (L <= 15): one
+// load per output, the window re-summed every step (no subtraction, see above).  Longer windows read their L taps.
+template <int C>
+__global__ void __launch_bounds__(256) box_time_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g, int run_t)
 {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	const int r = blockIdx.y;
+	const int r0 = blockIdx.y * run_t;
 	if (c >= g.F)
 		return;
+	const int r1 = min(g.T, r0 + run_t);
+	const int L = g.L;
+	float w[C];
+#pragma unroll
+	for (int t = 0; t < C; ++t)
+		w[t] = 0.0f;
+	// taps of output r: rows r + tap_off + t, t < L; w[C - L .. C) holds them, oldest first
+#pragma unroll
+	for (int t = 0; t < C - 1; ++t) {
+		const int tt = t - (C - L);   // tap index of slot t for the first output, minus the one loaded in the loop
+		w[t + 1] = tt >= 0 && tt < L - 1 ? __ldg(src + (size_t)wrap_idx(r0 + g.tap_off + tt, g.T) * g.F + c) : 0.0f;
+	}
+	for (int r = r0; r < r1; ++r) {
+#pragma unroll
+		for (int t = 0; t < C - 1; ++t)
+			w[t] = w[t + 1];
+		w[C - 1] = __ldg(src + (size_t)wrap_idx(r + g.tap_off + L - 1, g.T) * g.F + c);
+		float acc = 0.0f;
+#pragma unroll
+		for (int t = 0; t < C; ++t)
+			if (t >= C - L) acc += w[t];
+		dst[(size_t)r * g.F + c] = acc / (float)L;
+	}
+}
+
+__global__ void __launch_bounds__(256) box_time_direct_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	const long r = grid_row();
+	if (c >= g.F || r >= g.T)
+		return;
 	float acc = 0.0f;
-	if (g.axis == 1) {
-		const float* row = src + (size_t)r * g.F;
-		for (int t = 0; t < g.L; ++t)
-			acc += __ldg(row + wrap_idx(c + g.tap_off + t, g.F));
-	}
-	else {
-		for (int t = 0; t < g.L; ++t)
-			acc += __ldg(src + (size_t)wrap_idx(r + g.tap_off + t, g.T) * g.F + c);
-	}
+	for (int t = 0; t < g.L; ++t)
+		acc += __ldg(src + (size_t)wrap_idx((int)r + g.tap_off + t, g.T) * g.F + c);
 	dst[(size_t)r * g.F + c] = acc / (float)g.L;
 }
 
@@ -218,7 +309,7 @@ void launch_run(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
 {
 	if (g.axis == 1) {
 		constexpr int CHUNK = SM_NT * RUN_F;
-		dim3 grid((g.n_out + CHUNK - 1) / CHUNK, g.T);
+		dim3 grid = rows_grid((g.n_out + CHUNK - 1) / CHUNK, g.T);
 		size_t smem = sizeof(float) * (size_t)(2 * CHUNK + g.L + 8);
 		median_run_freq_kernel<C><<<grid, SM_NT, smem, s>>>(src, dst, g);
 	}
@@ -228,6 +319,8 @@ void launch_run(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
 		int run_t = 64;
 		while (run_t > 8 && (long)col_blocks * ((g.n_out + run_t - 1) / run_t) < 600)
 			run_t >>= 1;
+		if ((g.n_out + run_t - 1) / run_t > 65535)
+			run_t = (g.n_out + 65534) / 65535;
 		dim3 grid(col_blocks, (g.n_out + run_t - 1) / run_t);
 		median_run_time_kernel<C><<<grid, 256, 0, s>>>(src, dst, g, run_t);
 	}
@@ -250,7 +343,7 @@ int zen_median_filter(int time, int freq, int filter_len, int direction, int cop
 		return ZEN_OK;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
 	if (g.L == 1) {
-		dim3 grid((g.F + 255) / 256, g.T);
+		dim3 grid = rows_grid((g.F + 255) / 256, g.T);
 		copy_axis_kernel<<<grid, 256, 0, s>>>(d_src, d_dst, g);
 	}
 	else if (g.L <= 47) {
@@ -271,13 +364,13 @@ int zen_median_filter(int time, int freq, int filter_len, int direction, int cop
 	else {
 		const int K = g.axis == 1 ? sliding_K_for(g.L) : 0;
 		if (K > 0) {
-			dim3 grid((g.n_out + SL_CHUNK - 1) / SL_CHUNK, g.T);
+			dim3 grid = rows_grid((g.n_out + SL_CHUNK - 1) / SL_CHUNK, g.T);
 			size_t smem = sizeof(unsigned) * (size_t)(2 * SL_CHUNK + g.L + 8);
 			median_slide_freq_kernel<<<grid, SL_NT, smem, s>>>(d_src, d_dst, g, K);
 		}
 		else {
 			const int n_other = g.axis == 0 ? g.F : g.T;
-			dim3 grid((n_other + 255) / 256, g.n_out);
+			dim3 grid = rows_grid((n_other + 255) / 256, g.n_out);
 			median_generic_kernel<<<grid, 256, 0, s>>>(d_src, d_dst, g);
 		}
 	}
@@ -293,8 +386,30 @@ int zen_box_filter(int time, int freq, int filter_len, int direction, const floa
 	int rc = make_geom(g, time, freq, filter_len, direction, 1);  // BoxFilterGPU always wrap-pads
 	if (rc != ZEN_OK)
 		return rc;
-	dim3 grid((freq + 255) / 256, time);
-	box_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_src, d_dst, g);
+	cudaStream_t s = (cudaStream_t)cuda_stream;
+	if (g.axis == 1) {
+		const size_t smem = sizeof(float) * 3 * (size_t)((BOX_CHUNK + g.L - 1 + 3) & ~3);
+		if (smem > 200 * 1024)
+			return ZEN_ERR_UNSUPPORTED;
+		ZEN_CUDA_CHECK(cudaFuncSetAttribute(box_freq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		dim3 grid = rows_grid((freq + BOX_CHUNK - 1) / BOX_CHUNK, time);
+		box_freq_kernel<<<grid, BOX_NT, smem, s>>>(d_src, d_dst, g);
+	}
+	else if (g.L <= 15) {
+		const int col_blocks = (freq + 255) / 256;
+		int run_t = 64;
+		while (run_t > 8 && (long)col_blocks * ((time + run_t - 1) / run_t) < 600)
+			run_t >>= 1;
+		if ((time + run_t - 1) / run_t > 65535)
+			run_t = (time + 65534) / 65535;
+		dim3 grid(col_blocks, (time + run_t - 1) / run_t);
+		if (g.L <= 7) box_time_kernel<8><<<grid, 256, 0, s>>>(d_src, d_dst, g, run_t);
+		else box_time_kernel<16><<<grid, 256, 0, s>>>(d_src, d_dst, g, run_t);
+	}
+	else {
+		dim3 grid = rows_grid((freq + 255) / 256, time);
+		box_time_direct_kernel<<<grid, 256, 0, s>>>(d_src, d_dst, g);
+	}
 	ZEN_CUDA_CHECK(cudaGetLastError());
 	return ZEN_OK;
 }

@@ -38,9 +38,17 @@ template <int CH, bool VEC>
 __global__ void __launch_bounds__(256) pcm16_decode_kernel(const int16_t* __restrict__ pcm, long pcm_stride, float* __restrict__ out,
                                                           long out_stride, long n_frames, long items_per_row, long total_items)
 {
-	for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < total_items; it += (long)gridDim.x * blockDim.x) {
-		const long row = it / items_per_row;
-		const long i0 = (it - row * items_per_row) * 8;
+	// work unit = (row, chunk of 256 items): one division per CTA and unit, not per thread and item
+	const long chunks_per_row = (items_per_row + 255) / 256;
+	long row = blockIdx.x / chunks_per_row, chunk = blockIdx.x - row * chunks_per_row;   // one division per CTA, then counters
+	for (long unit = blockIdx.x; unit < total_items; unit += gridDim.x, chunk += gridDim.x) {
+		while (chunk >= chunks_per_row) {
+			chunk -= chunks_per_row;
+			++row;
+		}
+		const long item = chunk * 256 + threadIdx.x;
+		if (item >= items_per_row) continue;
+		const long i0 = item * 8;
 		const int16_t* src = pcm + (size_t)row * pcm_stride + (size_t)i0 * CH;
 		float* dst = out + (size_t)row * out_stride + i0;
 		if (VEC && i0 + 8 <= n_frames) {
@@ -72,19 +80,24 @@ __global__ void __launch_bounds__(256) pcm16_decode_kernel(const int16_t* __rest
 }
 
 // max(-min, max) of a row == max |x| ; non-negative floats order like their bit patterns.
-// One work item = 8 consecutive samples; a warp's 32 items never straddle more than two rows, so the warp
-// reduces per row segment before its atomics.
+// One work item = 8 consecutive samples, one work unit = 256 items of ONE row: the CTA reduces per warp.
 template <bool VEC>
 __global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ in, long in_stride, long n, long items_per_row,
                                                   long total_items, unsigned* __restrict__ peak_bits)
 {
-	for (long it0 = (long)blockIdx.x * blockDim.x; it0 < total_items; it0 += (long)gridDim.x * blockDim.x) {
-		const long it = it0 + threadIdx.x;
+	const long chunks_per_row = (items_per_row + 255) / 256;
+	long urow = blockIdx.x / chunks_per_row, chunk = blockIdx.x - urow * chunks_per_row;
+	for (long unit = blockIdx.x; unit < total_items; unit += gridDim.x, chunk += gridDim.x) {
+		while (chunk >= chunks_per_row) {
+			chunk -= chunks_per_row;
+			++urow;
+		}
+		const long item = chunk * 256 + threadIdx.x;
 		float m = 0.0f;
 		long row = -1;
-		if (it < total_items) {
-			row = it / items_per_row;
-			const long i0 = (it - row * items_per_row) * 8;
+		if (item < items_per_row) {
+			row = urow;
+			const long i0 = item * 8;
 			const float* src = in + (size_t)row * in_stride + i0;
 			if (VEC && i0 + 8 <= n) {
 				const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
@@ -96,17 +109,10 @@ __global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ in,
 					m = fmaxf(m, fabsf(src[i]));
 			}
 		}
-		// segmented warp reduction: lanes of the same row combine
-		const long row0 = __shfl_sync(0xffffffffu, row, 0);
-		const bool uniform = __all_sync(0xffffffffu, row == row0);
-		if (uniform) {
-			for (int s = 16; s > 0; s >>= 1)
-				m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-			if ((threadIdx.x & 31) == 0 && row >= 0 && m > 0.0f) atomicMax(peak_bits + row, __float_as_uint(m));
-		}
-		else if (row >= 0 && m > 0.0f) {
-			atomicMax(peak_bits + row, __float_as_uint(m));
-		}
+		// the whole CTA works on one row: warp reduction, one atomic per warp
+		for (int s = 16; s > 0; s >>= 1)
+			m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+		if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(peak_bits + urow, __float_as_uint(m));
 	}
 }
 
@@ -123,9 +129,16 @@ __global__ void __launch_bounds__(256) pcm16_encode_kernel(const float* __restri
                                                           const unsigned* __restrict__ peak_bits, int16_t* __restrict__ out,
                                                           long out_stride, long items_per_row, long total_items)
 {
-	for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < total_items; it += (long)gridDim.x * blockDim.x) {
-		const long row = it / items_per_row;
-		const long i0 = (it - row * items_per_row) * 8;
+	const long chunks_per_row = (items_per_row + 255) / 256;
+	long row = blockIdx.x / chunks_per_row, chunk = blockIdx.x - row * chunks_per_row;
+	for (long unit = blockIdx.x; unit < total_items; unit += gridDim.x, chunk += gridDim.x) {
+		while (chunk >= chunks_per_row) {
+			chunk -= chunks_per_row;
+			++row;
+		}
+		const long item = chunk * 256 + threadIdx.x;
+		if (item >= items_per_row) continue;
+		const long i0 = item * 8;
 		const float* src = in + (size_t)row * in_stride + i0;
 		int16_t* dst = out + (size_t)row * out_stride + i0;
 		const float peak = __uint_as_float(__ldg(peak_bits + row));
@@ -145,13 +158,14 @@ __global__ void __launch_bounds__(256) pcm16_encode_kernel(const float* __restri
 	}
 }
 
-int grid_for(long total_items)
+// work units (row, chunk of 256 items) of a launch and the grid that walks them
+long units_for(long items_per_row, int n_streams) { return ((items_per_row + 255) / 256) * (long)n_streams; }
+int grid_for(long units)
 {
 	int sms = 148, dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	long need = (total_items + 255) / 256;
 	long cap = (long)sms * 8;  // eight 256-thread CTAs per SM, grid-stride beyond that
-	long g = need < cap ? need : cap;
+	long g = units < cap ? units : cap;
 	return (int)(g < 1 ? 1 : g);
 }
 
@@ -172,7 +186,7 @@ int zen_pcm16_decode_mono_async(const int16_t* d_pcm, long pcm_stride, int chann
 	if (n_frames == 0)
 		return ZEN_OK;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	const long ipr = (n_frames + 7) / 8, total = ipr * n_streams;
+	const long ipr = (n_frames + 7) / 8, total = units_for(ipr, n_streams);
 	const bool vec = aligned16(d_pcm) && aligned16(d_out) && (pcm_stride % 8) == 0 && (out_stride % 4) == 0;
 	const int g = grid_for(total);
 	if (channels == 1) {
@@ -197,7 +211,7 @@ int zen_pcm16_peaks_async(const float* d_in, long in_stride, int n_streams, long
 	ZEN_CUDA_CHECK(cudaMemsetAsync(d_peaks, 0, sizeof(float) * (size_t)n_streams, s));
 	if (n == 0)
 		return ZEN_OK;
-	const long ipr = (n + 7) / 8, total = ipr * n_streams;
+	const long ipr = (n + 7) / 8, total = units_for(ipr, n_streams);
 	const bool vec = aligned16(d_in) && (in_stride % 4) == 0;
 	const int g = grid_for(total);
 	if (vec) peak_kernel<true><<<g, 256, 0, s>>>(d_in, in_stride, n, ipr, total, reinterpret_cast<unsigned*>(d_peaks));
@@ -216,7 +230,7 @@ int zen_pcm16_encode_with_peaks_async(const float* d_in, long in_stride, int n_s
 	if (n == 0)
 		return ZEN_OK;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	const long ipr = (n + 7) / 8, total = ipr * n_streams;
+	const long ipr = (n + 7) / 8, total = units_for(ipr, n_streams);
 	const bool vec = aligned16(d_in) && aligned16(d_out) && (in_stride % 4) == 0 && (out_stride % 8) == 0;
 	const int g = grid_for(total);
 	if (vec)
