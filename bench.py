@@ -409,7 +409,7 @@ def run_ours(args, rank, world, local_rank):
     kern_avg_ms = float(np.mean(kern_ms))
     achieved = n_local * n_hops * BYTES_PER_HOP / (kern_avg_ms * 1e-3) / 1e9
     roof = {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": peak_src, "kernel": "hpr_tile_kernel<4096,256>", "kernel_ms": kern_avg_ms,
+            "peak_source": peak_src, "kernel": "hpr_tile_fast_kernel<4096,256,false>", "kernel_ms": kern_avg_ms,
             "algorithmic_bytes_per_launch": n_local * n_hops * BYTES_PER_HOP,
             "note": "achieved / peak / frac are the compulsory-byte HBM figures the contract asks for; the fused kernel is bound by "
                     "instruction issue (mask decision + FFT), not by HBM - issue_frac / alu_pipe_frac / fma_pipe_frac are ncu's "

@@ -95,7 +95,17 @@ int zen_box_filter(int time, int freq, int filter_len, int direction,
 int zen_fft_c2c(int nfft, float* d_inout, int inverse, void* cuda_stream);
 
 /* ---- HPR<Backend::GPU>, libzen/hps.h:152-322 + libzen/hps.cu:429-652 ----
- * Streaming harmonic/percussive/residual separation, one hop per call. */
+ * Streaming harmonic/percussive/residual separation, one hop per call.
+ *
+ * Limits of this build (everything else the reference accepts is accepted):
+ *   - hop must be a power of two in [32, 4096] (nfft = 4 hop in [128, 16384], one transform per CTA);
+ *     the reference's GPU path takes any hop cuFFT does, its IPP path powers of two only (libzen/fftw.h:57-60).
+ *     zen_hpr_create / zen_offline_process* / zen_hpr_batch_* return ZEN_ERR_UNSUPPORTED otherwise.
+ *   - the time-axis median reads at most ZEN_MAX_TAPS = 128 frames (csrc/hpr_core.cuh): l_harm, roughly
+ *     0.2 fs / (3 hop) frames (libzen/hps.h:227), must not exceed 128, i.e. hop >= fs / 1920
+ *     (fs 44.1 / 48 kHz: every supported hop; fs 192 kHz: hop >= 128).  ZEN_ERR_UNSUPPORTED otherwise.
+ *   - the frequency-axis median window l_perc (500 nfft / fs bins, libzen/hps.h:229) must not exceed 255
+ *     (fs >= 8 kHz at hop 1024).  ZEN_ERR_UNSUPPORTED otherwise. */
 typedef struct zen_hpr zen_hpr;
 int zen_hpr_create(zen_hpr** out, float fs, int hop, float beta, unsigned output_flags,
                    int causality /* ZEN_TIME_CAUSAL | ZEN_TIME_ANTICAUSAL */, int copy_bord);

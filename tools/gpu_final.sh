@@ -6,7 +6,7 @@ timeout 1500 python -m pytest tests -q -m gpu > $O/gpu_tests.log 2>&1
 echo "tests rc=$?" >> $O/gpu_tests.log
 timeout 900 python bench.py --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err
 echo "bench rc=$?" >> $O/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launch_list_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-parity --no-latency --no-e2e-f32 > $O/launch_list_bench.out 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"hpr_|pcm16|peak_kernel|copy_hop|mask_rows|scale_recip" -c 4000 --csv --log-file $O/launch_list_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-parity --no-latency --no-e2e-f32 > $O/launch_list_bench.out 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:hpr_tile -s 1 -c 1 -o $O/tile_kernel_296x30 python tools/prof_batch.py 296 30 2 > $O/ncu_296.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:hpr_tile -s 1 -c 1 -o $O/tile_kernel_full python tools/prof_batch.py 4096 60 2 > $O/ncu_full.log 2>&1
 timeout 300 python tools/rt_latency.py 1024 512 256 > $O/rt_latency.log 2>&1; cp gpurun_out/rt_latency.json $O/ 2>/dev/null

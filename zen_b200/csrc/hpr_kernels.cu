@@ -280,6 +280,7 @@ struct zen_hpr {
 	float* rt_out_host[3] = {nullptr, nullptr, nullptr};
 	bool rt_out_all_host = false;    // every non-null destination of the current call is host memory
 	bool rt_stamps = false;          // ZEN_B200_RT_STAMPS=1: the kernel records its phase boundaries (diagnostics)
+	bool rt_fenced = false;          // ZEN_B200_RT_FENCED: see RtArgs::fenced
 	int rt_cluster = 8;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop (8: p50 10.7 us / p99 11.2 us at hop 1024 against 11.0 / 14.1 with 4, profiles/r02_rt_latency.json)
 	// A process_next_hop without destinations is only SUBMITTED (like the reference's, which queues its kernels and lets
 	// copy_* wait, hps.cu:341-363): its outputs land in the tagged staging buffers and the copy_* that follows unpacks them
@@ -373,6 +374,8 @@ int rt_launch(zen_hpr* h)
 			const int c = std::atoi(e);
 			if (c == 1 || c == 2 || c == 4 || c == 8) h->rt_cluster = c;
 		}
+		if (const char* e = std::getenv("ZEN_B200_RT_FENCED"))
+			h->rt_fenced = std::atoi(e) != 0;
 	}
 	const int groups = (h->hop + 2) / 3;
 	if (!h->rt_stage_in || h->rt_groups != groups) {
@@ -412,6 +415,7 @@ int rt_launch(zen_hpr* h)
 	a.iter = h->d_iter;
 	a.seq0 = h->rt_seq;
 	a.idle_ns = h->rt_idle_ns;
+	a.fenced = h->rt_fenced ? 1 : 0;
 	a.stream = h->rt_stream;
 	h->rt_args_valid = false;
 	h->rt_ctrl->seq_out = h->rt_seq;

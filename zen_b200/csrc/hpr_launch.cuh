@@ -94,6 +94,7 @@ struct RtArgs {
 	unsigned seq0;         // last sequence number already served
 	unsigned long long idle_ns;
 	int state_in_smem;     // bit 0: ring + tails + previous hop resident in shared memory; bit 1: window / twiddle tables too
+	int fenced;            // cluster hand-off of the pushed hop behind fence.acq_rel.cluster on both sides (ZEN_B200_RT_FENCED, see hpr_rt_kernel)
 	int cluster;           // CTAs of the thread-block cluster that serves the stream (1: a single CTA)
 	cudaStream_t stream;
 };
@@ -385,6 +386,8 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 	const int rank = SPLIT ? (int)cg::this_cluster().block_rank() : 0;
 	const bool leader = rank == 0;
 	const int state_in_smem = smem_flags & 1;
+	const bool fenced = (smem_flags & 4) != 0;  // every hand-off of the hop to the other CTAs behind a cluster-scope fence
+	(void)fenced;
 	const int ring_n = P.W * (M + 1);
 
 	if (tid == 0) {
@@ -868,7 +871,7 @@ int launch_rt_variant(const RtArgs& a)
 	cfg.attrs = attr;
 	cfg.numAttrs = SPLIT ? 1 : 0;
 	ZEN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a.dev, a.ctrl, a.stage_in, a.stage_out[0], a.stage_out[1], a.stage_out[2], a.mag_ring,
-	                                  a.input, a.ola[0], a.ola[1], a.ola[2], a.iter, a.seq0, a.idle_ns, a.state_in_smem));
+	                                  a.input, a.ola[0], a.ola[1], a.ola[2], a.iter, a.seq0, a.idle_ns, a.state_in_smem | (a.fenced ? 4 : 0)));
 	return ZEN_OK;
 }
 
