@@ -99,6 +99,171 @@ __global__ void __launch_bounds__(SM_NT) median_run_freq_kernel(const float* __r
 		dst[(size_t)r * g.F + g.first + q0 + t] = O[t];
 }
 
+// ---- windows up to 15 taps: selection networks shared by two neighbouring outputs ----
+// Outputs q and q + 1 of an L-tap filter (L = 2 m + 1) share 2 m taps.  If lo / hi are the taps of rank m - 1 / m among
+// those 2 m, the median of the shared taps plus ONE more tap x is min(max(x, lo), hi): x itself when it falls between
+// them, the nearer bound otherwise.  lo and hi come out of Batcher's odd-even merge sorting network over the shared taps
+// with every comparator that does not feed rank m - 1 or m removed by the compiler (everything lives in registers with
+// constant indices): about 13 min/max pairs per output at L = 11 against 48 ALU operations for the sliding sorted
+// window, so these kernels are bound by memory, not by the FMNMX rate.  A median is still a selection: the output is the
+// bit pattern of one of the taps.
+template <int N>
+struct OemNetwork {
+	int n = 0;
+	unsigned char a[N * N + 4] = {}, b[N * N + 4] = {};
+	constexpr OemNetwork()
+	{
+		for (int p = 1; p < N; p *= 2)
+			for (int k = p; k >= 1; k /= 2)
+				for (int j = k % p; j + k < N; j += 2 * k)
+					for (int i = 0; i < k && i + j + k < N; ++i)
+						if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+							a[n] = (unsigned char)(i + j);
+							b[n] = (unsigned char)(i + j + k);
+							++n;
+						}
+	}
+};
+
+// the two middle taps of the 2 m = L - 1 shared ones w[1] .. w[L - 1]
+template <int L>
+__device__ __forceinline__ void pair_bounds(const float (&w)[L + 1], float& lo, float& hi)
+{
+	constexpr int N = L - 1;
+	constexpr OemNetwork<N> net;
+	float c[N];
+#pragma unroll
+	for (int i = 0; i < N; ++i)
+		c[i] = w[i + 1];
+#pragma unroll
+	for (int i = 0; i < net.n; ++i) {
+		const float x = c[net.a[i]], y = c[net.b[i]];
+		c[net.a[i]] = fminf(x, y);
+		c[net.b[i]] = fmaxf(x, y);
+	}
+	lo = c[N / 2 - 1];
+	hi = c[N / 2];
+}
+
+// Time axis: a thread owns one column and a run of consecutive output rows; lanes are adjacent columns, so every load
+// and store is coalesced.  The window of L + 1 rows slides through registers two rows per step; the rows of the next
+// step are fetched before the network of this one runs.
+// EDGE: the run touches the last row of the matrix (wrap to row 0 with copy_bord, stop there without)
+template <int L, bool EDGE>
+__device__ __forceinline__ void median_pair_time_run(const float* __restrict__ p, float* __restrict__ out, int n_out, int row, int T, size_t stride, bool wrap)
+{
+	const size_t rewind = (size_t)(T - 1) * stride;
+	auto next = [&]() -> float {
+		const float v = __ldg(p);
+		if (!EDGE)
+			p += stride;
+		else if (row < T - 1) {
+			p += stride;
+			++row;
+		}
+		else if (wrap) {
+			p -= rewind;
+			row = 0;
+		}
+		return v;
+	};
+	float w[L + 1];
+#pragma unroll
+	for (int i = 0; i < L - 1; ++i)
+		w[i] = next();
+	float n0 = next(), n1 = next();
+#pragma unroll((L + 1) / 2)
+	for (int q = 0; q < n_out; q += 2) {
+		w[L - 1] = n0;
+		w[L] = n1;
+		n0 = next();
+		n1 = next();
+		float lo, hi;
+		pair_bounds<L>(w, lo, hi);
+		out[0] = fminf(fmaxf(w[0], lo), hi);
+		if (q + 1 < n_out) out[stride] = fminf(fmaxf(w[L], lo), hi);
+		out += 2 * stride;
+#pragma unroll
+		for (int i = 0; i < L - 1; ++i)
+			w[i] = w[i + 2];
+	}
+}
+
+template <int L>
+__global__ void __launch_bounds__(256) median_pair_time_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g, int run_t)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	const long q0 = grid_row() * run_t;
+	if (c >= g.F || q0 >= g.n_out)
+		return;
+	const int n_out = (int)min((long)run_t, g.n_out - q0);
+	// tap j of this run is row (first + q0 + tap_off + j), wrapped; a pointer walks the rows without a multiplication
+	// or a division per load.  The walk reads up to three rows past the run's last tap (the next pair is fetched
+	// ahead; an odd run has half a pair too many): a run that would leave the matrix that way takes the EDGE path,
+	// where the pointer wraps to row 0 (copy_bord) or stays on the last row (those taps only feed outputs that are
+	// not stored).
+	int row = (int)(g.first + q0 + g.tap_off);
+	if (g.wrap) row = wrap_idx(row, g.T);
+	const float* p = src + (size_t)row * g.F + c;
+	float* out = dst + (size_t)(g.first + q0) * g.F + c;
+	if ((long)row + n_out + L + 3 <= g.T)
+		median_pair_time_run<L, false>(p, out, n_out, row, g.T, (size_t)g.F, false);
+	else
+		median_pair_time_run<L, true>(p, out, n_out, row, g.T, (size_t)g.F, g.wrap != 0);
+}
+
+// Frequency axis: a CTA stages one row segment (+ L - 1 taps of halo, wrap by index arithmetic) in shared memory with
+// coalesced loads; a thread takes output pairs (2 p, 2 p + 1), p = thread, thread + 256, ...: its L + 1 taps are
+// consecutive floats at an even offset (8-byte shared loads, no bank conflicts), its two outputs one 8-byte store.
+constexpr int PAIR_CHUNK = 4096;
+constexpr int PAIR_NT = 256;
+
+template <int L>
+__global__ void __launch_bounds__(PAIR_NT) median_pair_freq_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+{
+	__shared__ __align__(16) float E[PAIR_CHUNK + 16];
+	const long r = grid_row();
+	if (r >= g.T)
+		return;
+	const int q0 = blockIdx.x * PAIR_CHUNK;
+	const int nq = min(PAIR_CHUNK, g.n_out - q0);
+	const float* row = src + (size_t)r * g.F;
+	const int i0 = g.first + q0 + g.tap_off;
+	for (int t = threadIdx.x; t < nq + L - 1; t += PAIR_NT) {
+		int i = i0 + t;
+		if (g.wrap) {  // |i0 + t| stays within one period of the row: L <= F
+			if (i < 0) i += g.F;
+			if (i >= g.F) i -= g.F;
+		}
+		E[t] = __ldg(row + i);
+	}
+	__syncthreads();
+	float* orow = dst + (size_t)r * g.F + g.first + q0;
+	const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7u) == 0u);
+	for (int p = threadIdx.x; 2 * p < nq; p += PAIR_NT) {
+		float w[L + 1];
+#pragma unroll
+		for (int i = 0; i < (L + 1) / 2; ++i) {
+			const float2 v = *reinterpret_cast<const float2*>(E + 2 * p + 2 * i);
+			w[2 * i] = v.x;
+			w[2 * i + 1] = v.y;
+		}
+		float lo, hi;
+		pair_bounds<L>(w, lo, hi);
+		const float a = fminf(fmaxf(w[0], lo), hi), b = fminf(fmaxf(w[L], lo), hi);
+		if (2 * p + 1 < nq) {
+			if (vec)
+				*reinterpret_cast<float2*>(orow + 2 * p) = make_float2(a, b);
+			else {
+				orow[2 * p] = a;
+				orow[2 * p + 1] = b;
+			}
+		}
+		else
+			orow[2 * p] = a;
+	}
+}
+
 __global__ void __launch_bounds__(256) copy_axis_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
 {
 	// L == 1: the median of one tap is the tap
@@ -304,6 +469,24 @@ int make_geom(AxisGeom& g, int T, int F, int filter_len, int dir, int copy_bord)
 	return ZEN_OK;
 }
 
+template <int L>
+void launch_pair(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
+{
+	if (g.axis == 1) {
+		dim3 grid = rows_grid((g.n_out + PAIR_CHUNK - 1) / PAIR_CHUNK, g.T);
+		median_pair_freq_kernel<L><<<grid, PAIR_NT, 0, s>>>(src, dst, g);
+	}
+	else {
+		// run length (even): long enough to amortise the L - 1 rows of halo, short enough to fill the GPU
+		const int col_blocks = (g.F + 255) / 256;
+		int run_t = 128;
+		while (run_t > 8 && (long)col_blocks * ((g.n_out + run_t - 1) / run_t) < 1200)
+			run_t >>= 1;
+		dim3 grid = rows_grid(col_blocks, (g.n_out + run_t - 1) / run_t);
+		median_pair_time_kernel<L><<<grid, 256, 0, s>>>(src, dst, g, run_t);
+	}
+}
+
 template <int C>
 void launch_run(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
 {
@@ -348,13 +531,13 @@ int zen_median_filter(int time, int freq, int filter_len, int direction, int cop
 	}
 	else if (g.L <= 47) {
 		switch (g.L) {
-		case 3: launch_run<4>(d_src, d_dst, g, s); break;
-		case 5: launch_run<6>(d_src, d_dst, g, s); break;
-		case 7: launch_run<8>(d_src, d_dst, g, s); break;
-		case 9: launch_run<10>(d_src, d_dst, g, s); break;
-		case 11: launch_run<12>(d_src, d_dst, g, s); break;
-		case 13: launch_run<14>(d_src, d_dst, g, s); break;
-		case 15: launch_run<16>(d_src, d_dst, g, s); break;
+		case 3: launch_pair<3>(d_src, d_dst, g, s); break;
+		case 5: launch_pair<5>(d_src, d_dst, g, s); break;
+		case 7: launch_pair<7>(d_src, d_dst, g, s); break;
+		case 9: launch_pair<9>(d_src, d_dst, g, s); break;
+		case 11: launch_pair<11>(d_src, d_dst, g, s); break;
+		case 13: launch_pair<13>(d_src, d_dst, g, s); break;
+		case 15: launch_pair<15>(d_src, d_dst, g, s); break;
 		default:
 			if (g.L <= 23) launch_run<24>(d_src, d_dst, g, s);
 			else if (g.L <= 31) launch_run<32>(d_src, d_dst, g, s);

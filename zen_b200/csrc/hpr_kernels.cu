@@ -280,7 +280,7 @@ struct zen_hpr {
 	float* rt_out_host[3] = {nullptr, nullptr, nullptr};
 	bool rt_out_all_host = false;    // every non-null destination of the current call is host memory
 	bool rt_stamps = false;          // ZEN_B200_RT_STAMPS=1: the kernel records its phase boundaries (diagnostics)
-	bool rt_fenced = false;          // ZEN_B200_RT_FENCED: see RtArgs::fenced
+	bool rt_fenced = true;           // ZEN_B200_RT_FENCED=0 drops the cluster-scope fences of the hop hand-off (RtArgs::fenced): same latency either way (profiles/r02_rt_latency_fenced.txt)
 	int rt_cluster = 8;              // ZEN_B200_RT_CLUSTER: CTAs serving the stream when the plan allows the split hop (8: p50 10.7 us / p99 11.2 us at hop 1024 against 11.0 / 14.1 with 4, profiles/r02_rt_latency.json)
 	// A process_next_hop without destinations is only SUBMITTED (like the reference's, which queues its kernels and lets
 	// copy_* wait, hps.cu:341-363): its outputs land in the tagged staging buffers and the copy_* that follows unpacks them

@@ -596,11 +596,15 @@ __global__ void __launch_bounds__(NT, 1) hpr_rt_kernel(const __grid_constant__ H
 				// them while they window it (rt_microbench: pushing 1026 floats costs ~0.7 us per CTA with 4-byte stores,
 				// pulling them ~0.35 us for all CTAs at once).  The command word doubles as the flag the other CTAs spin
 				// on: no cluster barrier (0.2 us + the leader waiting for it) at the start of a hop.
-				// The LAST thread signals, after the barrier, while the other warps already start on the hop.  No
-				// cluster-scope fence on the common path: the stash lives in this CTA's shared memory - one physical
-				// copy, no cache in front of it - and BAR.SYNC has drained the stores into it before the command word
-				// leaves; a reader that has seen the word issues its (remote) loads afterwards.  A fence costs ~0.5 us
-				// of the leader's and of everybody else's hop.  Changed arguments (rare) do travel behind a fence.
+				// The LAST thread signals, after the barrier, while the other warps already start on the hop.  The
+				// command word is released at cluster scope (fence.acq_rel.cluster before the store, and again in the
+				// reader once it has seen the word), as the PTX memory model asks for a hand-off through another CTA's
+				// shared memory.  Measured: the fences sit on one thread while the other warps work and cost nothing
+				// at the host (p50 10.68 us with, 10.70 us without, profiles/r02_rt_latency_fenced.txt).  Without
+				// them the protocol has never delivered a stale word either (2 x 10^6 rounds x 7 readers of
+				// tests/cpp/handoff_litmus.cu: shared memory is one physical copy and BAR.SYNC has drained the
+				// stores), but that is evidence, not a guarantee: `fenced` is the default, ZEN_B200_RT_FENCED=0
+				// the experiment.
 				if (tid == NT - 1) {
 					const unsigned cw = S.op;  // (opw is thread 0's: this thread may not own a tagged group)
 					if (cw & RT_F_NEW_ARGS) {
