@@ -143,3 +143,39 @@ def test_pcm16_round_trip_and_strides(torch):
     q, peaks = hps.pcm16_encode_normalized(f)
     assert np.all(peaks.cpu().numpy() == 1.0)
     assert np.array_equal(q.cpu().numpy(), big[:, :20000])
+
+
+@pytest.mark.gpu
+def test_pcm16_encode_fast_division_is_the_ieee_one(torch):
+    """The encode kernel divides by the row's peak with a hoisted reciprocal and two residual corrections instead of one
+    IEEE division per sample (csrc/pcm.cu, pcm_from_float_fast).  Peaks with awkward significands (all ones, one ulp
+    around powers of two, random), samples drawn uniformly and packed around the PCM16 rounding boundaries
+    (k + 1/2) / 32767 x peak +- a few ulps: every integer must be the one float32 division gives."""
+    from zen_b200 import hps
+    rng = np.random.default_rng(99)
+    n_rows, n = 96, 1 << 19
+    mant = rng.integers(0, 1 << 23, n_rows).astype(np.uint32)
+    mant[:8] = [0x7fffff, 0x7ffffe, 0, 1, 0x400000, 0x3fffff, 0x555555, 0x2aaaaa]
+    expo = rng.integers(127 - 40, 127 + 40, n_rows).astype(np.uint32)
+    expo[8:16] = 127
+    expo[16:20] = [127 + 70, 127 - 70, 127 + 100, 127 - 100]      # outside the fast path's range: IEEE division per sample
+    peaks = ((expo << 23) | mant).view(np.float32)
+    x = np.empty((n_rows, n), np.float32)
+    for r in range(n_rows):
+        pk = peaks[r]
+        u = rng.uniform(-1.0, 1.0, n // 2).astype(np.float32) * pk
+        k = rng.integers(-32767, 32767, n - n // 2 - 1).astype(np.float64)
+        b = ((k + 0.5) / 32767.0 * np.float64(pk)).astype(np.float32)
+        b = (b.view(np.int32) + rng.integers(-3, 4, b.size).astype(np.int32)).view(np.float32)
+        row = np.concatenate([u, b, np.array([pk], np.float32)])
+        np.clip(row, -pk, pk, out=row)
+        row[-1] = pk if r % 2 else -pk
+        x[r] = row
+    q, pk_out = hps.pcm16_encode_normalized(torch.from_numpy(x).cuda())
+    q, pk_out = q.cpu().numpy(), pk_out.cpu().numpy()
+    assert np.array_equal(pk_out.view(np.uint32), peaks.view(np.uint32))
+    bad = 0
+    for r in range(n_rows):
+        eq, _ = np_model.pcm16_encode_normalized(x[r])
+        bad += int((eq != q[r]).sum())
+    assert bad == 0

@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out/y; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "median or filter or mfilt or npp or tall or box" > $O/tests.log 2>&1
-timeout 300 python -m pytest tests/test_reference_tests.py -q -m gpu >> $O/tests.log 2>&1
-timeout 200 python tools/mfilt_bench.py > $O/mfilt_bench.json 2>&1
-tail -5 $O/tests.log; cat $O/mfilt_bench.json
+timeout 900 python -m pytest tests/test_pcm.py tests/test_batch_host.py -q -m gpu > $O/tests.log 2>&1
+timeout 200 python tools/pcm_bench.py > $O/pcm_bench.log 2>&1
+tail -5 $O/tests.log; cat $O/pcm_bench.log
