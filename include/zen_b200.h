@@ -90,8 +90,8 @@ int zen_box_filter(int time, int freq, int filter_len, int direction,
 
 /* ---- FFTC2CWrapperGPU, libzen/fftw.h:20-49 ----
  * In-place 1-D complex-to-complex FFT on interleaved float pairs, unnormalised
- * in both directions; nfft a power of two in [2, 65536] (one CTA up to 16384,
- * a two-kernel four-step transform above). */
+ * in both directions; nfft a power of two in [2, 65536] (one CTA up to 4096,
+ * a two-kernel four-step transform from 8192). */
 int zen_fft_c2c(int nfft, float* d_inout, int inverse, void* cuda_stream);
 
 /* ---- HPR<Backend::GPU>, libzen/hps.h:152-322 + libzen/hps.cu:429-652 ----
