@@ -266,6 +266,13 @@ int zen_offline_process_device(float fs, int hop_h, int hop_p, float beta_h, flo
 int zen_mpm_pitch(int n, float sample_rate, const float* d_audio, long stride, int n_buffers, float* d_pitch, float* d_nsdf,
                   void* cuda_stream);
 
+/* ---- the consumer of the percussive output: BTrack's onset detection function, demos/beat-tracking/OnsetDetection.cpp:60-131
+ * (complex spectral difference, half-wave rectified; 512-sample frames, 256-sample hops as OnsetDetection.h:15,27 fix them),
+ * called per hop by BTrack::processHop (BTrack.cpp:93-98) on the hops main.cu:107-118 copies out of the GPU.  Here the hops
+ * are read in device memory: row s of d_audio (stride in floats, >= 256 n_hops) is one stream from its start, row s of
+ * d_odf (odf_stride >= n_hops) receives one sample per hop - what BTrack::processOnsetDetectionFunctionSample consumes. */
+int zen_onset_csd(const float* d_audio, long stride, int n_streams, long n_hops, float* d_odf, long odf_stride, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -710,3 +710,58 @@ float zo_mpm_pitch(const float* audio, int n, float sample_rate, float* nsdf_out
 	free(ey);
 	return result;
 }
+
+/* ---- demos/beat-tracking/OnsetDetection.cpp:60-131: the onset detection function BTrack::processHop (BTrack.cpp:93-98)
+ * computes from every 256-sample hop of the percussive output (main.cu:92-118).  Literal restatement, the in-place
+ * window + swap of perform_FFT (OnsetDetection.cpp:72-85) included: the frame it shifts next time is the one it has just
+ * windowed. ---- */
+void zo_onset_window(float* w512)
+{
+	/* Window.h:31-40 calculate_hanning_window<512>; the reference evaluates cos with gcem at compile time */
+	const float PI = 3.14159265359F, N = (float)(512 - 1);
+	for (int n = 0; n < 512; ++n)
+		w512[n] = 0.5F * (1.0F - cosf(2.0F * PI * ((float)n / N)));
+}
+
+void zo_onset_csd(const float* audio, long n_hops, float* out)
+{
+	enum { FS = 512, HS = 256 };
+	float w[FS], frame[FS] = {0}, mag[FS], pmag[FS] = {0}, ph[FS], pph[FS] = {0}, pph2[FS] = {0};
+	float z[2 * FS];
+	zo_onset_window(w);
+	for (long h = 0; h < n_hops; ++h) {
+		/* calculate_sample, OnsetDetection.cpp:60-69 */
+		memmove(frame, frame + HS, sizeof(float) * (FS - HS));
+		memcpy(frame + FS - HS, audio + h * HS, sizeof(float) * HS);
+		/* perform_FFT, :72-85 */
+		for (int i = 0; i < HS; ++i) {
+			const float t = frame[i];
+			frame[i] = frame[i + HS];
+			frame[i + HS] = t;
+			frame[i] *= w[i + HS];
+			frame[i + HS] *= w[i];
+		}
+		for (int i = 0; i < FS; ++i) {
+			z[2 * i] = frame[i];
+			z[2 * i + 1] = 0.0f; /* imIn stays zero */
+		}
+		zo_fft(FS, z, 0);
+		/* complex_spectral_difference_hwr, :87-131 */
+		float sum = 0;
+		for (int i = 0; i < FS; ++i) {
+			const float re = z[2 * i], im = z[2 * i + 1];
+			ph[i] = atan2f(im, re);
+			mag[i] = sqrtf(powf(re, 2) + powf(im, 2));
+			const float dev = ph[i] - (2 * pph[i]) + pph2[i];
+			const float md = mag[i] - pmag[i];
+			if (md > 0) {
+				const float csd = sqrtf(powf(mag[i], 2) + powf(pmag[i], 2) - 2 * mag[i] * pmag[i] * cosf(dev));
+				sum = sum + csd;
+			}
+			pph2[i] = pph[i];
+			pph[i] = ph[i];
+			pmag[i] = mag[i];
+		}
+		out[h] = sum;
+	}
+}

@@ -75,6 +75,11 @@ int zo_offline_process(int geom, float fs, int hop_h, int hop_p, float beta_h, f
  * pitch in Hz or -1; nsdf_out (optional, n floats) receives real_autocorrelation's output */
 float zo_mpm_pitch(const float* audio, int n, float sample_rate, float* nsdf_out);
 
+/* demos/beat-tracking/OnsetDetection.cpp:60-131 (complex spectral difference, half-wave rectified; the consumer of the
+ * percussive output, main.cu:92-118): n_hops hops of 256 samples in, one ODF sample per hop out */
+void zo_onset_csd(const float* audio, long n_hops, float* out);
+void zo_onset_window(float* w512); /* Window.h:31-40, Hann, 512 */
+
 /* zen/fakert.h:15-34 get_chunk_limits: number of hops fakert processes */
 long zo_fakert_n_chunks(long size, long hop);
 

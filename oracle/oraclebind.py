@@ -58,6 +58,10 @@ def lib():
         L.zo_offline_process.argtypes = [ci, cf, ci, ci, cf, cf, ci, ci, vp, cl, vp, vp, vp]
         L.zo_mpm_pitch.argtypes = [vp, ci, cf, vp]
         L.zo_mpm_pitch.restype = cf
+        L.zo_onset_csd.argtypes = [vp, cl, vp]
+        L.zo_onset_csd.restype = None
+        L.zo_onset_window.argtypes = [vp]
+        L.zo_onset_window.restype = None
         L.zo_fakert_n_chunks.argtypes = [cl, cl]
         L.zo_fakert_n_chunks.restype = cl
         _lib = L
@@ -182,3 +186,18 @@ def mpm_pitch(audio, sample_rate, want_nsdf=False):
     nsdf = np.zeros(a.size, dtype=np.float32) if want_nsdf else None
     p = float(lib().zo_mpm_pitch(_p(a), a.size, sample_rate, _p(nsdf)))
     return (p, nsdf) if want_nsdf else p
+
+
+def onset_csd(audio):
+    """demos/beat-tracking/OnsetDetection.cpp calculate_sample over consecutive 256-sample hops: one ODF sample per hop"""
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    n_hops = a.size // 256
+    out = np.zeros(n_hops, dtype=np.float32)
+    lib().zo_onset_csd(_p(a), n_hops, _p(out))
+    return out
+
+
+def onset_window():
+    w = np.zeros(512, dtype=np.float32)
+    lib().zo_onset_window(_p(w))
+    return w

@@ -244,4 +244,35 @@ static inline IppStatus ippsFFTInv_CToC_32fc_I(Ipp32fc* x, const IppsFFTSpec_C_3
 	return ippStsNoErr;
 }
 
+/* split-array variant (demos/beat-tracking/OnsetDetection.cpp:16-47, 72-85): real and imaginary parts in separate
+ * arrays, out of place */
+typedef IppsFFTSpec_C_32fc IppsFFTSpec_C_32f;
+static inline IppStatus ippsFFTGetSize_C_32f(int order, int flag, IppHintAlgorithm hint, int* specSize, int* initSize, int* bufSize)
+{
+	IppStatus st = ippsFFTGetSize_C_32fc(order, flag, hint, specSize, initSize, bufSize);
+	*bufSize += (int)sizeof(Ipp32fc) * (1 << order);
+	return st;
+}
+static inline IppStatus ippsFFTInit_C_32f(IppsFFTSpec_C_32f** pp, int order, int flag, IppHintAlgorithm hint, Ipp8u* specMem, Ipp8u* initMem)
+{
+	return ippsFFTInit_C_32fc(pp, order, flag, hint, specMem, initMem);
+}
+static inline IppStatus ippsFFTFwd_CToC_32f(const Ipp32f* srcRe, const Ipp32f* srcIm, Ipp32f* dstRe, Ipp32f* dstIm,
+                                            const IppsFFTSpec_C_32f* s, Ipp8u* buf)
+{
+	const int n = s->n;
+	Ipp32fc* x = (Ipp32fc*)(((size_t)buf + 15) & ~(size_t)15);
+	Ipp8u* rest = (Ipp8u*)(x + n);
+	for (int i = 0; i < n; ++i) {
+		x[i].re = srcRe[i];
+		x[i].im = srcIm[i];
+	}
+	ipp_standin_fft(x, s, rest, -1);
+	for (int i = 0; i < n; ++i) {
+		dstRe[i] = x[i].re;
+		dstIm[i] = x[i].im;
+	}
+	return ippStsNoErr;
+}
+
 #endif /* ZEN_ORACLE_IPP_STANDIN_H */

@@ -472,3 +472,25 @@ class MPM:
                                        nsdf.data_ptr() if want_nsdf else None, torch.cuda.current_stream().cuda_stream), "zen_mpm_pitch")
         res = out[0] if one else out
         return (res, nsdf[0] if one else nsdf) if want_nsdf else res
+
+
+class OnsetDetectionFunction:
+    """The onset detection function BTrack computes from the percussive output (demos/beat-tracking/OnsetDetection.cpp:60-131,
+    complex spectral difference, half-wave rectified; FrameSize 512, HopSize 256), batched on the device:
+    calculate_samples(x) takes a float32 CUDA tensor [n_streams, n_hops * 256] (or one stream, 1-D) - e.g. the percussive
+    output of HPRBatch at hop 256 - and returns one sample per hop, [n_streams, n_hops]: the sequence the reference's
+    calculate_sample() returns hop after hop on a fresh object."""
+    FrameSize, HopSize = 512, 256
+
+    def calculate_samples(self, x):
+        torch = _torch()
+        one = x.dim() == 1
+        x2 = x.reshape(1, -1) if one else x
+        assert x2.is_cuda and x2.dtype == torch.float32 and (x2.shape[1] == 0 or x2.stride(1) == 1)
+        n_streams, n_hops = x2.shape[0], x2.shape[1] // self.HopSize
+        out = torch.empty((n_streams, n_hops), dtype=torch.float32, device=x.device)
+        if n_hops:
+            stride = x2.stride(0) if n_streams > 1 else x2.shape[1]
+            check(_lib.lib().zen_onset_csd(x2.data_ptr(), stride, n_streams, n_hops, out.data_ptr(), max(1, out.stride(0)),
+                                           torch.cuda.current_stream().cuda_stream), "zen_onset_csd")
+        return out[0] if one else out
