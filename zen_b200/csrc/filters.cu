@@ -145,12 +145,54 @@ __device__ __forceinline__ void pair_bounds(const float (&w)[L + 1], float& lo, 
 	hi = c[N / 2];
 }
 
+// What a thread does with the L + 1 taps w[0 .. L] of an output pair: a = f(w[0 .. L - 1]), b = f(w[1 .. L]).
+template <int L>
+struct MedianPairOp {
+	static __device__ __forceinline__ void apply(const float (&w)[L + 1], float& a, float& b)
+	{
+		float lo, hi;
+		pair_bounds<L>(w, lo, hi);
+		a = fminf(fmaxf(w[0], lo), hi);
+		b = fminf(fmaxf(w[L], lo), hi);
+	}
+};
+
+// x / L for a small integer L, correctly rounded like the IEEE division it replaces: q = x r with r = RN(1 / L), then
+// two residual corrections (the residual fma(-q, L, x) is exact); inf and NaN sums pass through untouched.
+template <int L>
+__device__ __forceinline__ float div_by_len(float x)
+{
+	constexpr float r = 1.0f / (float)L;
+	float q = x * r;
+	if (fabsf(q) < CUDART_INF_F && fabsf(x) > 1e-30f) {
+		q = __fmaf_rn(__fmaf_rn(-q, (float)L, x), r, q);
+		q = __fmaf_rn(__fmaf_rn(-q, (float)L, x), r, q);
+	}
+	else if (fabsf(q) < CUDART_INF_F)
+		q = __fdiv_rn(x, (float)L);  // results near the subnormal range: the plain division
+	return q;
+}
+
+// Box filter: the two windows share the sum of their L - 1 common taps; nothing is ever subtracted (see box_freq_kernel)
+template <int L>
+struct BoxPairOp {
+	static __device__ __forceinline__ void apply(const float (&w)[L + 1], float& a, float& b)
+	{
+		float s = w[1];
+#pragma unroll
+		for (int i = 2; i < L; ++i)
+			s += w[i];
+		a = div_by_len<L>(w[0] + s);
+		b = div_by_len<L>(s + w[L]);
+	}
+};
+
 // Time axis: a thread owns one column and a run of consecutive output rows; lanes are adjacent columns, so every load
 // and store is coalesced.  The window of L + 1 rows slides through registers two rows per step; the rows of the next
 // step are fetched before the network of this one runs.
 // EDGE: the run touches the last row of the matrix (wrap to row 0 with copy_bord, stop there without)
-template <int L, bool EDGE>
-__device__ __forceinline__ void median_pair_time_run(const float* __restrict__ p, float* __restrict__ out, int n_out, int row, int T, size_t stride, bool wrap)
+template <int L, bool EDGE, class OP>
+__device__ __forceinline__ void pair_time_run(const float* __restrict__ p, float* __restrict__ out, int n_out, int row, int T, size_t stride, bool wrap)
 {
 	const size_t rewind = (size_t)(T - 1) * stride;
 	auto next = [&]() -> float {
@@ -178,10 +220,10 @@ __device__ __forceinline__ void median_pair_time_run(const float* __restrict__ p
 		w[L] = n1;
 		n0 = next();
 		n1 = next();
-		float lo, hi;
-		pair_bounds<L>(w, lo, hi);
-		out[0] = fminf(fmaxf(w[0], lo), hi);
-		if (q + 1 < n_out) out[stride] = fminf(fmaxf(w[L], lo), hi);
+		float a, b;
+		OP::apply(w, a, b);
+		out[0] = a;
+		if (q + 1 < n_out) out[stride] = b;
 		out += 2 * stride;
 #pragma unroll
 		for (int i = 0; i < L - 1; ++i)
@@ -189,8 +231,8 @@ __device__ __forceinline__ void median_pair_time_run(const float* __restrict__ p
 	}
 }
 
-template <int L>
-__global__ void __launch_bounds__(256) median_pair_time_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g, int run_t)
+template <int L, class OP>
+__global__ void __launch_bounds__(256) pair_time_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g, int run_t)
 {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	const long q0 = grid_row() * run_t;
@@ -207,9 +249,9 @@ __global__ void __launch_bounds__(256) median_pair_time_kernel(const float* __re
 	const float* p = src + (size_t)row * g.F + c;
 	float* out = dst + (size_t)(g.first + q0) * g.F + c;
 	if ((long)row + n_out + L + 3 <= g.T)
-		median_pair_time_run<L, false>(p, out, n_out, row, g.T, (size_t)g.F, false);
+		pair_time_run<L, false, OP>(p, out, n_out, row, g.T, (size_t)g.F, false);
 	else
-		median_pair_time_run<L, true>(p, out, n_out, row, g.T, (size_t)g.F, g.wrap != 0);
+		pair_time_run<L, true, OP>(p, out, n_out, row, g.T, (size_t)g.F, g.wrap != 0);
 }
 
 // Frequency axis: a CTA stages one row segment (+ L - 1 taps of halo, wrap by index arithmetic) in shared memory with
@@ -218,8 +260,8 @@ __global__ void __launch_bounds__(256) median_pair_time_kernel(const float* __re
 constexpr int PAIR_CHUNK = 4096;
 constexpr int PAIR_NT = 256;
 
-template <int L>
-__global__ void __launch_bounds__(PAIR_NT) median_pair_freq_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
+template <int L, class OP>
+__global__ void __launch_bounds__(PAIR_NT) pair_freq_kernel(const float* __restrict__ src, float* __restrict__ dst, AxisGeom g)
 {
 	__shared__ __align__(16) float E[PAIR_CHUNK + 16];
 	const long r = grid_row();
@@ -229,14 +271,29 @@ __global__ void __launch_bounds__(PAIR_NT) median_pair_freq_kernel(const float* 
 	const int nq = min(PAIR_CHUNK, g.n_out - q0);
 	const float* row = src + (size_t)r * g.F;
 	const int i0 = g.first + q0 + g.tap_off;
-	for (int t = threadIdx.x; t < nq + L - 1; t += PAIR_NT) {
-		int i = i0 + t;
-		if (g.wrap) {  // |i0 + t| stays within one period of the row: L <= F
-			if (i < 0) i += g.F;
-			if (i >= g.F) i -= g.F;
-		}
-		E[t] = __ldg(row + i);
+	const int n_used = nq + L - 1;
+	// staging: every thread issues all its loads before it stores the first (17 independent 4-byte loads in flight per
+	// thread is what keeps this kernel on the memory roofline); only the first and the last chunk of a row wrap
+	constexpr int NLD = (PAIR_CHUNK + 16 + PAIR_NT - 1) / PAIR_NT;
+	float v[NLD];
+	if (i0 >= 0 && i0 + n_used <= g.F) {
+		const float* p0 = row + i0 + threadIdx.x;
+#pragma unroll
+		for (int k = 0; k < NLD; ++k)
+			v[k] = threadIdx.x + k * PAIR_NT < n_used ? __ldg(p0 + k * PAIR_NT) : 0.0f;
 	}
+	else {
+#pragma unroll
+		for (int k = 0; k < NLD; ++k) {
+			const int t = threadIdx.x + k * PAIR_NT;
+			int i = i0 + t;
+			if (g.wrap) i = wrap_idx(i, g.F);
+			v[k] = t < n_used ? __ldg(row + i) : 0.0f;
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < NLD; ++k)
+		if (threadIdx.x + k * PAIR_NT < PAIR_CHUNK + 16) E[threadIdx.x + k * PAIR_NT] = v[k];
 	__syncthreads();
 	float* orow = dst + (size_t)r * g.F + g.first + q0;
 	const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7u) == 0u);
@@ -248,9 +305,8 @@ __global__ void __launch_bounds__(PAIR_NT) median_pair_freq_kernel(const float* 
 			w[2 * i] = v.x;
 			w[2 * i + 1] = v.y;
 		}
-		float lo, hi;
-		pair_bounds<L>(w, lo, hi);
-		const float a = fminf(fmaxf(w[0], lo), hi), b = fminf(fmaxf(w[L], lo), hi);
+		float a, b;
+		OP::apply(w, a, b);
 		if (2 * p + 1 < nq) {
 			if (vec)
 				*reinterpret_cast<float2*>(orow + 2 * p) = make_float2(a, b);
@@ -469,12 +525,12 @@ int make_geom(AxisGeom& g, int T, int F, int filter_len, int dir, int copy_bord)
 	return ZEN_OK;
 }
 
-template <int L>
+template <int L, class OP>
 void launch_pair(const float* src, float* dst, const AxisGeom& g, cudaStream_t s)
 {
 	if (g.axis == 1) {
 		dim3 grid = rows_grid((g.n_out + PAIR_CHUNK - 1) / PAIR_CHUNK, g.T);
-		median_pair_freq_kernel<L><<<grid, PAIR_NT, 0, s>>>(src, dst, g);
+		pair_freq_kernel<L, OP><<<grid, PAIR_NT, 0, s>>>(src, dst, g);
 	}
 	else {
 		// run length (even): long enough to amortise the L - 1 rows of halo, short enough to fill the GPU
@@ -483,7 +539,7 @@ void launch_pair(const float* src, float* dst, const AxisGeom& g, cudaStream_t s
 		while (run_t > 8 && (long)col_blocks * ((g.n_out + run_t - 1) / run_t) < 1200)
 			run_t >>= 1;
 		dim3 grid = rows_grid(col_blocks, (g.n_out + run_t - 1) / run_t);
-		median_pair_time_kernel<L><<<grid, 256, 0, s>>>(src, dst, g, run_t);
+		pair_time_kernel<L, OP><<<grid, 256, 0, s>>>(src, dst, g, run_t);
 	}
 }
 
@@ -531,13 +587,13 @@ int zen_median_filter(int time, int freq, int filter_len, int direction, int cop
 	}
 	else if (g.L <= 47) {
 		switch (g.L) {
-		case 3: launch_pair<3>(d_src, d_dst, g, s); break;
-		case 5: launch_pair<5>(d_src, d_dst, g, s); break;
-		case 7: launch_pair<7>(d_src, d_dst, g, s); break;
-		case 9: launch_pair<9>(d_src, d_dst, g, s); break;
-		case 11: launch_pair<11>(d_src, d_dst, g, s); break;
-		case 13: launch_pair<13>(d_src, d_dst, g, s); break;
-		case 15: launch_pair<15>(d_src, d_dst, g, s); break;
+		case 3: launch_pair<3, MedianPairOp<3>>(d_src, d_dst, g, s); break;
+		case 5: launch_pair<5, MedianPairOp<5>>(d_src, d_dst, g, s); break;
+		case 7: launch_pair<7, MedianPairOp<7>>(d_src, d_dst, g, s); break;
+		case 9: launch_pair<9, MedianPairOp<9>>(d_src, d_dst, g, s); break;
+		case 11: launch_pair<11, MedianPairOp<11>>(d_src, d_dst, g, s); break;
+		case 13: launch_pair<13, MedianPairOp<13>>(d_src, d_dst, g, s); break;
+		case 15: launch_pair<15, MedianPairOp<15>>(d_src, d_dst, g, s); break;
 		default:
 			if (g.L <= 23) launch_run<24>(d_src, d_dst, g, s);
 			else if (g.L <= 31) launch_run<32>(d_src, d_dst, g, s);
@@ -570,7 +626,19 @@ int zen_box_filter(int time, int freq, int filter_len, int direction, const floa
 	if (rc != ZEN_OK)
 		return rc;
 	cudaStream_t s = (cudaStream_t)cuda_stream;
-	if (g.axis == 1) {
+	if (g.L >= 3 && g.L <= 15) {
+		// short windows: the output-pair kernels of the median filter with a sum in place of the selection
+		switch (g.L) {
+		case 3: launch_pair<3, BoxPairOp<3>>(d_src, d_dst, g, s); break;
+		case 5: launch_pair<5, BoxPairOp<5>>(d_src, d_dst, g, s); break;
+		case 7: launch_pair<7, BoxPairOp<7>>(d_src, d_dst, g, s); break;
+		case 9: launch_pair<9, BoxPairOp<9>>(d_src, d_dst, g, s); break;
+		case 11: launch_pair<11, BoxPairOp<11>>(d_src, d_dst, g, s); break;
+		case 13: launch_pair<13, BoxPairOp<13>>(d_src, d_dst, g, s); break;
+		default: launch_pair<15, BoxPairOp<15>>(d_src, d_dst, g, s); break;
+		}
+	}
+	else if (g.axis == 1) {
 		const size_t smem = sizeof(float) * 3 * (size_t)((BOX_CHUNK + g.L - 1 + 3) & ~3);
 		if (smem > 200 * 1024)
 			return ZEN_ERR_UNSUPPORTED;
