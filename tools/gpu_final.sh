@@ -18,6 +18,10 @@ timeout 200 python tools/box_bench.py > $O/box_bench.json 2>&1
 timeout 200 python tools/fft_bench.py > $O/fft_bench.json 2>&1
 timeout 200 python tools/pcm_bench.py > $O/pcm_bench.log 2>&1
 timeout 200 python tools/link_bw.py > $O/link_bw_n1.json 2>&1
+timeout 400 python tools/hps_bench.py > $O/hps_bench_sweep.log 2>&1; cp gpurun_out/hps_bench.json $O/hps_bench_sweep.json 2>/dev/null
+timeout 120 tools/_build/stream_bench > $O/stream_bench.json 2>&1
+timeout 120 tools/_build/tma_poll_microbench 3000 > $O/tma_poll_microbench.json 2>&1
+cp gpurun_out/handoff_litmus_c8.json gpurun_out/pcm_bench.json $O/ 2>/dev/null
 cp gpurun_out/long_parity.json $O/ 2>/dev/null
 rm -f $O/tile_kernel_296x30.ncu-rep.keep
 tail -4 $O/gpu_tests.log; cut -c1-400 $O/bench.json; tail -2 $O/bench.err; tail -3 $O/rt_latency.log; ls -la $O

@@ -22,8 +22,10 @@ def cp(a, b):
 
 for a, b in [("bench.json", "bench_n1.json"), ("rt_latency.json", "rt_latency.json"), ("rt_phases_hop1024.txt", "rt_phases_hop1024.txt"),
              ("batch_sweep.json", "batch_sweep.json"), ("other_configs.json", "other_configs.json"), ("mfilt_bench.json", "mfilt_bench_vs_npp.json"),
-             ("box_bench.json", "box_bench.json"), ("fft_bench.json", "fft_bench_vs_cufft.json"), ("pcm_bench.log", "pcm_bench.json"),
-             ("link_bw_n1.json", "link_bw_n1.json"), ("long_parity.json", "long_parity.json"), ("gpu_tests.log", "gpu_tests.txt")]:
+             ("box_bench.json", "box_bench.json"), ("fft_bench.json", "fft_bench_vs_cufft.json"),
+             ("link_bw_n1.json", "link_bw_n1.json"), ("long_parity.json", "long_parity.json"), ("gpu_tests.log", "gpu_tests.txt"),
+             ("hps_bench_sweep.json", "hps_bench_sweep.json"), ("stream_bench.json", "stream_bench.json"), ("tma_poll_microbench.json", "tma_poll_microbench.json"),
+             ("handoff_litmus_c8.json", "handoff_litmus_c8.json"), ("pcm_bench.json", "pcm_bench.json")]:
     cp(a, b)
 
 # ---- ncu --set full captures -> text summaries + the json bench.py reads

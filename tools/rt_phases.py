@@ -31,7 +31,7 @@ for i in range(400):
         if r[12] > r[9] > 0:
             g1 = (r[11] - r[10]) / max(1.0, float(r[12] - r[9]))
             c1 = 1e3 * g1
-            acc1.append([(r[9] - s[9]) * 1e-3, (r[12] - s[12]) * 1e-3] + [(r[k + 1] - r[k]) / c1 for k in range(8)] + [(r[0] - r[10]) / c1])
+            acc1.append([(r[9] - s[9]) * 1e-3, (r[12] - s[12]) * 1e-3] + [(r[k + 1] - r[k]) / c1 for k in range(5)] + [(r[11] - r[5]) / c1, (r[0] - r[10]) / c1])
 a = np.median(np.array(acc), axis=0)
 names = ["host call us", "A load+window", "B fft fwd", "C split+mag", "F' H row", "E' decide", "G build", "G ifft", "G ola+emit", "pre", "kernel total", "SM clock GHz",
          "E'.1 H+thresholds (thread 0)", "E'.2 counting (thread 0)", "E'.3 rest + barrier"]
@@ -41,5 +41,5 @@ h.close()
 if acc1:
     b = np.median(np.array(acc1), axis=0)
     print("-- CTA 1 of the cluster (globaltimer relative to the leader)")
-    for n, v in zip(["saw the command after the leader detected the hop", "finished after the leader", "A", "B fft fwd", "C split+mag", "F'", "E' decide", "G build", "G ifft", "G ola", "pre"], b):
+    for n, v in zip(["saw the command after the leader detected the hop", "finished after the leader", "A", "B fft fwd (incl. pulling the hop from the leader)", "C split+mag", "F'", "E' decide", "masked spectrum to its owner + cluster barrier", "pre"], b):
         print("%-52s %7.2f us" % (n, v))
