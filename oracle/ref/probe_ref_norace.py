@@ -23,16 +23,25 @@ from zen_b200.synth import synth_audio  # noqa: E402
 out_dir = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/ref_norace"
 os.makedirs(out_dir, exist_ok=True)
 CASES = [
-    # name, fs, hop, beta, flags, copy_bord, n_hops, seed      (HPRRealtime<GPU>: causal, hard mask)
-    ("rt1024_cb", 44100.0, 1024, 2.5, 7, 1, 40, 31),
-    ("rt512_cb", 44100.0, 512, 2.5, 7, 1, 60, 32),
-    ("rt256_cb", 44100.0, 256, 2.5, 7, 1, 100, 33),
-    ("rt1024_nocb", 44100.0, 1024, 2.5, 7, 0, 40, 34),
+    # name, fs, hop, beta, flags, copy_bord, n_hops, seed, sse, soft      (HPRRealtime<GPU>: causal)
+    ("rt1024_cb", 44100.0, 1024, 2.5, 7, 1, 40, 31, 0, 0),
+    ("rt512_cb", 44100.0, 512, 2.5, 7, 1, 60, 32, 0, 0),
+    ("rt256_cb", 44100.0, 256, 2.5, 7, 1, 100, 33, 0, 0),
+    ("rt1024_nocb", 44100.0, 1024, 2.5, 7, 0, 40, 34, 0, 0),
+    # the soft-mask and SSE variants (BASELINE.json configs[3] is hop 512 with both switches)
+    ("rt512_sse_soft", 44100.0, 512, 2.5, 3, 1, 60, 35, 1, 1),
+    ("rt1024_soft", 44100.0, 1024, 2.5, 7, 1, 40, 36, 0, 1),
+    ("rt1024_sse", 44100.0, 1024, 2.5, 3, 1, 40, 37, 1, 0),
 ]
+ONLY = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None
 
 
-def one_run(fs, hop, beta, flags, cb, audio, n_hops):
+def one_run(fs, hop, beta, flags, cb, audio, n_hops, sse=0, soft=0):
     h = rb.RefHPR(rb.GPU, fs, hop, beta, flags, rb.CAUSAL, cb)
+    if sse:
+        h.use_sse_filter()
+    if soft:
+        h.use_soft_mask()
     row = h.stft_width - h.lag
     outs = [np.zeros(n_hops * hop, np.float32) for _ in range(3)]
     masks = {"harmonic_mask": [], "percussive_mask": []}
@@ -47,16 +56,18 @@ def one_run(fs, hop, beta, flags, cb, audio, n_hops):
     return outs, {k: np.stack(v) for k, v in masks.items()}, geom
 
 
-for name, fs, hop, beta, flags, cb, n_hops, seed in CASES:
+for name, fs, hop, beta, flags, cb, n_hops, seed, sse, soft in CASES:
+    if ONLY and name not in ONLY:
+        continue
     audio = synth_audio(n_hops * hop, seed=seed, fs=int(fs))
-    a = one_run(fs, hop, beta, flags, cb, audio, n_hops)
-    b = one_run(fs, hop, beta, flags, cb, audio, n_hops)
+    a = one_run(fs, hop, beta, flags, cb, audio, n_hops, sse, soft)
+    b = one_run(fs, hop, beta, flags, cb, audio, n_hops, sse, soft)
     same = all(np.array_equal(x, y) for x, y in zip(a[0], b[0])) and all(np.array_equal(a[1][k], b[1][k]) for k in a[1])
     print(name, "deterministic", same, "peaks", [float(np.abs(o).max()) for o in a[0]], flush=True)
     if not same:
         continue
     np.savez_compressed(os.path.join(out_dir, "ref_norace_%s.npz" % name),
-                        params=np.array([fs, hop, beta, flags, cb, n_hops, seed], dtype=np.float64), geom=a[2],
+                        params=np.array([fs, hop, beta, flags, cb, n_hops, seed, sse, soft], dtype=np.float64), geom=a[2],
                         audio_sha=np.frombuffer(hashlib.sha256(audio.tobytes()).digest(), dtype=np.uint8),
                         harmonic=a[0][0], percussive=a[0][1], residual=a[0][2],
                         harmonic_mask_bits=a[1]["harmonic_mask"], percussive_mask_bits=a[1]["percussive_mask"])
