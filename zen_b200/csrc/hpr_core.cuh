@@ -238,6 +238,20 @@ __device__ __forceinline__ void hpr_masks(const HprDev& P, const float* prow, co
 	}
 }
 
+// |X[k]|: the reference takes thrust::abs of the complex bin (hps.cu:492-493), which is hypotf.  CUDA's hypotf rescales
+// its arguments to survive squares that leave the float range: about 25 instructions per bin, 8 % of everything the
+// batched kernel executes.  Where x^2 + y^2 stays well inside the normal range - every bin of real audio - the plain
+// formula with one fused product is within one ulp of the exact magnitude, like hypotf itself; a bin outside that
+// range (or exactly zero) takes hypotf.  Every kernel of the library takes its magnitudes here, so they stay
+// bit-identical to each other.
+__device__ __forceinline__ float zen_cabs(float x, float y)
+{
+	const float s = __fmaf_rn(x, x, __fmul_rn(y, y));
+	if (s > 1e-30f && s < 1e30f)
+		return __fsqrt_rn(s);
+	return hypotf(x, y);
+}
+
 // ---- hard-mask decisions without computing the median ------------------------
 // The hard masks only need to know on which side of a threshold the frequency
 // median P[k] lies:  Mp = [P/(H+eps) >= beta],  Mh = [H/(P+eps) >= beta-eps]
@@ -497,7 +511,7 @@ __device__ __forceinline__ void hpr_iteration(const HprDev& P, HprSmem<NFFT>& sm
 			else {
 				rfft_split_pair(sm.zbuf[k], sm.zbuf[M - k], ldt(&t_twr[k]), Xa, Xb);
 			}
-			float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
+			float ma = zen_cabs(Xa.x, Xa.y), mb = zen_cabs(Xb.x, Xb.y);
 			if (P.sse) {
 				ma = powf(ma, 2.0f);  // hps.h:91-98
 				mb = powf(mb, 2.0f);
@@ -789,20 +803,23 @@ struct FastSmem {
 	float2* za;            // ZN
 	float2* zb;            // ZN
 	float* erow;           // |X| of the consumed frame with mirrored borders: bin k is element midp + k, stored at
-	                       // fast_esw(midp + k) (16-byte chunks swizzled against bank conflicts); 16-byte aligned
+	                       // fast_esw(midp + k) (16-byte chunks swizzled against bank conflicts); 16-byte aligned.
+	                       // NOT storage of its own: between the split and the masked pack one of the two FFT buffers is
+	                       // free (the split works in place), and erow lives there (set per hop by hpr_fast_iteration)
 	unsigned short* codes; // entry k >> 3, bit k & 7: percussive decision of bin k; bit 8 + (k & 7): harmonic
 	// (a multiple of 32 floats: the swizzle permutes chunks within blocks of eight)
 	static __host__ __device__ size_t erow_floats(int Lp) { return (size_t)((M + 1 + Lp + 16 + 31) & ~31); }
 	static __host__ __device__ size_t bytes(int Lp)
 	{
-		return 2 * sizeof(float2) * (size_t)ZN + sizeof(float) * erow_floats(Lp) + sizeof(unsigned short) * (size_t)((M / 8 + 1 + 7) & ~7);
+		return 2 * sizeof(float2) * (size_t)ZN + sizeof(unsigned short) * (size_t)((M / 8 + 1 + 7) & ~7);
 	}
 	__device__ void carve(unsigned char* base, int Lp)
 	{
+		(void)Lp;
 		za = reinterpret_cast<float2*>(base);
 		zb = za + ZN;
-		erow = reinterpret_cast<float*>(zb + ZN);
-		codes = reinterpret_cast<unsigned short*>(erow + erow_floats(Lp));
+		erow = nullptr;
+		codes = reinterpret_cast<unsigned short*>(zb + ZN);
 	}
 };
 
@@ -822,7 +839,12 @@ struct FastState {
 
 __host__ __device__ inline bool hpr_fast_supported(const HprDev& P)
 {
-	return P.decide && !P.sse && !P.soft && P.copy_bord && P.lag == 1 && P.Lp >= 9 && (P.n_taps == 1 || P.n_taps == 3 || P.n_taps == 5 || P.n_taps == 7);
+	// (the magnitude row borrows one FFT buffer of fpad_size(M) float2: it must fit, which it does from nfft 512 on
+	// whatever the window, and for the shorter transforms unless the window is nearly as long as the row)
+	const int M = 2 * P.hop;
+	const long buf_bytes = 8L * ((M + M / 8 + 2) & ~1), erow_bytes = 4L * ((M + 1 + P.Lp + 16 + 31) & ~31);
+	return P.decide && !P.sse && !P.soft && P.copy_bord && P.lag == 1 && P.Lp >= 9 && (P.n_taps == 1 || P.n_taps == 3 || P.n_taps == 5 || P.n_taps == 7)
+	       && erow_bytes <= buf_bytes;
 }
 
 // peak of |emitted sample| per output, kept by each thread across the hops of a tile (optional)
@@ -1059,10 +1081,12 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 	constexpr int HC = M / 4;     // complex (packed even/odd) samples per hop
 	const int tid = threadIdx.x;
 	const int midp = P.midp;
-	// the two FFT buffers swap roles every hop: the last inverse stage of hop i still reads the buffer the first
-	// forward stage of hop i wrote, so hop i + 1 starts in the other one and no barrier is needed in between
-	float2* const a = (i & 1) ? sm.zb : sm.za;
-	float2* const b = (i & 1) ? sm.za : sm.zb;
+	// The two FFT buffers keep their roles: the forward transform ends in `zres`, the split turns it into X IN PLACE,
+	// the other buffer (`zoth`) holds the magnitude row while the masks are decided and then receives the masked
+	// spectrum; the inverse stages ping-pong from there, so the last one (the overlap-add) reads `zres` - the buffer the
+	// first forward stage of the next hop does NOT write.  No barrier is needed between two hops.
+	float2* const a = sm.za;
+	float2* const b = sm.zb;
 
 	if (next_hop != nullptr && tid < (HC * 8) / 128)
 		asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(next_hop) + tid * 128));
@@ -1089,17 +1113,18 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 	float2* const zres = fft_pp_fused<M, NT, -1, true, false, false, false>(a, b, P.tw, tid, load_frame, NoFn{});
 	float2* const zoth = zres == a ? b : a;
 
-	// ---- C. split into the real-input spectrum X[0..M] (into zoth, natural order), magnitudes into the ring and
-	// into erow (hps.cu:469-472, 492-493)
+	// ---- C. split into the real-input spectrum X[0..M] (in place in zres, natural order: a thread owns its pair
+	// (k, M - k)), magnitudes into the ring and into erow, which borrows zoth (hps.cu:469-472, 492-493)
+	sm.erow = reinterpret_cast<float*>(zoth);
 	{
 		float* mag_row = st.mag_ring + (size_t)slot * st.ring_stride;
 		float* const E = sm.erow;
 		auto put = [&](int k, int kb, float2 Xa, float2 Xb) {
-			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
+			const float ma = zen_cabs(Xa.x, Xa.y), mb = zen_cabs(Xb.x, Xb.y);
 			mag_row[k] = ma;
 			mag_row[kb] = mb;
-			zoth[k] = Xa;
-			zoth[kb] = Xb;
+			zres[k] = Xa;
+			zres[kb] = Xb;
 			E[fast_esw(midp + k)] = ma;
 			E[fast_esw(midp + kb)] = mb;
 			// mirrored borders: |X[-t]| = |X[t]|, |X[M+t]| = |X[M-t]|
@@ -1186,11 +1211,12 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 		const int o = oi == 0 ? 1 : (oi == 1 ? 0 : 2);
 		if (!(P.out_flags & (1 << o)))
 			continue;
-		// masked spectrum packed for the M-point inverse transform, into zres (X stays in zoth)
+		// masked spectrum packed for the M-point inverse transform, into zoth (the magnitude row is no longer needed;
+		// X stays in zres)
 		switch (o) {
-		case 1: fast_pack<NFFT, NT, 1>(P, sm.codes, zoth, zres); break;
-		case 0: fast_pack<NFFT, NT, 0>(P, sm.codes, zoth, zres); break;
-		default: fast_pack<NFFT, NT, 2>(P, sm.codes, zoth, zres); break;
+		case 1: fast_pack<NFFT, NT, 1>(P, sm.codes, zres, zoth); break;
+		case 0: fast_pack<NFFT, NT, 0>(P, sm.codes, zres, zoth); break;
+		default: fast_pack<NFFT, NT, 2>(P, sm.codes, zres, zoth); break;
 		}
 		__syncthreads();
 		// inverse FFT (hps.cu:522) whose last stage IS the overlap-add (hps.h:68-80): the thread that holds sample
@@ -1216,11 +1242,11 @@ __device__ __forceinline__ void hpr_fast_iteration(const HprDev& P, FastSmem<NFF
 		};
 		if (o == last_o) {
 			// nobody needs X any more: ping-pong through its buffer, one barrier per stage, none at the end
-			fft_pp_rest<M, NT, +1, 1, false, true, false, true, LAY_N>(zres, zoth, P.tw, tid, ola);
+			fft_pp_rest<M, NT, +1, 1, false, true, false, true, LAY_N>(zoth, zres, P.tw, tid, ola);
 		}
 		else {
-			fft_inplace_last<M, NT, +1, 1, true, false>(zres, P.tw, tid, ola);
-			__syncthreads();  // the next output packs into zres
+			fft_inplace_last<M, NT, +1, 1, true, false>(zoth, P.tw, tid, ola);
+			__syncthreads();  // the next output packs into zoth
 		}
 		if (PEAKS) {
 			if (o == 0) peaks.v[0] = fmaxf(peaks.v[0], pk_local);
@@ -1325,7 +1351,7 @@ __device__ __forceinline__ void hpr_split_analyse(const HprDev& P, HprSmem<NFFT>
 			else {
 				rfft_split_pair(sm.zbuf[k], sm.zbuf[M - k], tb.twr[k], Xa, Xb);
 			}
-			const float ma = hypotf(Xa.x, Xa.y), mb = hypotf(Xb.x, Xb.y);
+			const float ma = zen_cabs(Xa.x, Xa.y), mb = zen_cabs(Xb.x, Xb.y);
 			mag_row[ka] = ma;
 			sm.xbuf[ka] = Xa;
 			sm.erow[eoff + ka] = ma;

@@ -1467,6 +1467,17 @@ int choose_tile_hops(const Plan& pl, int n_streams, long n_hops, int resident)
 	long min_tile = 4L * pl.dev.W;  // the halo (analysis only, roughly a third of a full hop) stays below ~10 % of the tile's work
 	if (min_tile < 16) min_tile = 16;
 	if (tile < min_tile) tile = min_tile;
+	// Items are queued tile-major (all first tiles, then all second tiles, ...), so the LAST tiles of the streams are what
+	// the CTAs work on when the queue runs dry.  With enough streams to give every resident CTA one of them, the regular
+	// tiles are stretched a little so that the last one is an eighth of their length: the CTAs then finish within an
+	// eighth of an item of each other instead of a whole one.
+	if (n_streams >= resident && tile < n_hops && !std::getenv("ZEN_B200_NO_STRETCH")) {
+		const long k = (n_hops + tile - 1) / tile - 1;  // regular tiles per stream
+		if (k >= 1) {
+			long stretched = (8 * n_hops + 8 * k) / (8 * k + 1);  // k tiles + one eighth cover n_hops
+			if (stretched * k < n_hops && stretched > tile / 2) tile = stretched;
+		}
+	}
 	if (tile > n_hops) tile = n_hops;
 	if (tile < 1) tile = 1;
 	return (int)tile;

@@ -1,6 +1,7 @@
 // Kernels of the fused HPR step and their launchers, instantiated once per FFT
 // size in hpr_inst_<NFFT>.cu so the sizes compile in parallel.
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 
 #include <cooperative_groups.h>
@@ -23,6 +24,17 @@ constexpr int min_blocks_for()
 {
 	// 512-thread CTAs: two fit at nfft 8192 (101 KB of shared memory each), one at 16384 (200 KB)
 	return NT >= 512 ? (NFFT == 8192 ? 2 : 1) : ZEN_TILE_THREADS_PER_SM / NT;
+}
+
+// the fast kernel keeps 37 KB of shared memory per CTA at nfft 4096 (the magnitude row borrows an FFT buffer), so a
+// fifth CTA fits an SM if the registers allow it (ZEN_FAST_BLOCKS: 4 = 64 registers, 5 = 48)
+#ifndef ZEN_FAST_BLOCKS
+#define ZEN_FAST_BLOCKS 5
+#endif
+template <int NT, int NFFT>
+constexpr int min_blocks_fast()
+{
+	return (NFFT == 4096 && NT == 256) ? ZEN_FAST_BLOCKS : min_blocks_for<NT, NFFT>();
 }
 
 struct TileArgs {
@@ -169,7 +181,9 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_kerne
 		const int item = s_item;
 		if (item >= total_items)
 			break;
-		const int stream = item / n_tiles, tile = item - stream * n_tiles;
+		// n_tiles > 0: tile-major order (the short last tiles of the streams close the queue); < 0: stream-major
+		const int nt_ = n_tiles < 0 ? -n_tiles : n_tiles, n_str = total_items / nt_;
+		const int tile = n_tiles < 0 ? item % nt_ : item / n_str, stream = n_tiles < 0 ? item / nt_ : item - tile * n_str;
 		const float* sin = in + (size_t)stream * in_stride;
 		const long e0 = (long)tile * tile_hops;
 		const long e1 = min(n_hops, e0 + (long)tile_hops);
@@ -200,7 +214,7 @@ constexpr int fast_ring_stride()
 	return NFFT / 2 + 4;
 }
 template <int NFFT, int NT, bool PEAKS>
-__global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_fast_kernel(const __grid_constant__ HprDev P,
+__global__ void __launch_bounds__(NT, min_blocks_fast<NT, NFFT>()) hpr_tile_fast_kernel(const __grid_constant__ HprDev P,
                                                                                  const float* __restrict__ in, long in_stride,
                                                                                  float* out_h, float* out_p, float* out_r, long out_stride,
                                                                                  long n_hops, int tile_hops, int n_tiles, int total_items,
@@ -229,7 +243,9 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_fast_
 		const int item = s_item;
 		if (item >= total_items)
 			break;
-		const int stream = item / n_tiles, tile = item - stream * n_tiles;
+		// n_tiles > 0: tile-major order (the short last tiles of the streams close the queue); < 0: stream-major
+		const int nt_ = n_tiles < 0 ? -n_tiles : n_tiles, n_str = total_items / nt_;
+		const int tile = n_tiles < 0 ? item % nt_ : item / n_str, stream = n_tiles < 0 ? item / nt_ : item - tile * n_str;
 		const float* sin = in + (size_t)stream * in_stride;
 		const long e0 = (long)tile * tile_hops;
 		const long e1 = min(n_hops, e0 + (long)tile_hops);
@@ -771,6 +787,7 @@ int launch_tile_impl(const TileArgs& a)
 	constexpr int NT = nt_for<NFFT>();
 	const int n_tiles = (int)((a.n_hops + a.tile_hops - 1) / a.tile_hops);
 	const long total = (long)n_tiles * a.n_streams;
+	static const int order = std::getenv("ZEN_B200_STREAM_MAJOR") ? -1 : 1;  // A/B switch of the queue order
 	if (total > 0x7fffffffL)
 		return ZEN_ERR_UNSUPPORTED;
 	ZEN_CUDA_CHECK(cudaMemsetAsync(a.work_counter, 0, sizeof(int), a.stream));
@@ -782,7 +799,7 @@ int launch_tile_impl(const TileArgs& a)
 			ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 			ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 			kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
-			                                   n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta, a.peaks[0], a.peaks[1],
+			                                   order * n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta, a.peaks[0], a.peaks[1],
 			                                   a.peaks[2]);
 			ZEN_CUDA_CHECK(cudaGetLastError());
 			return ZEN_OK;
@@ -796,7 +813,7 @@ int launch_tile_impl(const TileArgs& a)
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
-	                                   n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta);
+	                                   order * n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta);
 	ZEN_CUDA_CHECK(cudaGetLastError());
 	return ZEN_OK;
 }
