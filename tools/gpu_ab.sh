@@ -1,11 +1,13 @@
 #!/bin/bash
-# A/B on one box: queue order / stretched tiles of the batched kernel
+# A/B on one box: long first tiles when a GPU holds fewer streams than resident CTAs (the 8-GPU shard: 512 streams)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-run() { python bench.py --steps 5 --warmup 3 --no-e2e-f32 --no-cpu --no-parity --no-latency 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', round(d['value']), d['ms_per_step'])"; }
-run tile_major_stretch
-ZEN_B200_NO_STRETCH=1 run tile_major_plain
-ZEN_B200_STREAM_MAJOR=1 ZEN_B200_NO_STRETCH=1 run stream_major_plain
-ZEN_B200_STREAM_MAJOR=1 run stream_major_stretch
-run tile_major_stretch_again
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_batch_host.py -q -m gpu -k "fast_tile or batch or tile" 2>&1 | tail -2
+run() { python bench.py --streams $2 --scaling weak --steps 5 --warmup 3 --no-e2e-f32 --no-cpu --no-parity --no-latency 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', $2, round(d['value']), d['ms_per_step'])"; }
+run two_sizes 512
+ZEN_B200_NO_STRETCH=1 run one_size 512
+run two_sizes 1024
+ZEN_B200_NO_STRETCH=1 run one_size 1024
+run two_sizes 512
+run full 4096

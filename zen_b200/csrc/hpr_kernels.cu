@@ -224,6 +224,17 @@ int dispatch_tile(const Plan& pl, const float* in, long in_stride, float* oh, fl
 	TileArgs a{pl.dev, in, in_stride, oh, op, orr, out_stride, n_streams, n_hops, tile_hops, scratch, tile_scratch_floats(pl),
 	           work_counter, resident, s};
 	a.force_general = std::getenv("ZEN_B200_NO_FAST") ? 1 : 0;  // debugging aid / A-B test: the general kernel everywhere
+	// Fewer streams than resident CTAs (e.g. a 4096-stream job sharded over eight GPUs): choose_tile_hops cuts the streams
+	// into many short tiles so that the queue balances, and every tile re-analyses W hops in front of it.  Only the END of
+	// the queue needs short items: the first tiles of every stream are four times as long, the last ones - about four per
+	// CTA, queued last (tile-major order) - keep the short length.
+	if (resident > 0 && n_streams < resident && tile_hops < n_hops && !std::getenv("ZEN_B200_NO_STRETCH")) {
+		const long n_small = (4L * resident + n_streams - 1) / n_streams;
+		const long hops_small = std::min<long>(n_hops, n_small * tile_hops);
+		const long big = 4L * tile_hops;
+		a.big_hops = (int)big;
+		a.n_big = (int)((n_hops - hops_small) / big);
+	}
 	if (peaks)
 		for (int o = 0; o < 3; ++o)
 			a.peaks[o] = reinterpret_cast<unsigned*>(peaks[o]);

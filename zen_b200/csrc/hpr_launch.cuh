@@ -45,7 +45,7 @@ struct TileArgs {
 	long out_stride;
 	int n_streams;
 	long n_hops;
-	int tile_hops;
+	int tile_hops;           // tile length (of the closing tiles when the first ones are longer: big_hops / n_big below)
 	float* scratch;          // resident_ctas * scratch_per_cta floats
 	size_t scratch_per_cta;
 	int* work_counter;       // device int, zeroed by the launcher
@@ -53,6 +53,8 @@ struct TileArgs {
 	cudaStream_t stream;
 	unsigned* peaks[3] = {nullptr, nullptr, nullptr};  // optional per-stream max |out| (fast path only), zeroed by the caller
 	int force_general = 0;   // debugging / A-B: run hpr_iteration even where the fast path applies
+	int big_hops = 0;        // length of the first n_big tiles of every stream (n_big == 0: all tiles are tile_hops long)
+	int n_big = 0;
 };
 
 struct HopArgs {
@@ -152,7 +154,7 @@ template <int NFFT, int NT>
 __global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_kernel(const __grid_constant__ HprDev P,
                                                                             const float* __restrict__ in, long in_stride,
                                                                             float* out_h, float* out_p, float* out_r, long out_stride,
-                                                                            long n_hops, int tile_hops, int n_tiles, int total_items,
+                                                                            long n_hops, int tile_hops, int big_hops, int n_big, int n_tiles, int total_items,
                                                                             int* work_counter, float* scratch, size_t scratch_per_cta)
 {
 	constexpr int M = NFFT / 2, HOP = M / 2;
@@ -185,8 +187,9 @@ __global__ void __launch_bounds__(NT, min_blocks_for<NT, NFFT>()) hpr_tile_kerne
 		const int nt_ = n_tiles < 0 ? -n_tiles : n_tiles, n_str = total_items / nt_;
 		const int tile = n_tiles < 0 ? item % nt_ : item / n_str, stream = n_tiles < 0 ? item / nt_ : item - tile * n_str;
 		const float* sin = in + (size_t)stream * in_stride;
-		const long e0 = (long)tile * tile_hops;
-		const long e1 = min(n_hops, e0 + (long)tile_hops);
+		// the first n_big tiles of a stream are big_hops long, the rest (the closing ones) tile_hops
+		const long e0 = tile < n_big ? (long)tile * big_hops : (long)n_big * big_hops + (long)(tile - n_big) * tile_hops;
+		const long e1 = tile < n_big ? e0 + big_hops : min(n_hops, e0 + (long)tile_hops);
 		const long i_begin = max(0L, e0 - P.W);
 		const long i_full = max(0L, e0 - 1);
 		for (long i = i_begin; i < e1; ++i) {
@@ -217,7 +220,7 @@ template <int NFFT, int NT, bool PEAKS>
 __global__ void __launch_bounds__(NT, min_blocks_fast<NT, NFFT>()) hpr_tile_fast_kernel(const __grid_constant__ HprDev P,
                                                                                  const float* __restrict__ in, long in_stride,
                                                                                  float* out_h, float* out_p, float* out_r, long out_stride,
-                                                                                 long n_hops, int tile_hops, int n_tiles, int total_items,
+                                                                                 long n_hops, int tile_hops, int big_hops, int n_big, int n_tiles, int total_items,
                                                                                  int* work_counter, float* scratch, size_t scratch_per_cta,
                                                                                  unsigned* peaks_h, unsigned* peaks_p, unsigned* peaks_r)
 {
@@ -247,8 +250,9 @@ __global__ void __launch_bounds__(NT, min_blocks_fast<NT, NFFT>()) hpr_tile_fast
 		const int nt_ = n_tiles < 0 ? -n_tiles : n_tiles, n_str = total_items / nt_;
 		const int tile = n_tiles < 0 ? item % nt_ : item / n_str, stream = n_tiles < 0 ? item / nt_ : item - tile * n_str;
 		const float* sin = in + (size_t)stream * in_stride;
-		const long e0 = (long)tile * tile_hops;
-		const long e1 = min(n_hops, e0 + (long)tile_hops);
+		// the first n_big tiles of a stream are big_hops long, the rest (the closing ones) tile_hops
+		const long e0 = tile < n_big ? (long)tile * big_hops : (long)n_big * big_hops + (long)(tile - n_big) * tile_hops;
+		const long e1 = tile < n_big ? e0 + big_hops : min(n_hops, e0 + (long)tile_hops);
 		const long i_begin = max(0L, e0 - P.W);
 		const long i_full = max(0L, e0 - 1);
 		int slot = (int)(i_begin % P.W);
@@ -785,7 +789,8 @@ template <int NFFT>
 int launch_tile_impl(const TileArgs& a)
 {
 	constexpr int NT = nt_for<NFFT>();
-	const int n_tiles = (int)((a.n_hops + a.tile_hops - 1) / a.tile_hops);
+	const long hops_big = (long)a.n_big * a.big_hops;
+	const int n_tiles = a.n_big + (int)((a.n_hops - hops_big + a.tile_hops - 1) / a.tile_hops);
 	const long total = (long)n_tiles * a.n_streams;
 	static const int order = std::getenv("ZEN_B200_STREAM_MAJOR") ? -1 : 1;  // A/B switch of the queue order
 	if (total > 0x7fffffffL)
@@ -798,7 +803,7 @@ int launch_tile_impl(const TileArgs& a)
 		auto launch = [&](auto kern) -> int {
 			ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 			ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-			kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
+			kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops, a.big_hops, a.n_big,
 			                                   order * n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta, a.peaks[0], a.peaks[1],
 			                                   a.peaks[2]);
 			ZEN_CUDA_CHECK(cudaGetLastError());
@@ -812,7 +817,7 @@ int launch_tile_impl(const TileArgs& a)
 	size_t smem = HprSmem<NFFT>::bytes(a.dev.Lp);
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	ZEN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops,
+	kern<<<grid, NT, smem, a.stream>>>(a.dev, a.in, a.in_stride, a.out_h, a.out_p, a.out_r, a.out_stride, a.n_hops, a.tile_hops, a.big_hops, a.n_big,
 	                                   order * n_tiles, (int)total, a.work_counter, a.scratch, a.scratch_per_cta);
 	ZEN_CUDA_CHECK(cudaGetLastError());
 	return ZEN_OK;
