@@ -26,15 +26,16 @@ constexpr int min_blocks_for()
 	return NT >= 512 ? (NFFT == 8192 ? 2 : 1) : ZEN_TILE_THREADS_PER_SM / NT;
 }
 
-// the fast kernel keeps 37 KB of shared memory per CTA at nfft 4096 (the magnitude row borrows an FFT buffer), so a
-// fifth CTA fits an SM if the registers allow it (ZEN_FAST_BLOCKS: 4 = 64 registers, 5 = 48)
-#ifndef ZEN_FAST_BLOCKS
-#define ZEN_FAST_BLOCKS 5
+// The fast kernel keeps 37 KB of shared memory per CTA at nfft 4096 (the magnitude row borrows an FFT buffer), and
+// proportionally less for the shorter transforms, so a fifth "quarter SM" of threads fits if the registers allow it:
+// ZEN_FAST_THREADS_PER_SM 1280 = 48 registers per thread (1024 = 64; 1536 = 40 spills and is slower, measured at nfft 4096).
+#ifndef ZEN_FAST_THREADS_PER_SM
+#define ZEN_FAST_THREADS_PER_SM 1280
 #endif
 template <int NT, int NFFT>
 constexpr int min_blocks_fast()
 {
-	return (NFFT == 4096 && NT == 256) ? ZEN_FAST_BLOCKS : min_blocks_for<NT, NFFT>();
+	return NT <= 256 ? ZEN_FAST_THREADS_PER_SM / NT : min_blocks_for<NT, NFFT>();
 }
 
 struct TileArgs {
