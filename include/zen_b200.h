@@ -273,6 +273,19 @@ int zen_mpm_pitch(int n, float sample_rate, const float* d_audio, long stride, i
  * d_odf (odf_stride >= n_hops) receives one sample per hop - what BTrack::processOnsetDetectionFunctionSample consumes. */
 int zen_onset_csd(const float* d_audio, long stride, int n_streams, long n_hops, float* d_odf, long odf_stride, void* cuda_stream);
 
+/* ---- the beat tracker behind that onset detection function: BTrack::processOnsetDetectionFunctionSample and what it
+ * calls, demos/beat-tracking/BTrack.cpp:100-397 (cumulative score, beat prediction, tempo update once per beat).  Host
+ * code, as in the reference: it consumes one float per 256-sample hop, e.g. a row of zen_onset_csd copied to the host.
+ * zen_btrack_process feeds n consecutive samples; per sample it reports (each array optional) whether a beat is due in
+ * that hop (beatDueInFrame), the tempo estimate in BPM (estimatedTempo) and the cumulative score
+ * (latestCumulativeScoreValue).  The object keeps its state between calls (a stream can be fed in pieces). */
+typedef struct zen_btrack zen_btrack;
+int zen_btrack_create(zen_btrack** out, int sample_rate);
+void zen_btrack_destroy(zen_btrack* b);
+int zen_btrack_process(zen_btrack* b, const float* h_odf, long n, unsigned char* h_beat, float* h_tempo, float* h_cumscore);
+/* its two lookup tables (BTrackPrecomputed.h, recomputed from their formulas): 128 and 41 x 41 floats */
+int zen_btrack_tables(const zen_btrack* b, float* h_rayleigh128, float* h_transition41x41);
+
 #ifdef __cplusplus
 }
 #endif

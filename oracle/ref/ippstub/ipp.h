@@ -275,4 +275,22 @@ static inline IppStatus ippsFFTFwd_CToC_32f(const Ipp32f* srcRe, const Ipp32f* s
 	return ippStsNoErr;
 }
 
+/* in-place inverse of the split-array variant (demos/beat-tracking/BTrack.cpp:289-290) */
+static inline IppStatus ippsFFTInv_CToC_32f_I(Ipp32f* re, Ipp32f* im, const IppsFFTSpec_C_32f* s, Ipp8u* buf)
+{
+	const int n = s->n;
+	Ipp32fc* x = (Ipp32fc*)(((size_t)buf + 15) & ~(size_t)15);
+	Ipp8u* rest = (Ipp8u*)(x + n);
+	for (int i = 0; i < n; ++i) {
+		x[i].re = re[i];
+		x[i].im = im[i];
+	}
+	ipp_standin_fft(x, s, rest, +1);
+	for (int i = 0; i < n; ++i) {
+		re[i] = x[i].re;
+		im[i] = x[i].im;
+	}
+	return ippStsNoErr;
+}
+
 #endif /* ZEN_ORACLE_IPP_STANDIN_H */

@@ -45,7 +45,7 @@ EXPORTS = [
     "zen_offline_process_device", "zen_copy_to_host", "zen_copy_to_device", "zen_fakert_run", "zen_host_alloc", "zen_host_free", "zen_hpr_bind_state", "zen_hpr_realtime_begin", "zen_hpr_realtime_end", "zen_hpr_realtime_stamps",
     "zen_rt_pack_groups", "zen_rt_unpack_groups", "zen_pcm16_decode_mono", "zen_pcm16_encode_normalized",
     "zen_rt_split_ranges", "zen_pcm16_decode_mono_async", "zen_pcm16_peaks_async", "zen_pcm16_encode_with_peaks_async",
-    "zen_pcm16_encode_normalized_async", "zen_hpr_batch_process_host_pcm16", "zen_hpr_wait_input_consumed", "zen_hpr_realtime_stamps_rank1", "zen_mpm_pitch", "zen_onset_csd",
+    "zen_pcm16_encode_normalized_async", "zen_hpr_batch_process_host_pcm16", "zen_hpr_wait_input_consumed", "zen_hpr_realtime_stamps_rank1", "zen_mpm_pitch", "zen_onset_csd", "zen_btrack_create", "zen_btrack_destroy", "zen_btrack_process", "zen_btrack_tables",
 ]
 
 _lib = None
@@ -75,6 +75,11 @@ def lib():
     L.zen_hpr_batch_process_host_pcm16.argtypes = [vp, vp, cl, ci, cl, vp, vp, vp, cl, vp, vp, vp]
     L.zen_mpm_pitch.argtypes = [ci, cf, vp, cl, ci, vp, vp, vp]
     L.zen_onset_csd.argtypes = [vp, cl, ci, cl, vp, cl, vp]
+    L.zen_btrack_create.argtypes = [ctypes.POINTER(vp), ci]
+    L.zen_btrack_destroy.argtypes = [vp]
+    L.zen_btrack_destroy.restype = None
+    L.zen_btrack_process.argtypes = [vp, vp, cl, vp, vp, vp]
+    L.zen_btrack_tables.argtypes = [vp, vp, vp]
     L.zen_median_filter.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp]
     L.zen_box_filter.argtypes = [ci, ci, ci, ci, vp, vp, vp]
     L.zen_fft_c2c.argtypes = [ci, vp, ci, vp]

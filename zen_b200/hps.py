@@ -494,3 +494,44 @@ class OnsetDetectionFunction:
             check(_lib.lib().zen_onset_csd(x2.data_ptr(), stride, n_streams, n_hops, out.data_ptr(), max(1, out.stride(0)),
                                            torch.cuda.current_stream().cuda_stream), "zen_onset_csd")
         return out[0] if one else out
+
+
+class BTrack:
+    """The beat tracker of the reference's beat-tracking demo (demos/beat-tracking/BTrack.cpp) behind
+    OnsetDetectionFunction: host-side control logic that consumes one onset-detection sample per 256-sample hop.
+    process_odf(samples) -> (beat_due [n] bool, tempo_bpm [n], cumulative_score [n]); process_percussive(x) runs the
+    onset detection function on the device first (x: float32 CUDA tensor, one stream, 256 n_hops samples)."""
+
+    def __init__(self, sample_rate):
+        self._h = ctypes.c_void_p()
+        check(_lib.lib().zen_btrack_create(ctypes.byref(self._h), int(sample_rate)), "zen_btrack_create")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().zen_btrack_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def process_odf(self, samples):
+        s = np.ascontiguousarray(samples, dtype=np.float32)
+        n = s.size
+        beat = np.zeros(n, np.uint8)
+        tempo = np.zeros(n, np.float32)
+        score = np.zeros(n, np.float32)
+        check(_lib.lib().zen_btrack_process(self._h, s.ctypes.data, n, beat.ctypes.data, tempo.ctypes.data, score.ctypes.data), "zen_btrack_process")
+        return beat.astype(bool), tempo, score
+
+    def process_percussive(self, x):
+        odf = OnsetDetectionFunction().calculate_samples(x.reshape(-1))
+        return self.process_odf(odf.cpu().numpy())
+
+    def tables(self):
+        r = np.zeros(128, np.float32)
+        t = np.zeros((41, 41), np.float32)
+        check(_lib.lib().zen_btrack_tables(self._h, r.ctypes.data, t.ctypes.data), "zen_btrack_tables")
+        return r, t
